@@ -1,0 +1,178 @@
+/*
+ * trw_b200.h -- C ABI of libtrw_b200.so: the B200 (sm_100a) random-walk sampler and window
+ * generator behind torch_rw's `torch_rw_native` module.
+ *
+ * Drop-in boundary.  Each entry point below replaces one function of the reference's pybind11
+ * module (/root/reference/csrc/rw_init.cpp:133-141); the reference interface it stands in for
+ * is cited on each declaration.  Signatures carry plain pointers and sizes only: device
+ * pointers to contiguous row-major int64 arrays, a CUDA device ordinal and a cudaStream_t
+ * passed as void*.  Nothing here allocates device memory, synchronises the stream or touches
+ * host copies of the data (the *_host entry point excepted, which says so): the binding
+ * (torch_random_walk_b200/native.py, or the cgo/JNI/ctypes stub of INTEGRATION.md) owns
+ * allocation, exactly as the reference's launchers call torch::empty before their kernels.
+ *
+ * Every function returns TRW_OK (0) or a negative status; trw_last_error() then holds a
+ * message for the calling thread.  There is no CPU fallback: without a usable sm_100 device
+ * every launch returns TRW_ERR_DEVICE.
+ *
+ * Randomness: counter-based Philox4x32-10 keyed by (seed, entry-point tag) and indexed by
+ * (global walk id, step, trial) or (output element).  Output therefore depends only on the
+ * arguments -- not on grid shape, stream, rerun, or on how walks are sharded over GPUs, as
+ * long as each shard passes its global `walk_id_offset`.
+ */
+#ifndef TRW_B200_H
+#define TRW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRW_ABI_VERSION 1
+
+enum {
+    TRW_OK = 0,
+    TRW_ERR_ARG = -1,     /* bad argument (null pointer, negative size, ...)        */
+    TRW_ERR_DEVICE = -2,  /* no CUDA device / not an sm_100 part / cudaSetDevice     */
+    TRW_ERR_CUDA = -3,    /* a CUDA runtime call or kernel launch failed             */
+    TRW_ERR_WORKSPACE = -4 /* workspace pointer missing or too small                 */
+};
+
+/* ABI version of the loaded library (== TRW_ABI_VERSION it was built with). */
+int trw_abi_version(void);
+
+/* Message describing the last non-zero status returned to this thread ("" if none). */
+const char* trw_last_error(void);
+
+/* Number of kernels this library has launched since load / since the last reset
+ * (bench.py's `gpu_launches`). */
+int64_t trw_launch_count(void);
+void trw_reset_launch_count(void);
+
+/* TRW_OK when `device` is a compute-capability-10.x GPU the kernels can run on. */
+int trw_device_check(int device);
+
+/* ---------------------------------------------------------------------------------------
+ * CSR walks.   Replaces walk() -> walk_gpu(): csrc/rw_init.cpp:11-25,
+ * csrc/cuda/rw_cuda.cu:186-248 (kernels :59-98 uniform, :100-184 node2vec).
+ *
+ *   row_ptr[n_nodes+1], col_idx[nnz], targets[n_walks]  -> out[n_walks, walk_length+1]
+ *   out_row_stride: elements between consecutive rows of `out` (>= walk_length+1).
+ *   p == 1.0 && q == 1.0 selects the first-order kernel, as rw_cuda.cu:226 does.
+ *   walk_id_offset: global index of this call's first walk (0 for an unsharded call).
+ *   A node without out-edges keeps the walk on that node (rw_cuda.cu:25-30).
+ *
+ * The node2vec path tests "x in adj(t)" against a per-call hashed copy of the adjacency that
+ * it builds in `workspace` (trw_walk_csr_workspace_bytes bytes, 256-byte aligned device
+ * memory, contents undefined before and after).  With workspace == NULL it falls back to the
+ * reference's linear scan of adj(t).
+ * ------------------------------------------------------------------------------------- */
+size_t trw_walk_csr_workspace_bytes(int64_t n_nodes, int64_t nnz, double p, double q);
+
+int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                 const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
+                 double p, double q, int walk_length, int64_t seed,
+                 int64_t* out, int64_t out_row_stride,
+                 void* workspace, size_t workspace_bytes,
+                 int device, void* stream);
+
+/* Same computation with every buffer in HOST memory (pinned or pageable): stages the graph and
+ * the start nodes to the device, walks in chunks and streams finished chunks back while the
+ * next ones run.  Allocates and frees its own device memory and returns after `out` is
+ * complete.  This is the end-to-end path a caller holding CPU tensors uses. */
+int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                      const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
+                      double p, double q, int walk_length, int64_t seed,
+                      int64_t* out, int device);
+
+/* ---------------------------------------------------------------------------------------
+ * Edge-list walks.   Replaces walk_edge_list() -> walk_edge_list_gpu():
+ * csrc/rw_init.cpp:27-45, csrc/cuda/rw_cuda_edge_list.cu:243-308 (kernels :42-96, :126-240).
+ *
+ *   edge_list[n_edges,2] sorted by head, node_edge_index[n_index_rows,2] = inclusive
+ *   [first,last] edge row per node or [-1,-1]  ->  out[n_walks, walk_length+1].
+ *   Dead end -> padding_idx, then the start node (restart != 0) or padding for ever.
+ *   The second-order path keeps the reference's acceptance rule verbatim (half-open
+ *   neighbour scan, fall-through after a rejected return).
+ * ------------------------------------------------------------------------------------- */
+int trw_walk_edge_list(const int64_t* edge_list, int64_t n_edges,
+                       const int64_t* node_edge_index, int64_t n_index_rows,
+                       const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
+                       double p, double q, int walk_length, int64_t seed,
+                       int64_t padding_idx, int restart,
+                       int64_t* out, int64_t out_row_stride, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Knowledge-graph triple walks.   Replaces walk_triples() -> triples::walk_triples_gpu():
+ * csrc/rw_init.cpp:47-75, csrc/cuda/rw_cuda_triples.cu:103-169 (kernel :49-96).
+ *
+ *   triples[n_triples,3] sorted by head, relation_tail_index[n_index_rows,2]
+ *   -> out[n_walks, 2*walk_length+1] = head, rel, tail, rel, tail, ...
+ *   `restart` is accepted and ignored, as in the reference.  Unlike the reference's CUDA
+ *   launcher (which discards a non-zero seed, rw_cuda_triples.cu:143-148) the seed is honoured.
+ * ------------------------------------------------------------------------------------- */
+int trw_walk_triples(const int64_t* triples, int64_t n_triples,
+                     const int64_t* relation_tail_index, int64_t n_index_rows,
+                     const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
+                     int walk_length, int64_t padding_idx, int restart, int64_t seed,
+                     int64_t* out, int64_t out_row_stride, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Window generation (one gather kernel per call).  walks[n_walks, walk_cols] contiguous.
+ * Positives/targets are bit-exact with the reference; negatives are Philox draws with the
+ * reference's support (uniform node id / uniform row of `triples`).
+ *
+ * trw_windows            replaces to_windows()      csrc/rw_init.cpp:77-88,
+ *                                                   csrc/cuda/windows_cuda.cu:67-119 (:7-65)
+ *   -> target[K], pos[K,W-1], neg[K,W-1],  K = n_walks*(walk_cols-W+1)
+ * trw_windows_cbow       replaces to_windows_cbow() csrc/rw_init.cpp:90-101,
+ *                                                   csrc/cuda/windows_cuda.cu:187-239 (:122-185)
+ *   -> pos_nodes[K], neg_nodes[K] (!= pos_nodes[k], up to 101 redraws), windows[K,W-1]
+ * trw_windows_triples    replaces to_windows_triples()  csrc/rw_init.cpp:103-116,
+ *                                                   csrc/cuda/windows_cuda.cu:375-435 (:241-373)
+ *   -> target[K,3], pos[K,2W,3], neg[K,2W,3],  K = n_walks*((walk_cols-1)/2)
+ * trw_windows_triples_cbow replaces to_windows_triples_cbow() csrc/rw_init.cpp:118-131,
+ *                                                   csrc/cuda/windows_cuda.cu:584-644 (:438-582)
+ *   -> pos_triples[K,3], neg_triples[K,3], pos_windows[K,2W,3]
+ * ------------------------------------------------------------------------------------- */
+int trw_windows(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                int64_t num_nodes, int64_t seed,
+                int64_t* target, int64_t* pos, int64_t* neg, int device, void* stream);
+
+int trw_windows_cbow(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                     int64_t num_nodes, int64_t seed,
+                     int64_t* pos_nodes, int64_t* neg_nodes, int64_t* windows,
+                     int device, void* stream);
+
+int trw_windows_triples(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                        int64_t num_nodes, int64_t padding_idx,
+                        const int64_t* triples, int64_t n_triples, int64_t seed,
+                        int64_t* target, int64_t* pos, int64_t* neg, int device, void* stream);
+
+int trw_windows_triples_cbow(const int64_t* walks, int64_t n_walks, int64_t walk_cols,
+                             int window_size, int64_t num_nodes, int64_t padding_idx,
+                             const int64_t* triples, int64_t n_triples, int64_t seed,
+                             int64_t* pos_triples, int64_t* neg_triples, int64_t* pos_windows,
+                             int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py / profiles only; not part of the reference's surface).
+ * trw_calib_gather: every thread performs `loads_per_thread` dependent random loads of
+ * `bytes_per_load` (8 or 32) from table[0, table_elems) -- the attainable random-sector rate
+ * the walk kernels are compared against.  sink[>=1] receives a checksum.
+ * ------------------------------------------------------------------------------------- */
+int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_threads,
+                     int loads_per_thread, int bytes_per_load, int64_t seed, int64_t* sink,
+                     int device, void* stream);
+
+/* Tuning knobs for experiments ("name" -> integer); returns TRW_ERR_ARG for unknown names.
+ * Defaults are the shipped configuration; bench.py records any override it applies. */
+int trw_set_option(const char* name, int64_t value);
+int64_t trw_get_option(const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRW_B200_H */

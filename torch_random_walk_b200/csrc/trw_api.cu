@@ -1,0 +1,159 @@
+// Error plumbing, options, device checks and the calibration gather of libtrw_b200.so.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "trw_common.cuh"
+#include "trw_options.h"
+
+namespace trw {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return TRW_OK;
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return TRW_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count(int device) {
+    static int cached[64];
+    if (device < 0 || device >= 64) return 148;
+    if (cached[device] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cached[device] = v;
+    }
+    return cached[device];
+}
+
+Options& options() {
+    static Options o;
+    return o;
+}
+
+int resolve_device(int device) {
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) {
+            set_error("no current CUDA device (this library has no CPU fallback)");
+            return -1;
+        }
+    }
+    static int checked[64];
+    if (device < 64 && checked[device] == 1) return device;
+    int major = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e != cudaSuccess) {
+        set_error("CUDA device %d unavailable: %s (this library has no CPU fallback)", device, cudaGetErrorString(e));
+        cudaGetLastError();
+        return -1;
+    }
+    if (major != 10) {
+        set_error("device %d has compute capability %d.x; libtrw_b200 carries sm_100a code only", device, major);
+        return -1;
+    }
+    if (device < 64) checked[device] = 1;
+    return device;
+}
+
+// ------------------------------------------------------------------ calibration gather
+// Each thread chases `loads` dependent pseudo-random locations: the address of load k+1 mixes
+// the value returned by load k, like a walk step.  BYTES = 8 reads one int64, 32 one sector.
+template <int BYTES>
+__global__ void __launch_bounds__(256) calib_gather_kernel(const int64_t* __restrict__ table, uint64_t n_units,
+                                                           int64_t n_threads, int loads, uint2 key,
+                                                           int64_t* __restrict__ sink) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_threads) return;
+    uint64_t acc = 0;
+    uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0, 0), key);
+    uint64_t state = ((uint64_t)r.x << 32) | r.y;
+    for (int k = 0; k < loads; ++k) {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        uint64_t unit = __umul64hi(state ^ (state >> 29), n_units);
+        if (BYTES == 8) {
+            uint64_t v = (uint64_t)ldg64_stream(table + unit);
+            acc += v;
+            state += v;
+        } else {
+            Sector64 s = ldg_sector(table + unit * 4);
+            acc += s.a ^ s.b ^ s.c ^ s.d;
+            state += s.a;
+        }
+    }
+    if (acc == 0x9E3779B97F4A7C15ull) sink[0] = (int64_t)acc;  // keeps the loads alive
+}
+
+}  // namespace trw
+
+using namespace trw;
+
+extern "C" {
+
+int trw_abi_version(void) { return TRW_ABI_VERSION; }
+const char* trw_last_error(void) { return g_err; }
+int64_t trw_launch_count(void) { return g_launches.load(); }
+void trw_reset_launch_count(void) { g_launches.store(0); }
+
+int trw_device_check(int device) {
+    int d = resolve_device(device);
+    return d < 0 ? TRW_ERR_DEVICE : TRW_OK;
+}
+
+int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_threads, int loads_per_thread,
+                     int bytes_per_load, int64_t seed, int64_t* sink, int device, void* stream) {
+    if (!table || !sink || table_elems < 4 || n_threads < 0 || loads_per_thread < 0 ||
+        (bytes_per_load != 8 && bytes_per_load != 32)) {
+        set_error("trw_calib_gather: bad argument");
+        return TRW_ERR_ARG;
+    }
+    if (bytes_per_load == 32 && ((uintptr_t)table & 31)) {
+        set_error("trw_calib_gather: table must be 32-byte aligned for sector loads");
+        return TRW_ERR_ARG;
+    }
+    int d = resolve_device(device);
+    if (d < 0) return TRW_ERR_DEVICE;
+    DeviceGuard g(d);
+    if (n_threads == 0) return TRW_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((n_threads + 255) / 256);
+    uint2 key = philox_key(seed, 0x43414C49u);
+    if (bytes_per_load == 8)
+        calib_gather_kernel<8><<<grid, 256, 0, st>>>(table, (uint64_t)table_elems, n_threads, loads_per_thread, key, sink);
+    else
+        calib_gather_kernel<32><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 4), n_threads, loads_per_thread, key, sink);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "calib_gather launch");
+}
+
+int trw_set_option(const char* name, int64_t value) {
+    if (!name) return TRW_ERR_ARG;
+    Options& o = options();
+#define TRW_OPT(field) if (!strcmp(name, #field)) { o.field = value; return TRW_OK; }
+    TRW_OPTION_LIST
+#undef TRW_OPT
+    set_error("trw_set_option: unknown option '%s'", name);
+    return TRW_ERR_ARG;
+}
+
+int64_t trw_get_option(const char* name) {
+    if (!name) return -1;
+    Options& o = options();
+#define TRW_OPT(field) if (!strcmp(name, #field)) return o.field;
+    TRW_OPTION_LIST
+#undef TRW_OPT
+    return -1;
+}
+
+}  // extern "C"

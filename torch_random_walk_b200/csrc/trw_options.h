@@ -1,0 +1,25 @@
+// Process-wide tuning knobs (trw_set_option / trw_get_option).  Defaults = shipped configuration.
+#pragma once
+#include <stdint.h>
+
+namespace trw {
+
+struct Options {
+    int64_t stage_output = 1;     // 1: 256-bit sector stores via the shared-memory ring; 0: plain 8-byte stores
+    int64_t n2v_table = 1;        // 1: hashed adjacency membership (needs workspace); 0: linear scan of adj(t)
+    int64_t n2v_speculate = 1;    // 1: fetch row_ptr[x] before the membership answer is known
+    int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
+    int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
+    int64_t host_chunk_walks = 1 << 20;  // walks per pipelined chunk in trw_walk_csr_host
+};
+
+#define TRW_OPTION_LIST                                                                      \
+    TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
+    TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks)
+
+Options& options();
+void count_launch(int n);
+// Validates `device` (or the current device when < 0) as an sm_100 part; returns its ordinal or -1.
+int resolve_device(int device);
+
+}  // namespace trw

@@ -1,0 +1,33 @@
+// Internal interface of the CSR walk (shared by trw_walk_csr and trw_walk_csr_host).
+#pragma once
+#include "trw_common.cuh"
+
+namespace trw {
+
+struct WalkArgs {
+    const int64_t* row_ptr;
+    const int64_t* col_idx;
+    int64_t n_nodes, nnz;
+    const int64_t* targets;
+    int64_t n_walks, walk_id_offset;
+    int walk_length;
+    uint2 key;
+    int64_t* out;
+    int64_t out_row_stride;
+    const uint32_t* table;
+    uint64_t thr0, thr1, thr2;  // acceptance thresholds on a 32-bit uniform, scaled by 2^32
+};
+
+struct CsrWalkPlan {
+    WalkArgs a;  // graph side filled by csr_walk_prepare; shard side by csr_walk_launch
+    int device;
+    bool uniform, table, speculate, stage, persist;
+};
+
+int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                     double p, double q, int walk_length, int64_t seed, void* workspace, size_t workspace_bytes,
+                     int device, cudaStream_t st);
+int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
+                    int64_t* out, int64_t out_row_stride, cudaStream_t st);
+
+}  // namespace trw

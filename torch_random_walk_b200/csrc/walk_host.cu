@@ -1,0 +1,114 @@
+// trw_walk_csr_host: the CSR walk for callers whose tensors live in host memory.
+//
+// The reference has no such path (a CPU tensor simply ran csrc/cpu); a drop-in user who holds
+// CPU tensors still has to get them to the GPU and the walks back, and that round trip is what
+// an end-to-end measurement pays for.  So it is engineered rather than left to three blocking
+// copies: the graph goes up once, the start nodes are walked in chunks on one stream, and each
+// finished chunk is copied back on a second stream while the next chunk is being walked
+// (PCIe is full duplex and the copy engines run beside the SMs).
+#include <algorithm>
+
+#include "trw_common.cuh"
+#include "trw_options.h"
+#include "walk_csr.h"
+
+namespace trw {
+
+struct HostWalkResources {
+    void* d_row_ptr = nullptr;
+    void* d_col_idx = nullptr;
+    void* d_targets = nullptr;
+    void* d_workspace = nullptr;
+    void* d_out[2] = {nullptr, nullptr};
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t walked[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    ~HostWalkResources() {
+        if (compute) cudaStreamSynchronize(compute);
+        if (copy) cudaStreamSynchronize(copy);
+        for (int k = 0; k < 2; ++k) {
+            if (walked[k]) cudaEventDestroy(walked[k]);
+            if (copied[k]) cudaEventDestroy(copied[k]);
+            if (d_out[k]) cudaFree(d_out[k]);
+        }
+        if (d_workspace) cudaFree(d_workspace);
+        if (d_targets) cudaFree(d_targets);
+        if (d_col_idx) cudaFree(d_col_idx);
+        if (d_row_ptr) cudaFree(d_row_ptr);
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+    }
+};
+
+#define TRW_TRY(expr, what)                       \
+    do {                                          \
+        int rc__ = check_cuda((expr), what);      \
+        if (rc__) return rc__;                    \
+    } while (0)
+
+}  // namespace trw
+
+using namespace trw;
+
+extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                                 const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, double p, double q,
+                                 int walk_length, int64_t seed, int64_t* out, int device) {
+    if (n_walks < 0 || n_nodes < 0 || nnz < 0 || walk_length < 0) {
+        set_error("trw_walk_csr_host: negative size");
+        return TRW_ERR_ARG;
+    }
+    if (n_walks > 0 && (!row_ptr || !targets || !out || (nnz > 0 && !col_idx))) {
+        set_error("trw_walk_csr_host: null pointer");
+        return TRW_ERR_ARG;
+    }
+    const int d = resolve_device(device);
+    if (d < 0) return TRW_ERR_DEVICE;
+    if (n_walks == 0) return TRW_OK;
+    DeviceGuard guard(d);
+    if (!guard.ok) { set_error("trw_walk_csr_host: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }
+
+    const int64_t row_len = (int64_t)walk_length + 1;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(options().host_chunk_walks, n_walks));
+    const size_t ws_bytes = trw_walk_csr_workspace_bytes(n_nodes, nnz, p, q);
+
+    HostWalkResources r;
+    TRW_TRY(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking), "stream create");
+    TRW_TRY(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking), "stream create");
+    for (int k = 0; k < 2; ++k) {
+        TRW_TRY(cudaEventCreateWithFlags(&r.walked[k], cudaEventDisableTiming), "event create");
+        TRW_TRY(cudaEventCreateWithFlags(&r.copied[k], cudaEventDisableTiming), "event create");
+    }
+    TRW_TRY(cudaMalloc(&r.d_row_ptr, (size_t)(n_nodes + 1) * 8), "cudaMalloc row_ptr");
+    TRW_TRY(cudaMalloc(&r.d_col_idx, std::max<size_t>((size_t)nnz * 8, 8)), "cudaMalloc col_idx");
+    TRW_TRY(cudaMalloc(&r.d_targets, (size_t)n_walks * 8), "cudaMalloc targets");
+    if (ws_bytes) TRW_TRY(cudaMalloc(&r.d_workspace, ws_bytes), "cudaMalloc workspace");
+    const int n_buf = n_walks > chunk ? 2 : 1;
+    for (int k = 0; k < n_buf; ++k) TRW_TRY(cudaMalloc(&r.d_out[k], (size_t)chunk * row_len * 8), "cudaMalloc walks");
+
+    TRW_TRY(cudaMemcpyAsync(r.d_row_ptr, row_ptr, (size_t)(n_nodes + 1) * 8, cudaMemcpyHostToDevice, r.compute), "H2D row_ptr");
+    if (nnz) TRW_TRY(cudaMemcpyAsync(r.d_col_idx, col_idx, (size_t)nnz * 8, cudaMemcpyHostToDevice, r.compute), "H2D col_idx");
+    TRW_TRY(cudaMemcpyAsync(r.d_targets, targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
+
+    CsrWalkPlan plan;
+    int rc = csr_walk_prepare(&plan, (const int64_t*)r.d_row_ptr, (const int64_t*)r.d_col_idx, n_nodes, nnz, p, q,
+                              walk_length, seed, r.d_workspace, ws_bytes, d, r.compute);
+    if (rc) return rc;
+
+    int64_t done = 0;
+    for (int c = 0; done < n_walks; ++c) {
+        const int b = c & 1;
+        const int64_t m = std::min(chunk, n_walks - done);
+        if (c >= 2) TRW_TRY(cudaStreamWaitEvent(r.compute, r.copied[b], 0), "wait copied");
+        rc = csr_walk_launch(plan, (const int64_t*)r.d_targets + done, m, walk_id_offset + done, (int64_t*)r.d_out[b],
+                             row_len, r.compute);
+        if (rc) return rc;
+        TRW_TRY(cudaEventRecord(r.walked[b], r.compute), "record walked");
+        TRW_TRY(cudaStreamWaitEvent(r.copy, r.walked[b], 0), "wait walked");
+        TRW_TRY(cudaMemcpyAsync(out + done * row_len, r.d_out[b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy),
+                "D2H walks");
+        TRW_TRY(cudaEventRecord(r.copied[b], r.copy), "record copied");
+        done += m;
+    }
+    TRW_TRY(cudaStreamSynchronize(r.compute), "sync compute");
+    TRW_TRY(cudaStreamSynchronize(r.copy), "sync copy");
+    return TRW_OK;
+}

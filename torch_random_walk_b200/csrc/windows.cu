@@ -1,0 +1,277 @@
+// Window generation for sm_100a: one coalesced gather kernel per call.
+//
+// Replaces the four launchers/kernels of csrc/cuda/windows_cuda.cu (to_windows_gpu :67-119 /
+// create_windows :7-65; to_windows_cbow_gpu :187-239 / :122-185; to_windows_triples_gpu
+// :375-435 / :241-373; to_windows_triples_cbow_gpu :584-644 / :438-582).
+//
+// The reference gives each walk to one thread, which then writes its windows with 8-byte
+// stores scattered over three tensors.  Here the problem is turned around: every output tensor
+// is a dense array whose element e is a pure function of e (which walk, which window, which
+// slot), so a CTA stages a tile of walk rows in shared memory once and then streams the three
+// contiguous output segments that belong to that tile with fully coalesced 16-byte stores.
+// Positives and targets are bit-exact with the reference; negatives are Philox draws indexed
+// by the output element, so they do not depend on the launch shape.
+#include "trw_common.cuh"
+#include "trw_options.h"
+
+namespace trw {
+
+enum WinMode { kSkipGram = 0, kCbow = 1, kTriples = 2, kTriplesCbow = 3 };
+
+// Exact division of a 32-bit numerator by a runtime constant (magic = floor(2^64/d)+1).
+struct FastDiv {
+    uint32_t d;
+    uint64_t magic;
+    __host__ void set(uint32_t div) { d = div; magic = div > 1 ? (~0ull / div) + 1 : 0; }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? (uint32_t)__umul64hi(n, magic) : n; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
+struct WinArgs {
+    const int64_t* walks;
+    int64_t n_walks;
+    int wl;        // columns of `walks`
+    int W;         // window_size
+    int mid;       // W / 2
+    int per_walk;  // windows (skip-gram/CBOW) or target triples per walk
+    int tile_walks;
+    int use_smem;
+    int64_t num_nodes, pad;
+    const int64_t* triples;
+    int64_t n_triples;
+    uint2 key;
+    int64_t* out[3];       // outputs in the API's order
+    uint32_t epw[3];       // elements of out[k] per walk
+    FastDiv by_per_walk;   // / per_walk
+    FastDiv by_row;        // / (W-1)   (node windows)  or  / (2W) (triple windows)
+    FastDiv by_3;
+};
+
+// Draw #draw of stream `stream` for item g: 64 random bits as two words.
+__device__ __forceinline__ uint2 draw64(const uint2 key, uint64_t g, uint32_t stream, uint32_t draw) {
+    uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), stream, draw >> 1), key);
+    return (draw & 1u) ? make_uint2(r.z, r.w) : make_uint2(r.x, r.y);
+}
+
+// Positive window slot (row h of 2W, component c) of target triple ti in walk row w
+// (windows_cuda.cu:284-345; note the head slot of a LEFT row holds walk[rel_idx], :294-295).
+__device__ __forceinline__ int64_t triple_window_value(const int64_t* w, int wl, int W, int64_t pad, int ti, int h, int c) {
+    const int r = 2 * ti + 1;
+    if (h < W) {
+        const int ri = r - 2 * (h + 1);
+        if (c == 2) return ri >= -1 ? w[ri + 1] : pad;
+        return ri >= 1 ? w[ri] : pad;
+    }
+    const int idx = r + 2 * (h - W + 1) - 1 + c;
+    return idx < wl ? w[idx] : pad;
+}
+
+template <int MODE>
+__device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_t* tile, int which, uint32_t e, uint64_t g) {
+    // e: element index inside this tile's segment of out[which]; g: the same index in the whole tensor.
+    if (MODE == kSkipGram || MODE == kCbow) {
+        const int pos_out = (MODE == kSkipGram) ? 1 : 2, neg_out = (MODE == kSkipGram) ? 2 : 1;
+        if (which == 0) {  // target_nodes / pos_nodes
+            uint32_t i, s;
+            a.by_per_walk.divmod(e, i, s);
+            return tile[(size_t)i * a.wl + s + a.mid];
+        }
+        if (which == pos_out) {  // pos_windows / windows: the window without its middle element
+            uint32_t k, j, i, s;
+            a.by_row.divmod(e, k, j);
+            a.by_per_walk.divmod(k, i, s);
+            return tile[(size_t)i * a.wl + s + j + (j >= (uint32_t)a.mid ? 1u : 0u)];
+        }
+        (void)neg_out;
+        if (MODE == kSkipGram) {  // neg_windows: uniform node id (windows_cuda.cu:57-62)
+            uint2 r = draw64(a.key, g, 1u, 0u);
+            return bounded(r.x, r.y, a.num_nodes);
+        }
+        // CBOW neg_nodes: redraw while equal to the positive node, at most 101 times (:160-167)
+        uint32_t i, s;
+        a.by_per_walk.divmod(e, i, s);
+        const int64_t pos = tile[(size_t)i * a.wl + s + a.mid];
+        int64_t neg = 0;
+        for (uint32_t attempt = 0; attempt <= 101u; ++attempt) {
+            uint2 r = draw64(a.key, g, 2u, attempt);
+            neg = bounded(r.x, r.y, a.num_nodes);
+            if (neg != pos) break;
+        }
+        return neg;
+    }
+    // Triple modes.
+    const int pos_out = (MODE == kTriples) ? 1 : 2;
+    uint32_t row, c;
+    a.by_3.divmod(e, row, c);
+    if (which == 0) {  // target_triples / pos_triples
+        uint32_t i, ti;
+        a.by_per_walk.divmod(row, i, ti);
+        return tile[(size_t)i * a.wl + 2 * ti + c];
+    }
+    if (which == pos_out) {
+        uint32_t k, h, i, ti;
+        a.by_row.divmod(row, k, h);
+        a.by_per_walk.divmod(k, i, ti);
+        return triple_window_value(tile + (size_t)i * a.wl, a.wl, a.W, a.pad, (int)ti, (int)h, (int)c);
+    }
+    const uint64_t grow = g / 3;  // row of the negative tensor
+    if (MODE == kTriples) {  // neg_windows: a uniformly drawn row of `triples` (:353-365)
+        uint2 r = draw64(a.key, grow, 3u, 0u);
+        const int64_t idx = bounded(r.x, r.y, a.n_triples);
+        return __ldg(a.triples + idx * 3 + c);
+    }
+    // Triple CBOW neg_triples: redraw while identical to the positive triple (:485-505)
+    uint32_t i, ti;
+    a.by_per_walk.divmod(row, i, ti);
+    const int64_t* w = tile + (size_t)i * a.wl + 2 * ti;
+    const int64_t ph = w[0], pr = w[1], pt = w[2];
+    int64_t idx = 0;
+    for (uint32_t attempt = 0; attempt <= 101u; ++attempt) {
+        uint2 r = draw64(a.key, grow, 4u, attempt);
+        idx = bounded(r.x, r.y, a.n_triples);
+        if (__ldg(a.triples + idx * 3) != ph || __ldg(a.triples + idx * 3 + 1) != pr || __ldg(a.triples + idx * 3 + 2) != pt) break;
+    }
+    return __ldg(a.triples + idx * 3 + c);
+}
+
+template <int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
+    extern __shared__ __align__(16) int64_t smem_tile[];
+    const int64_t i0 = (int64_t)blockIdx.x * a.tile_walks;
+    const int tw = (int)min((int64_t)a.tile_walks, a.n_walks - i0);
+    const int64_t* gsrc = a.walks + i0 * a.wl;
+    const int64_t* tile = gsrc;
+    if (a.use_smem) {
+        const int n = tw * a.wl;
+        if ((((uintptr_t)gsrc) & 15) == 0) {
+            const int n2 = n >> 1;
+            const longlong2* src2 = reinterpret_cast<const longlong2*>(gsrc);
+            longlong2* dst2 = reinterpret_cast<longlong2*>(smem_tile);
+            for (int k = threadIdx.x; k < n2; k += BLOCK) dst2[k] = __ldg(src2 + k);
+            if ((n & 1) && threadIdx.x == 0) smem_tile[n - 1] = __ldg(gsrc + n - 1);
+        } else {
+            for (int k = threadIdx.x; k < n; k += BLOCK) smem_tile[k] = __ldg(gsrc + k);
+        }
+        __syncthreads();
+        tile = smem_tile;
+    }
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+        const uint64_t gbase = (uint64_t)i0 * a.epw[which];
+        int64_t* dst = a.out[which] + gbase;
+        const uint32_t n = (uint32_t)tw * a.epw[which];
+        if ((((uintptr_t)dst) & 15) == 0) {
+            const uint32_t n2 = n >> 1;
+            for (uint32_t k = threadIdx.x; k < n2; k += BLOCK) {
+                longlong2 v;
+                v.x = window_element<MODE>(a, tile, which, 2 * k, gbase + 2 * k);
+                v.y = window_element<MODE>(a, tile, which, 2 * k + 1, gbase + 2 * k + 1);
+                reinterpret_cast<longlong2*>(dst)[k] = v;
+            }
+            if ((n & 1u) && threadIdx.x == 0) dst[n - 1] = window_element<MODE>(a, tile, which, n - 1, gbase + n - 1);
+        } else {
+            for (uint32_t k = threadIdx.x; k < n; k += BLOCK) dst[k] = window_element<MODE>(a, tile, which, k, gbase + k);
+        }
+    }
+}
+
+template <int MODE>
+static int launch_windows(const char* name, const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                          int64_t num_nodes, int64_t pad, const int64_t* triples, int64_t n_triples, int64_t seed,
+                          int64_t* o0, int64_t* o1, int64_t* o2, int device, void* stream) {
+    constexpr bool kTripleMode = (MODE == kTriples || MODE == kTriplesCbow);
+    if (n_walks < 0 || walk_cols < 0 || window_size < 0) { set_error("%s: negative size", name); return TRW_ERR_ARG; }
+    if (walk_cols > (1 << 24) || window_size > (1 << 15)) {
+        set_error("%s: walk rows longer than 2^24 or windows wider than 2^15 are not supported", name);
+        return TRW_ERR_ARG;
+    }
+    int64_t per_walk;
+    uint32_t epw[3];
+    const int W = window_size;
+    if (!kTripleMode) {
+        if (W < 1) { set_error("%s: window_size must be >= 1", name); return TRW_ERR_ARG; }
+        per_walk = walk_cols - W + 1;
+        if (per_walk < 0) per_walk = 0;  // the reference would ask torch for a negative size here
+        epw[0] = (uint32_t)per_walk;
+        epw[1] = epw[2] = (uint32_t)(per_walk * (W - 1));
+        if (MODE == kCbow) epw[1] = (uint32_t)per_walk;
+    } else {
+        per_walk = walk_cols >= 1 ? (walk_cols - 1) / 2 : 0;
+        epw[0] = (uint32_t)(per_walk * 3);
+        epw[1] = epw[2] = (uint32_t)(per_walk * 2 * W * 3);
+        if (MODE == kTriplesCbow) epw[1] = (uint32_t)(per_walk * 3);
+    }
+    const int64_t max_epw = (int64_t)per_walk * (kTripleMode ? (int64_t)6 * (W > 0 ? W : 1) : (W > 1 ? W - 1 : 1));
+    if (max_epw >= (1ll << 29)) { set_error("%s: more than 2^29 output elements per walk", name); return TRW_ERR_ARG; }
+    if (n_walks == 0 || per_walk == 0) return resolve_device(device) < 0 ? TRW_ERR_DEVICE : TRW_OK;
+    if (!walks || !o0 || (epw[1] && !o1) || (epw[2] && !o2)) { set_error("%s: null pointer", name); return TRW_ERR_ARG; }
+    if (!kTripleMode && num_nodes <= 0) { set_error("%s: num_nodes must be positive", name); return TRW_ERR_ARG; }
+    if (kTripleMode && (n_triples <= 0 || !triples)) { set_error("%s: triples must not be empty", name); return TRW_ERR_ARG; }
+    const int d = resolve_device(device);
+    if (d < 0) return TRW_ERR_DEVICE;
+    DeviceGuard guard(d);
+    if (!guard.ok) { set_error("%s: cudaSetDevice(%d) failed", name, d); return TRW_ERR_DEVICE; }
+
+    WinArgs a;
+    a.walks = walks; a.n_walks = n_walks; a.wl = (int)walk_cols; a.W = W; a.mid = W / 2; a.per_walk = (int)per_walk;
+    a.num_nodes = num_nodes; a.pad = pad; a.triples = triples; a.n_triples = n_triples;
+    a.key = philox_key(seed, kTagWindows);
+    a.out[0] = o0; a.out[1] = o1; a.out[2] = o2;
+    for (int k = 0; k < 3; ++k) a.epw[k] = epw[k];
+    a.by_per_walk.set((uint32_t)per_walk);
+    a.by_row.set(kTripleMode ? (uint32_t)(2 * W) : (uint32_t)(W - 1));
+    a.by_3.set(3);
+    // Tile: an even number of walk rows, about 32 KiB of them, and < 2^31 elements per output segment.
+    constexpr int BLOCK = 256;
+    int64_t tw = (32 * 1024) / (walk_cols * 8);
+    const int64_t cap = (1ll << 30) / (max_epw > 0 ? max_epw : 1);
+    if (tw > cap) tw = cap;
+    tw &= ~1ll;
+    if (tw < 2) tw = 2;
+    size_t smem = (size_t)tw * walk_cols * 8;
+    a.use_smem = 1;
+    if (smem > 200 * 1024) { a.use_smem = 0; smem = 0; }
+    a.tile_walks = (int)tw;
+    if (smem > 48 * 1024) {
+        int rc = check_cuda(cudaFuncSetAttribute(windows_kernel<MODE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        if (rc) return rc;
+    }
+    const int64_t tiles = (n_walks + tw - 1) / tw;
+    if (tiles > 0x7FFFFFFFll) { set_error("%s: too many tiles", name); return TRW_ERR_ARG; }
+    windows_kernel<MODE, BLOCK><<<(unsigned)tiles, BLOCK, smem, (cudaStream_t)stream>>>(a);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), name);
+}
+
+}  // namespace trw
+
+using namespace trw;
+
+extern "C" int trw_windows(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size, int64_t num_nodes,
+                           int64_t seed, int64_t* target, int64_t* pos, int64_t* neg, int device, void* stream) {
+    return launch_windows<kSkipGram>("trw_windows", walks, n_walks, walk_cols, window_size, num_nodes, 0, nullptr, 0, seed,
+                                     target, pos, neg, device, stream);
+}
+
+extern "C" int trw_windows_cbow(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                                int64_t num_nodes, int64_t seed, int64_t* pos_nodes, int64_t* neg_nodes, int64_t* windows,
+                                int device, void* stream) {
+    return launch_windows<kCbow>("trw_windows_cbow", walks, n_walks, walk_cols, window_size, num_nodes, 0, nullptr, 0, seed,
+                                 pos_nodes, neg_nodes, windows, device, stream);
+}
+
+extern "C" int trw_windows_triples(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                                   int64_t num_nodes, int64_t padding_idx, const int64_t* triples, int64_t n_triples,
+                                   int64_t seed, int64_t* target, int64_t* pos, int64_t* neg, int device, void* stream) {
+    return launch_windows<kTriples>("trw_windows_triples", walks, n_walks, walk_cols, window_size, num_nodes, padding_idx,
+                                    triples, n_triples, seed, target, pos, neg, device, stream);
+}
+
+extern "C" int trw_windows_triples_cbow(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                                        int64_t num_nodes, int64_t padding_idx, const int64_t* triples, int64_t n_triples,
+                                        int64_t seed, int64_t* pos_triples, int64_t* neg_triples, int64_t* pos_windows,
+                                        int device, void* stream) {
+    return launch_windows<kTriplesCbow>("trw_windows_triples_cbow", walks, n_walks, walk_cols, window_size, num_nodes,
+                                        padding_idx, triples, n_triples, seed, pos_triples, neg_triples, pos_windows, device,
+                                        stream);
+}

@@ -1,0 +1,243 @@
+"""The `torch_rw_native` surface over libtrw_b200.so (ctypes; C ABI in include/trw_b200.h).
+
+Stands where the reference's pybind11 module stood (/root/reference/csrc/rw_init.cpp:133-141):
+the same seven functions, positional arguments in the same order, same return values.  What the
+reference's launchers did around their kernels is done here -- device checks with the reference's
+messages (csrc/cuda/utils.cuh:7-9), `torch.empty` outputs on the inputs' device, launch on the
+current stream, no host synchronisation -- and nothing else: all arithmetic is in the CUDA
+library.  There is NO CPU path: CPU tensors raise, and a missing/unloadable library raises at
+import of this module.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _build
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_c_dbl = ctypes.c_double
+_c_ptr = ctypes.c_void_p
+_c_size = ctypes.c_size_t
+
+
+def _load():
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if os.environ.get("TRW_NO_AUTOBUILD"):
+            raise ImportError(f"{path} is missing; run `python -m torch_random_walk_b200._build`")
+        _build.build()
+    lib = ctypes.CDLL(path)
+    lib.trw_last_error.restype = ctypes.c_char_p
+    lib.trw_launch_count.restype = _c_i64
+    lib.trw_get_option.restype = _c_i64
+    lib.trw_get_option.argtypes = [ctypes.c_char_p]
+    lib.trw_set_option.argtypes = [ctypes.c_char_p, _c_i64]
+    lib.trw_walk_csr_workspace_bytes.restype = _c_size
+    lib.trw_walk_csr_workspace_bytes.argtypes = [_c_i64, _c_i64, _c_dbl, _c_dbl]
+    lib.trw_walk_csr.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
+                                 _c_i64, _c_ptr, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr]
+    lib.trw_walk_csr_host.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
+                                      _c_i64, _c_ptr, _c_int]
+    lib.trw_walk_edge_list.argtypes = [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
+                                       _c_i64, _c_i64, _c_int, _c_ptr, _c_i64, _c_int, _c_ptr]
+    lib.trw_walk_triples.argtypes = [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_int,
+                                     _c_i64, _c_ptr, _c_i64, _c_int, _c_ptr]
+    win = [_c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
+    lib.trw_windows.argtypes = win
+    lib.trw_windows_cbow.argtypes = win
+    wint = [_c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
+    lib.trw_windows_triples.argtypes = wint
+    lib.trw_windows_triples_cbow.argtypes = wint
+    lib.trw_calib_gather.argtypes = [_c_ptr, _c_i64, _c_i64, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_ptr]
+    lib.trw_device_check.argtypes = [_c_int]
+    if lib.trw_abi_version() != 1:
+        raise ImportError("libtrw_b200.so ABI version mismatch; rebuild with python -m torch_random_walk_b200._build")
+    return lib
+
+
+_lib = _load()
+LIB_PATH = _build.LIB_PATH
+
+
+def lib():
+    """The loaded ctypes library (tests check its exported symbols against include/trw_b200.h)."""
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise RuntimeError(_lib.trw_last_error().decode("utf-8", "replace") or f"libtrw_b200 status {status}")
+
+
+def _require_cuda(t, name):
+    # message convention of the reference's CHECK_CUDA (csrc/cuda/utils.cuh:7)
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"(*{name}) must be a CUDA tensor")
+    if t.dtype != torch.int64:
+        # the reference's packed_accessor64<int64_t> raises the same way
+        raise RuntimeError(f"expected scalar type Long but found {str(t.dtype).replace('torch.', '')} ({name})")
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t.numel() else 0)
+
+
+def set_option(name, value):
+    _check(_lib.trw_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(_lib.trw_get_option(name.encode()))
+
+
+def launch_count():
+    return int(_lib.trw_launch_count())
+
+
+def reset_launch_count():
+    _lib.trw_reset_launch_count()
+
+
+def walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None):
+    """csrc/rw_init.cpp:11-25 -> csrc/cuda/rw_cuda.cu:186-248.  Returns walks[n, walk_length+1] on
+    row_ptr's device.  `walk_id_offset` / `out` are extensions for sharded callers."""
+    _require_cuda(row_ptr, "row_ptr")
+    _require_cuda(column_idx, "column_idx")
+    _require_cuda(target_nodes, "target_nodes")
+    dev = row_ptr.device
+    row_ptr, column_idx, target_nodes = row_ptr.contiguous(), column_idx.contiguous(), target_nodes.contiguous()
+    n, wl = target_nodes.size(0), int(walk_length) + 1
+    n_nodes, nnz = max(row_ptr.numel() - 1, 0), column_idx.numel()
+    with torch.cuda.device(dev):
+        walks = torch.empty((n, wl), dtype=torch.int64, device=dev) if out is None else out
+        need = _lib.trw_walk_csr_workspace_bytes(n_nodes, nnz, float(p), float(q)) if n else 0
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
+        _check(_lib.trw_walk_csr(_ptr(row_ptr), _ptr(column_idx), n_nodes, nnz, _ptr(target_nodes), n,
+                                 int(walk_id_offset), float(p), float(q), int(walk_length), int(seed), _ptr(walks),
+                                 walks.stride(0) if n else wl, _ptr(ws) if ws is not None else None, need, dev.index,
+                                 _stream(dev)))
+    return walks
+
+
+def walk_edge_list(edge_list_indexed, node_edges_idx, target_nodes, p, q, walk_length, seed, padding_idx, restart,
+                   walk_id_offset=0):
+    """csrc/rw_init.cpp:27-45 -> csrc/cuda/rw_cuda_edge_list.cu:243-308.  Output on
+    node_edges_idx's device (rw_cuda_edge_list.cu:260)."""
+    _require_cuda(edge_list_indexed, "edge_list_indexed")
+    _require_cuda(node_edges_idx, "node_edges_idx")
+    _require_cuda(target_nodes, "target_nodes")
+    dev = node_edges_idx.device
+    el, nei, tg = edge_list_indexed.contiguous(), node_edges_idx.contiguous(), target_nodes.contiguous()
+    n, wl = tg.size(0), int(walk_length) + 1
+    with torch.cuda.device(dev):
+        walks = torch.empty((n, wl), dtype=torch.int64, device=dev)
+        _check(_lib.trw_walk_edge_list(_ptr(el), el.size(0), _ptr(nei), nei.size(0), _ptr(tg), n, int(walk_id_offset),
+                                       float(p), float(q), int(walk_length), int(seed), int(padding_idx),
+                                       1 if restart else 0, _ptr(walks), wl, dev.index, _stream(dev)))
+    return walks
+
+
+def walk_triples(triples_indexed, relation_tail_index, target_nodes, walk_length, padding_idx, restart, seed,
+                 walk_id_offset=0):
+    """csrc/rw_init.cpp:47-75 -> csrc/cuda/rw_cuda_triples.cu:103-169.  Output [n, 2*walk_length+1]
+    on target_nodes' device (rw_cuda_triples.cu:118)."""
+    _require_cuda(triples_indexed, "triples_indexed")
+    _require_cuda(relation_tail_index, "relation_tail_index")
+    _require_cuda(target_nodes, "target_nodes")
+    dev = target_nodes.device
+    tr, rti, tg = triples_indexed.contiguous(), relation_tail_index.contiguous(), target_nodes.contiguous()
+    n, wl = tg.size(0), 2 * int(walk_length) + 1
+    with torch.cuda.device(dev):
+        walks = torch.empty((n, wl), dtype=torch.int64, device=dev)
+        _check(_lib.trw_walk_triples(_ptr(tr), tr.size(0), _ptr(rti), rti.size(0), _ptr(tg), n, int(walk_id_offset),
+                                     int(walk_length), int(padding_idx), 1 if restart else 0, int(seed), _ptr(walks),
+                                     wl, dev.index, _stream(dev)))
+    return walks
+
+
+def _require_walks(walks):
+    _require_cuda(walks, "walks")
+    if walks.dim() != 2:
+        raise RuntimeError("walks must be a 2-d tensor")
+    if not walks.is_contiguous():
+        # CHECK_CONTIGUOUS, csrc/cuda/utils.cuh:9 (spelling kept)
+        raise RuntimeError("walks must be a contigous tensor")
+
+
+def _node_windows(fn, walks, window_size, num_nodes, seed, cbow):
+    _require_walks(walks)
+    dev = walks.device
+    n, wl = walks.shape
+    w = int(window_size)
+    k = (wl - w + 1) * n
+    with torch.cuda.device(dev):
+        first = torch.empty((k,), dtype=torch.int64, device=dev)
+        win_a = torch.empty((k, w - 1), dtype=torch.int64, device=dev)
+        other = torch.empty((k,) if cbow else (k, w - 1), dtype=torch.int64, device=dev)
+        outs = (first, other, win_a) if cbow else (first, win_a, other)
+        _check(fn(_ptr(walks), n, wl, w, int(num_nodes), int(seed), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
+                  dev.index, _stream(dev)))
+    return outs
+
+
+def to_windows(walks, window_size, num_nodes, seed):
+    """csrc/rw_init.cpp:77-88 -> (target_nodes[K], pos_windows[K,W-1], neg_windows[K,W-1])."""
+    return _node_windows(_lib.trw_windows, walks, window_size, num_nodes, seed, cbow=False)
+
+
+def to_windows_cbow(walks, window_size, num_nodes, seed):
+    """csrc/rw_init.cpp:90-101 -> (pos_nodes[K], neg_nodes[K], windows[K,W-1])."""
+    return _node_windows(_lib.trw_windows_cbow, walks, window_size, num_nodes, seed, cbow=True)
+
+
+def _triple_windows(fn, walks, window_size, num_nodes, padding_idx, triples, seed, cbow):
+    _require_walks(walks)
+    _require_cuda(triples, "triples")
+    dev = walks.device
+    triples = triples.contiguous()
+    n, wl = walks.shape
+    w = int(window_size)
+    k = ((wl - 1) // 2) * n
+    with torch.cuda.device(dev):
+        first = torch.empty((k, 3), dtype=torch.int64, device=dev)
+        win_a = torch.empty((k, 2 * w, 3), dtype=torch.int64, device=dev)
+        other = torch.empty((k, 3) if cbow else (k, 2 * w, 3), dtype=torch.int64, device=dev)
+        outs = (first, other, win_a) if cbow else (first, win_a, other)
+        _check(fn(_ptr(walks), n, wl, w, int(num_nodes), int(padding_idx), _ptr(triples), triples.size(0), int(seed),
+                  _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), dev.index, _stream(dev)))
+    return outs
+
+
+def to_windows_triples(walks, window_size, num_nodes, padding_idx, triples, seed):
+    """csrc/rw_init.cpp:103-116 -> (target_triples[K,3], pos_windows[K,2W,3], neg_windows[K,2W,3])."""
+    return _triple_windows(_lib.trw_windows_triples, walks, window_size, num_nodes, padding_idx, triples, seed, False)
+
+
+def to_windows_triples_cbow(walks, window_size, num_nodes, padding_idx, triples, seed):
+    """csrc/rw_init.cpp:118-131 -> (pos_triples[K,3], neg_triples[K,3], pos_windows[K,2W,3])."""
+    return _triple_windows(_lib.trw_windows_triples_cbow, walks, window_size, num_nodes, padding_idx, triples, seed, True)
+
+
+def walk_host(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, device=0, walk_id_offset=0, out=None):
+    """End-to-end entry for callers holding CPU tensors (trw_walk_csr_host): the graph and start
+    nodes are copied to `device`, walked in chunks, and the walks are streamed back into a (pinned)
+    CPU tensor.  Still the CUDA path -- there is no CPU implementation to fall back to."""
+    for t, name in ((row_ptr, "row_ptr"), (column_idx, "column_idx"), (target_nodes, "target_nodes")):
+        if t.is_cuda or t.dtype != torch.int64:
+            raise RuntimeError(f"(*{name}) must be an int64 CPU tensor for walk_host")
+    row_ptr, column_idx, target_nodes = row_ptr.contiguous(), column_idx.contiguous(), target_nodes.contiguous()
+    n, wl = target_nodes.size(0), int(walk_length) + 1
+    if out is None:
+        out = torch.empty((n, wl), dtype=torch.int64, pin_memory=True)
+    _check(_lib.trw_walk_csr_host(_ptr(row_ptr), _ptr(column_idx), max(row_ptr.numel() - 1, 0), column_idx.numel(),
+                                  _ptr(target_nodes), n, int(walk_id_offset), float(p), float(q), int(walk_length),
+                                  int(seed), _ptr(out), int(device)))
+    return out

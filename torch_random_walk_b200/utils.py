@@ -1,0 +1,114 @@
+"""Graph -> tensor preparation; drop-in for the reference's torch_rw/utils.py.
+
+Same function names, argument meaning and outputs (int64, contiguous CPU tensors) as
+/root/reference/torch_rw/utils.py:5-120, without its O(n^2) Python loops, its float32 round
+trip (utils.py:7-8 is wrong above 2^24) and its dependency on an API networkx 3 removed
+(`nx.to_scipy_sparse_matrix`, utils.py:6).  These run on the host, like the reference's: they
+feed the CUDA walk kernels, they are not part of them.
+"""
+import numpy as np
+import torch
+
+
+def to_csr(graph):
+    """networkx graph -> (row_ptr[n+1], col_idx[nnz]).  Reference: torch_rw/utils.py:5-9.
+
+    Node id = position in graph.nodes() order; rows are sorted and duplicate edges merged
+    (scipy canonical CSR, what `nx.to_scipy_sparse_matrix(graph, format='csr')` produced);
+    edge weights are dropped.
+    """
+    import networkx as nx
+
+    csr = nx.to_scipy_sparse_array(graph, format="csr")
+    csr.sum_duplicates()
+    csr.sort_indices()
+    row_ptr = torch.from_numpy(np.asarray(csr.indptr, dtype=np.int64)).contiguous()
+    col_idx = torch.from_numpy(np.asarray(csr.indices, dtype=np.int64)).contiguous()
+    return row_ptr, col_idx
+
+
+def nodes_tensor(graph):
+    """arange(number_of_nodes) as int64.  Reference: torch_rw/utils.py:11-18 (which finds each
+    node's position with list.index, i.e. its own position, in O(n^2))."""
+    return torch.arange(graph.number_of_nodes(), dtype=torch.int64).contiguous()
+
+
+def to_edge_list_indexed(graph):
+    """networkx graph -> (edge_list_indexed[E,2], node_index_mapping).  Reference:
+    torch_rw/utils.py:21-56.
+
+    A node's id is its rank among sorted(graph.nodes()).  The mapping dict holds only nodes that
+    occur in an edge, in order of first occurrence (head before tail) -- the reference's tests
+    take `list(node_idx_map.values())` as start nodes, so the order is part of the contract.
+    Undirected graphs get the reversed edges appended (utils.py:52-54).
+    """
+    import networkx as nx
+
+    edges = list(graph.edges())
+    rank = {node: i for i, node in enumerate(sorted(graph.nodes()))}
+    node_index_mapping = {}
+    flat = np.empty((len(edges), 2), dtype=np.int64)
+    for i, (head, tail) in enumerate(edges):
+        h = node_index_mapping.get(head)
+        if h is None:
+            h = node_index_mapping[head] = rank[head]
+        t = node_index_mapping.get(tail)
+        if t is None:
+            t = node_index_mapping[tail] = rank[tail]
+        flat[i, 0] = h
+        flat[i, 1] = t
+    edge_list_indexed = torch.from_numpy(flat).contiguous()
+    if not nx.is_directed(graph):
+        edge_list_indexed = torch.cat((edge_list_indexed, torch.fliplr(edge_list_indexed)), dim=0)
+    return edge_list_indexed, node_index_mapping
+
+
+def _sort_rows_by_head(rows: np.ndarray) -> np.ndarray:
+    # The reference sorts with pandas `sort_values(by="head")` (utils.py:62, 96): a single-key
+    # sort with the default kind, i.e. numpy's argsort(kind="quicksort") on the head column.
+    # Using the same call keeps the (unstable) order of rows that share a head identical.
+    order = np.argsort(rows[:, 0], kind="quicksort")
+    return rows[order]
+
+
+def _head_ranges(heads: np.ndarray, num_nodes: int) -> torch.Tensor:
+    """Inclusive [first,last] row range per head id, [-1,-1] for ids without rows.
+
+    Vectorised restatement of the loop at torch_rw/utils.py:74-87 / 106-118, including its
+    single-row corner: with exactly one row the loop only ever writes column 0, leaving [0,-1].
+    """
+    num_rows = heads.shape[0]
+    if num_rows == 0:
+        # the reference reads row 0 unconditionally (utils.py:73 / 105)
+        raise IndexError("index 0 is out of bounds for dimension 0 with size 0")
+    if heads.min() < 0 or heads.max() >= num_nodes:
+        raise IndexError(f"head id out of range for an index with {num_nodes} rows")
+    index = np.full((num_nodes, 2), -1, dtype=np.int64)
+    starts = np.flatnonzero(np.r_[True, heads[1:] != heads[:-1]])
+    ends = np.r_[starts[1:] - 1, num_rows - 1]
+    index[heads[starts], 0] = starts
+    index[heads[starts], 1] = ends
+    if num_rows == 1:
+        index[heads[0], 1] = -1
+    return torch.from_numpy(index).contiguous()
+
+
+def build_node_edge_index(edge_list_indexed, nodes_tensor):
+    """(edge_list_indexed[E,2], node ids) -> (node_edge_index[N,2], edge list sorted by head).
+    Reference: torch_rw/utils.py:58-89.  N = number of distinct ids in nodes_tensor."""
+    rows = np.ascontiguousarray(torch.as_tensor(edge_list_indexed).cpu().numpy()).astype(np.int64, copy=False)
+    rows = _sort_rows_by_head(rows.reshape(-1, 2))
+    num_nodes = int(torch.unique(torch.as_tensor(nodes_tensor)).numel())
+    node_edge_index = _head_ranges(rows[:, 0], num_nodes)
+    return node_edge_index, torch.from_numpy(np.ascontiguousarray(rows)).contiguous()
+
+
+def build_relation_tail_index(triples_indexed_tensor, all_entities_tensor):
+    """(triples[T,3], entity ids) -> (relation_tail_index[N,2], triples sorted by head).
+    Reference: torch_rw/utils.py:91-120.  N = len(all_entities_tensor) (not de-duplicated, as in
+    the reference); float inputs are truncated to int64 after sorting, like `.to(int)` there."""
+    raw = np.ascontiguousarray(torch.as_tensor(triples_indexed_tensor).cpu().numpy()).reshape(-1, 3)
+    rows = _sort_rows_by_head(raw).astype(np.int64)
+    num_nodes = int(torch.as_tensor(all_entities_tensor).numel())
+    relation_tail_index = _head_ranges(rows[:, 0], num_nodes)
+    return relation_tail_index, torch.from_numpy(np.ascontiguousarray(rows)).contiguous()
