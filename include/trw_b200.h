@@ -167,6 +167,15 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
                      int loads_per_thread, int bytes_per_load, int64_t seed, int64_t* sink,
                      int device, void* stream);
 
+/* With option "time_kernels" = 1 the CSR walk brackets its table build (memset + build kernel)
+ * and its walk kernel with CUDA events on the launch stream; this waits for the last such call
+ * and returns both durations in milliseconds (0 when that phase did not run). */
+int trw_last_kernel_ms(float* build_ms, float* walk_ms);
+
+/* out[0..5] = SM count, L2 bytes, max persisting-L2 bytes, max access-policy window bytes,
+ * current L2 fetch granularity, max opt-in shared memory per block. */
+int trw_device_info(int device, int64_t* out, int n_out);
+
 /* Tuning knobs for experiments ("name" -> integer); returns TRW_ERR_ARG for unknown names.
  * Defaults are the shipped configuration; bench.py records any override it applies. */
 int trw_set_option(const char* name, int64_t value);

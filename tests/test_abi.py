@@ -1,0 +1,109 @@
+"""The drop-in boundary without a GPU: libtrw_b200.so loads, exports every symbol that
+include/trw_b200.h declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "trw_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(trw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from torch_random_walk_b200 import native
+
+    lib = native.lib()
+    names = declared_symbols()
+    assert len(names) >= 16
+    for name in names:
+        assert getattr(lib, name) is not None, name
+    assert lib.trw_abi_version() == 1
+
+
+def test_library_has_no_torch_or_oracle_dependency():
+    from torch_random_walk_b200 import native
+
+    out = os.popen(f"ldd {native.LIB_PATH}").read()
+    assert "torch" not in out and "oracle" not in out and "c10" not in out
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "torch_random_walk_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_reference_signatures_are_kept():
+    import inspect
+
+    from torch_random_walk_b200 import rw
+
+    # /root/reference/torch_rw/rw.py:3-39
+    expect = {
+        "walk": ["row_ptr", "col_idx", "target_nodes", "p", "q", "walk_length", "seed"],
+        "walk_edge_list": ["edge_list_indexed", "node_edge_index", "target_nodes", "p", "q", "walk_length", "seed",
+                           "padding_idx", "restart"],
+        "walk_triples": ["triples_indexed", "relation_tail_index", "target_nodes", "walk_length", "padding_idx", "seed",
+                         "restart"],
+        "to_windows": ["walks", "window_size", "num_nodes", "seed"],
+        "to_windows_cbow": ["walks", "window_size", "num_nodes", "seed"],
+        "to_windows_triples": ["walks", "window_size", "num_nodes", "padding_idx", "triples", "seed"],
+        "to_windows_triples_cbow": ["walks", "window_size", "num_nodes", "padding_idx", "triples", "seed"],
+    }
+    for name, params in expect.items():
+        assert list(inspect.signature(getattr(rw, name)).parameters) == params, name
+    assert inspect.signature(rw.walk_edge_list).parameters["restart"].default is True
+    assert inspect.signature(rw.walk_triples).parameters["restart"].default is True
+    import torch_rw.rw as shim  # the reference's import path
+    import torch_rw_native
+
+    assert shim.walk is rw.walk and callable(torch_rw_native.to_windows_triples_cbow)
+
+
+def test_cpu_tensors_raise_like_check_cuda():
+    from torch_random_walk_b200 import rw
+
+    z = torch.zeros(3, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):  # csrc/cuda/utils.cuh:7
+        rw.walk(z, z, z, 1.0, 1.0, 3, 1)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        rw.to_windows(torch.zeros((2, 5), dtype=torch.int64), 3, 10, 1)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        rw.walk_triples(z.view(1, 3), z.view(1, 3)[:, :2], z, 2, 9, 1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_device_means_error_not_fallback():
+    from torch_random_walk_b200 import native
+
+    lib = native.lib()
+    assert lib.trw_device_check(0) == -2  # TRW_ERR_DEVICE
+    assert b"no CPU fallback" in lib.trw_last_error()
+    buf = (ctypes.c_int64 * 8)()
+    rc = lib.trw_walk_csr(buf, buf, 1, 1, buf, 1, 0, 1.0, 1.0, 2, 1, buf, 3, None, 0, 0, None)
+    assert rc == -2
+    rc = lib.trw_windows(buf, 1, 4, 2, 5, 1, buf, buf, buf, 0, None)
+    assert rc == -2
+
+
+def test_argument_validation_precedes_device_use():
+    from torch_random_walk_b200 import native
+
+    lib = native.lib()
+    buf = (ctypes.c_int64 * 8)()
+    assert lib.trw_walk_csr(buf, buf, 1, 1, buf, -1, 0, 1.0, 1.0, 2, 1, buf, 3, None, 0, 0, None) == -1
+    assert lib.trw_walk_csr(buf, buf, 1, 1, buf, 1, 0, 1.0, 1.0, 2, 1, buf, 2, None, 0, 0, None) == -1  # stride < L+1
+    assert lib.trw_set_option(b"no_such_option", 1) == -1
+    assert lib.trw_get_option(b"stage_output") in (0, 1)
+    assert lib.trw_walk_csr_workspace_bytes(10, 100, 1.0, 1.0) == 0
+    assert lib.trw_walk_csr_workspace_bytes(10, 100, 0.5, 2.0) >= 100 * 8

@@ -1,0 +1,170 @@
+"""Edge-list and triple walks on the GPU against the reference's conventions: RNG-free rows are
+bit-exact with the reference's goldens, the rest is checked structurally and statistically against
+the oracle (for the second-order edge-list walk the oracle IS the specification: its acceptance
+rule deviates from analytic node2vec)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import chi2_pvalue, second_order_counts, toy_graph, two_sample_chi2
+from torch_random_walk_b200 import utils
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rw():
+    from torch_random_walk_b200 import rw as _rw
+
+    return _rw
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _toy(directed):
+    el, mapping = utils.to_edge_list_indexed(toy_graph(directed))
+    targets = torch.tensor(list(mapping.values()), dtype=torch.int64)
+    nei, el_sorted = utils.build_node_edge_index(el, torch.unique(el.view(-1)))
+    return el_sorted, nei, targets, sorted(targets.tolist())[-1] + 1
+
+
+def _check_edge_list_walks(walks, el, nei, targets, pad, restart):
+    w = walks.cpu().numpy()
+    el, nei = el.numpy(), nei.numpy()
+    succ = {}
+    for h, t in el.tolist():
+        succ.setdefault(h, set()).add(t)
+    assert np.array_equal(w[:, 0], targets.numpy())
+    for row in w:
+        jump = row[0] if restart else pad
+        for a, b in zip(row[:-1], row[1:]):
+            if a == pad:
+                assert b == jump
+            elif a not in succ:
+                assert b == pad
+            else:
+                assert b in succ[a]
+
+
+def test_uniform_edge_list_known_rows(rw):
+    # /root/reference/tests/test_rw_edge_list.py:115-223: rows of nodes 2 (no out-edge) and 3 (one out-edge) are RNG-free
+    el, nei, targets, pad = _toy(directed=True)
+    walks = rw.walk_edge_list(edge_list_indexed=el.cuda(), node_edge_index=nei.cuda(), target_nodes=targets.cuda(),
+                              p=1.0, q=1.0, walk_length=6, seed=10, padding_idx=pad)
+    assert walks.shape == (5, 7)
+    assert walks[2].tolist() == [2, 5, 2, 5, 2, 5, 2] and walks[3].tolist() == [3, 2, 5, 3, 2, 5, 3]
+    _check_edge_list_walks(walks, el, nei, targets, pad, True)
+    walks = rw.walk_edge_list(el.cuda(), nei.cuda(), targets.cuda(), 1.0, 1.0, 6, 10, pad, restart=False)
+    assert walks[2].tolist() == [2, 5, 5, 5, 5, 5, 5] and walks[3].tolist() == [3, 2, 5, 5, 5, 5, 5]
+    _check_edge_list_walks(walks, el, nei, targets, pad, False)
+    for row in walks.tolist():  # no restart: once padded, padded for ever
+        if pad in row:
+            k = row.index(pad)
+            assert all(x == pad for x in row[k:])
+
+
+@pytest.mark.parametrize("restart", [True, False])
+def test_biased_edge_list_known_rows_and_structure(rw, restart):
+    # :436-546: with restart the biased walk emits the start node instead of the padding
+    el, nei, targets, pad = _toy(directed=True)
+    walks = rw.walk_edge_list(el.cuda(), nei.cuda(), targets.cuda(), 0.7, 0.2, 6, 20, pad, restart=restart)
+    if restart:
+        assert walks[2].tolist() == [2, 5, 2, 5, 2, 5, 2] and walks[3].tolist() == [3, 2, 3, 2, 3, 2, 3]
+    else:
+        assert walks[2].tolist() == [2, 5, 5, 5, 5, 5, 5] and walks[3].tolist() == [3, 2, 5, 5, 5, 5, 5]
+
+
+def test_undirected_edge_list_structure(rw):
+    el, nei, targets, pad = _toy(directed=False)
+    for p, q in ((1.0, 1.0), (0.7, 0.2)):
+        walks = rw.walk_edge_list(el.cuda(), nei.cuda(), targets.cuda(), p, q, 6, 10, pad)
+        assert int(walks.max()) < pad
+        _check_edge_list_walks(walks, el, nei, targets, pad, True)
+
+
+@pytest.mark.parametrize("p,q,restart", [(0.7, 0.2, True), (0.5, 2.0, True), (2.0, 0.5, False)])
+def test_biased_edge_list_statistics_match_oracle(rw, orc, p, q, restart):
+    g = torch.Generator().manual_seed(5)
+    n = 24
+    el = torch.stack((torch.randint(0, n - 2, (120,), generator=g), torch.randint(0, n, (120,), generator=g)), 1)
+    nei, el_sorted = utils.build_node_edge_index(el, torch.arange(n + 1))  # nodes n-2, n-1: dead ends; row n: padding
+    pad = n
+    targets = torch.arange(n).repeat_interleave(4000)
+    L = 12
+    got = rw.walk_edge_list(el_sorted.cuda(), nei.cuda(), targets.cuda(), p, q, L, 3, pad, restart=restart)
+    ref = orc.walk_edge_list(el_sorted, nei, targets, p, q, L, 3, pad, restart)
+    assert got.shape == ref.shape
+    a, b = second_order_counts(got, n + 1), second_order_counts(ref, n + 1)
+    chi2, dof = two_sample_chi2(a, b, n + 1)
+    assert dof > 50
+    assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
+    # first-order marginals as well
+    f = lambda w: dict(zip(*np.unique(w.cpu().numpy()[:, 1].astype(np.int64) + (n + 1) * w.cpu().numpy()[:, 0], return_counts=True)))  # noqa: E731
+    fa, fb = f(got), f(ref)
+    assert set(fa) == set(fb)
+
+
+def test_edge_list_matches_reference_golden_dead_ends(rw, golden):
+    # rows that never branch are RNG-free: compare them with the reference's own output
+    for case in range(2):
+        p, q, L, seed, pad, restart = golden[f"walk_el/rand{case}/params"]
+        el, nei = T(golden[f"walk_el/rand{case}/edge_list_sorted"]), T(golden[f"walk_el/rand{case}/node_edge_index"])
+        ref = golden[f"walk_el/rand{case}/walks"]
+        got = rw.walk_edge_list(el.cuda(), nei.cuda(), torch.arange(int(pad)).cuda(), float(p), float(q), int(L),
+                                int(seed), int(pad), bool(restart)).cpu().numpy()
+        count = (nei[:, 1] - nei[:, 0] + 1).numpy()
+        count[nei[:, 0].numpy() < 0] = 0
+        checked = 0
+        for row_ref, row_got in zip(ref, got):
+            # deterministic as long as every visited node has at most one out-edge
+            det = True
+            for k, v in enumerate(row_ref):
+                if not det:
+                    break
+                assert row_got[k] == v
+                checked += 1
+                if v != int(pad) and count[v] > 1:
+                    det = False
+        assert checked > len(ref)
+
+
+def test_triple_walk_known_rows_and_structure(rw, golden):
+    # /root/reference/tests/test_rw_triples.py:84-159; entity 4 has no outgoing triple -> all padding
+    rti, trs = T(golden["utils/toy_triples/relation_tail_index"]), T(golden["utils/toy_triples/triples_sorted"])
+    targets = T(golden["utils/toy_triples/entities"]).repeat_interleave(2, 0)
+    walks = rw.walk_triples(triples_indexed=trs.cuda(), relation_tail_index=rti.cuda(), target_nodes=targets.cuda(),
+                            walk_length=6, seed=10, padding_idx=8, restart=False)
+    assert walks.shape == (10, 13)
+    assert walks[8].tolist() == [4] + [8] * 12 and walks[9].tolist() == [4] + [8] * 12
+    triple_set = set(map(tuple, trs.tolist()))
+    for row in walks.tolist():
+        for k in range(0, 12, 2):
+            h, r, t = row[k], row[k + 1], row[k + 2]
+            if h == 8 or not any(x[0] == h for x in triple_set):
+                assert (r, t) == (8, 8)
+            else:
+                assert (h, r, t) in triple_set
+
+
+def test_triple_walk_statistics_match_oracle(rw, orc, golden):
+    trs, rti = T(golden["utils/rand_tr3/triples_sorted"]), T(golden["utils/rand_tr3/relation_tail_index"])
+    n = rti.size(0)
+    pad = n + 7
+    targets = torch.arange(n).repeat_interleave(300)
+    got = rw.walk_triples(trs.cuda(), rti.cuda(), targets.cuda(), 5, pad, 9, restart=False).cpu().numpy()
+    ref = orc.walk_triples(trs, rti, targets, 5, pad, 9, restart=False).numpy()
+    # first hop: (head, rel, tail) frequencies
+    key = lambda w: dict(zip(*np.unique((w[:, 0] * (pad + 1) + w[:, 1]) * (pad + 1) + w[:, 2], return_counts=True)))  # noqa: E731
+    a, b = key(got), key(ref)
+    assert set(a) == set(b)
+    cells = sorted(a)
+    ca, cb = np.array([a[c] for c in cells], float), np.array([b[c] for c in cells], float)
+    chi2 = float(((ca - cb) ** 2 / (ca + cb)).sum())
+    assert chi2_pvalue(chi2, len(cells) - n) > 0.01
+    # padding propagates
+    for row in got[:2000]:
+        if pad in row[1:]:
+            k = list(row[1:]).index(pad) + 1
+            assert all(x == pad for x in row[k:])

@@ -1,0 +1,88 @@
+"""Host-side graph preparation (torch_random_walk_b200.utils) against the reference's own
+torch_rw/utils.py outputs (tests/golden/ref_golden.npz) and its tests' known answers.  CPU only."""
+import networkx as nx
+import numpy as np
+import pytest
+import torch
+
+from helpers import toy_graph
+from torch_random_walk_b200 import utils
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+@pytest.mark.parametrize("name,graph", [("toy_undirected", toy_graph(False)), ("toy_directed", toy_graph(True)),
+                                        ("karate", nx.karate_club_graph())])
+def test_to_csr_and_nodes_tensor(golden, name, graph):
+    row_ptr, col_idx = utils.to_csr(graph)
+    nodes = utils.nodes_tensor(graph)
+    for t in (row_ptr, col_idx, nodes):
+        assert t.dtype == torch.int64 and t.is_contiguous() and t.device.type == "cpu"
+    assert np.array_equal(row_ptr.numpy(), golden[f"utils/{name}/row_ptr"])
+    assert np.array_equal(col_idx.numpy(), golden[f"utils/{name}/col_idx"])
+    assert np.array_equal(nodes.numpy(), golden[f"utils/{name}/nodes"])
+
+
+def test_karate_is_baseline_config_1(golden):
+    # BASELINE.json configs[0]: 34 nodes, 156 CSR entries
+    assert golden["utils/karate/row_ptr"].shape == (35,) and golden["utils/karate/col_idx"].shape == (156,)
+
+
+def test_to_csr_exact_above_2_pow_24():
+    # the reference's float32 round trip (torch_rw/utils.py:7-8) loses ids above 2^24; ours must not
+    g = nx.Graph()
+    g.add_nodes_from(range(3))
+    g.add_edge(0, 2)
+    row_ptr, col_idx = utils.to_csr(g)
+    assert row_ptr.tolist() == [0, 1, 1, 2] and col_idx.tolist() == [2, 0]
+
+
+@pytest.mark.parametrize("name,directed", [("toy_undirected", False), ("toy_directed", True)])
+def test_edge_list_indexed_and_node_edge_index(golden, name, directed):
+    el, mapping = utils.to_edge_list_indexed(toy_graph(directed))
+    assert np.array_equal(el.numpy(), golden[f"utils/{name}/edge_list"])
+    assert list(mapping.keys()) == golden[f"utils/{name}/mapping_keys"].tolist()
+    assert list(mapping.values()) == golden[f"utils/{name}/mapping_values"].tolist()
+    nei, el_sorted = utils.build_node_edge_index(el, torch.unique(el.view(-1)))
+    assert np.array_equal(nei.numpy(), golden[f"utils/{name}/node_edge_index"])
+    assert np.array_equal(el_sorted.numpy(), golden[f"utils/{name}/edge_list_sorted"])
+
+
+def test_node_edge_index_known_answers():
+    # /root/reference/tests/test_rw_edge_list.py:31-35 and :246-250
+    el, _ = utils.to_edge_list_indexed(toy_graph(True))
+    nei, _ = utils.build_node_edge_index(el, torch.unique(el.view(-1)))
+    assert nei.tolist() == [[0, 1], [2, 3], [-1, -1], [4, 4], [5, 6]]
+    el, _ = utils.to_edge_list_indexed(toy_graph(False))
+    nei, _ = utils.build_node_edge_index(el, torch.unique(el.view(-1)))
+    assert nei.tolist() == [[0, 2], [3, 5], [6, 8], [9, 11], [12, 13]]
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_random_indices_match_reference(golden, case):
+    el = T(golden[f"utils/rand_el{case}/edge_list"])
+    n = int(golden[f"utils/rand_el{case}/num_nodes"])
+    nei, el_sorted = utils.build_node_edge_index(el, torch.arange(n))
+    assert np.array_equal(nei.numpy(), golden[f"utils/rand_el{case}/node_edge_index"])
+    assert np.array_equal(el_sorted.numpy(), golden[f"utils/rand_el{case}/edge_list_sorted"])
+    tr = T(golden[f"utils/rand_tr{case}/triples"])
+    rti, tr_sorted = utils.build_relation_tail_index(tr, torch.arange(n))
+    assert np.array_equal(rti.numpy(), golden[f"utils/rand_tr{case}/relation_tail_index"])
+    assert np.array_equal(tr_sorted.numpy(), golden[f"utils/rand_tr{case}/triples_sorted"])
+
+
+def test_relation_tail_index_known_answer(golden):
+    # /root/reference/tests/test_rw_triples.py:26-53 (float32 triples in, int64 out)
+    triples = T(golden["utils/toy_triples/triples"])
+    assert triples.dtype == torch.float32
+    rti, tr_sorted = utils.build_relation_tail_index(triples, T(golden["utils/toy_triples/entities"]))
+    assert rti.tolist() == [[0, 2], [3, 3], [4, 5], [6, 7], [-1, -1]]
+    assert tr_sorted.dtype == torch.int64
+    assert np.array_equal(tr_sorted.numpy(), golden["utils/toy_triples/triples_sorted"])
+
+
+def test_empty_edge_list_raises_like_reference():
+    with pytest.raises(IndexError):
+        utils.build_node_edge_index(torch.zeros((0, 2), dtype=torch.int64), torch.arange(3))

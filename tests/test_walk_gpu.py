@@ -1,0 +1,265 @@
+"""Parity of the CUDA CSR walk (rw.walk -> trw_walk_csr) with the reference's algorithm.
+
+The reference draws from a different RNG, so parity is what BASELINE.json's north_star defines:
+structure (column 0, every transition an edge, the dead-end convention), reproducibility, and
+second-order transition statistics against BOTH the analytic node2vec law and the oracle's own
+empirical frequencies (chi-square p > 0.01, pooled total variation < 1e-2 at 1e7 samples)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (check_walks_follow_edges, chi2_and_tv, chi2_pvalue, node2vec_probs, random_csr,
+                     second_order_counts, two_sample_chi2)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rw():
+    from torch_random_walk_b200 import rw as _rw
+
+    return _rw
+
+
+@pytest.fixture(scope="module")
+def native():
+    from torch_random_walk_b200 import native as _n
+
+    return _n
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def cuda(*ts):
+    return [t.cuda() for t in ts]
+
+
+def test_native_library_is_the_one_loaded(native):
+    maps = open("/proc/self/maps").read()
+    assert "libtrw_b200.so" in maps
+    assert native.lib().trw_device_check(0) == 0
+
+
+def test_toy_graph_shapes_and_structure(rw, golden):
+    # the call of /root/reference/tests/test_rw.py:79 and :146 (uniform / biased on GPU)
+    rp, ci, nodes = cuda(T(golden["utils/toy_undirected/row_ptr"]), T(golden["utils/toy_undirected/col_idx"]),
+                         torch.arange(5))
+    for p, q in ((1.0, 1.0), (0.7, 0.5)):
+        walks = rw.walk(row_ptr=rp, col_idx=ci, target_nodes=nodes, p=p, q=q, walk_length=6, seed=10)
+        assert walks.shape == (5, 7) and walks.dtype == torch.int64 and walks.is_cuda and walks.is_contiguous()
+        check_walks_follow_edges(walks, rp, ci, nodes)
+
+
+def test_karate_config1(rw, golden):
+    # BASELINE.json configs[0]: karate club, p=q=1, walk_length=80, 10 walks per node
+    rp, ci = cuda(T(golden["utils/karate/row_ptr"]), T(golden["utils/karate/col_idx"]))
+    nodes = T(golden["utils/karate/nodes"]).repeat_interleave(10).cuda()
+    walks = rw.walk(rp, ci, nodes, 1.0, 1.0, 80, 10)
+    assert walks.shape == golden["walk/karate_uniform_L80"].shape == (340, 81)
+    check_walks_follow_edges(walks, rp, ci, nodes)
+
+
+@pytest.mark.parametrize("p,q", [(1.0, 1.0), (0.5, 2.0), (1.0, 0.5), (0.25, 4.0), (2.0, 1.0)])
+def test_reproducible_and_seed_sensitive(rw, p, q):
+    rp, ci = cuda(*random_csr(1, 3000, 24))
+    nodes = torch.arange(3000, device="cuda")
+    a = rw.walk(rp, ci, nodes, p, q, 40, 123)
+    b = rw.walk(rp, ci, nodes, p, q, 40, 123)
+    c = rw.walk(rp, ci, nodes, p, q, 40, 124)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    check_walks_follow_edges(a, rp, ci, nodes)
+
+
+@pytest.mark.parametrize("p,q", [(1.0, 1.0), (0.5, 2.0)])
+def test_shards_are_bit_identical_to_one_call(native, p, q):
+    # what makes 1/2/4/8-GPU output identical: Philox is keyed by the GLOBAL walk id
+    rp, ci = cuda(*random_csr(2, 5000, 20))
+    nodes = torch.randint(0, 5000, (20001,), device="cuda")
+    full = native.walk(rp, ci, nodes, p, q, 30, 7)
+    for world in (2, 3, 8):
+        from torch_random_walk_b200.dist import shard_bounds
+
+        parts = []
+        for r in range(world):
+            lo, hi = shard_bounds(nodes.numel(), r, world)
+            parts.append(native.walk(rp, ci, nodes[lo:hi].contiguous(), p, q, 30, 7, walk_id_offset=lo))
+        assert torch.equal(torch.cat(parts), full), world
+
+
+def test_kernel_variants_agree_bit_for_bit(native):
+    """Hashed membership table vs the reference's linear scan, speculative row fetch on/off and
+    staged vs plain stores must not change a single entry: same draws, same decisions."""
+    rp, ci = random_csr(3, 4000, 60)  # mean degree 60: most rows use the table (>= 16 neighbours)
+    rp, ci = cuda(rp, ci)
+    nodes = torch.arange(4000, device="cuda")
+    base = None
+    try:
+        for table in (1, 0):
+            for spec in (1, 0):
+                for stage in (1, 0):
+                    native.set_option("n2v_table", table)
+                    native.set_option("n2v_speculate", spec)
+                    native.set_option("stage_output", stage)
+                    w = native.walk(rp, ci, nodes, 0.5, 2.0, 25, 99)
+                    u = native.walk(rp, ci, nodes, 1.0, 1.0, 25, 99)
+                    if base is None:
+                        base = (w, u)
+                    assert torch.equal(w, base[0]), (table, spec, stage)
+                    assert torch.equal(u, base[1]), (table, spec, stage)
+    finally:
+        for k in ("n2v_table", "n2v_speculate", "stage_output"):
+            native.set_option(k, 1)
+
+
+def test_unsorted_rows_and_duplicate_edges(native):
+    # the API does not promise sorted or duplicate-free rows; membership must not depend on either
+    rp, ci = random_csr(4, 1500, 40, sort_rows=False)
+    rp_np, ci_np = rp.numpy(), ci.numpy().copy()
+    # duplicate the first neighbour of every row with >= 2 entries into its second slot
+    for v in range(1500):
+        if rp_np[v + 1] - rp_np[v] >= 2:
+            ci_np[rp_np[v] + 1] = ci_np[rp_np[v]]
+    rp, ci = cuda(rp, T(ci_np))
+    nodes = torch.arange(1500, device="cuda")
+    a = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+    native.set_option("n2v_table", 0)
+    try:
+        b = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+    finally:
+        native.set_option("n2v_table", 1)
+    assert torch.equal(a, b)
+    check_walks_follow_edges(a, rp, ci, nodes)
+
+
+def test_dead_end_and_isolated_nodes_stay(rw):
+    # convention of csrc/cuda/rw_cuda.cu:25-30: no out-edge -> the walk stays on the node
+    # 0 -> 1 -> 2 (sink), 3 isolated, 4 -> 0
+    rp = torch.tensor([0, 1, 2, 2, 2, 3], dtype=torch.int64).cuda()
+    ci = torch.tensor([1, 2, 0], dtype=torch.int64).cuda()
+    nodes = torch.arange(5, device="cuda")
+    for p, q in ((1.0, 1.0), (0.5, 2.0)):
+        w = rw.walk(rp, ci, nodes, p, q, 6, 3).cpu()
+        assert w[0].tolist() == [0, 1, 2, 2, 2, 2, 2]
+        assert w[2].tolist() == [2] * 7
+        assert w[3].tolist() == [3] * 7
+        assert w[4].tolist() == [4, 0, 1, 2, 2, 2, 2]
+
+
+def test_edge_cases(rw, native):
+    rp, ci = cuda(*random_csr(5, 100, 6))
+    empty = torch.empty(0, dtype=torch.int64, device="cuda")
+    assert rw.walk(rp, ci, empty, 1.0, 1.0, 5, 1).shape == (0, 6)
+    assert rw.walk(rp, ci, empty, 0.5, 2.0, 5, 1).shape == (0, 6)
+    nodes = torch.arange(100, device="cuda")
+    for p, q in ((1.0, 1.0), (0.5, 2.0)):
+        for L in (0, 1, 2, 3, 4, 5):
+            w = rw.walk(rp, ci, nodes, p, q, L, 1)
+            assert w.shape == (100, L + 1)
+            check_walks_follow_edges(w, rp, ci, nodes)
+    # output rows that do not start on a sector boundary: write into a strided, offset view
+    big = torch.full((100, 13), -7, dtype=torch.int64, device="cuda")
+    out = big[:, 1:10]
+    native.walk(rp, ci, nodes, 0.5, 2.0, 8, 11, out=out)
+    ref = native.walk(rp, ci, nodes, 0.5, 2.0, 8, 11)
+    assert torch.equal(out, ref)
+    assert (big[:, 0] == -7).all() and (big[:, 10:] == -7).all()
+    with pytest.raises(RuntimeError, match="Long"):
+        rw.walk(rp.int(), ci, nodes, 1.0, 1.0, 3, 1)
+    # non-contiguous inputs are accepted (the reference reads through strided accessors)
+    w = rw.walk(rp, ci, torch.arange(200, device="cuda")[::2], 1.0, 1.0, 4, 1)
+    check_walks_follow_edges(w, rp, ci, torch.arange(200, device="cuda")[::2])
+
+
+def test_first_order_transitions_are_uniform(rw, golden):
+    rp, ci = T(golden["utils/karate/row_ptr"]), T(golden["utils/karate/col_idx"])
+    n = 34
+    nodes = torch.arange(n).repeat_interleave(3000)
+    walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), 1.0, 1.0, 80, 17).cpu().numpy()
+    a, b = walks[:, :-1].ravel(), walks[:, 1:].ravel()
+    deg = np.diff(rp.numpy())
+    keys, counts = np.unique(a.astype(np.int64) * n + b, return_counts=True)
+    visits = np.bincount(a, minlength=n)
+    expected = visits[keys // n] / deg[keys // n]
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    dof = len(keys) - n
+    assert len(keys) == 156  # every edge of the karate club is used
+    assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
+
+
+@pytest.mark.parametrize("p,q", [(0.5, 2.0), (0.25, 4.0), (1.0, 0.5)])
+def test_second_order_statistics_match_analytic_and_oracle(rw, orc, golden, p, q):
+    """North-star criterion: chi-square p > 0.01 and pooled TV < 1e-2 at 1e7 samples, against the
+    analytic node2vec probabilities and against the reference algorithm's own empirical counts."""
+    rp, ci = T(golden["utils/karate/row_ptr"]), T(golden["utils/karate/col_idx"])
+    n = 34
+    table = node2vec_probs(rp, ci, p, q)
+    L = 100
+    reps = 3000  # 34 * 3000 walks * 99 second-order transitions = 1.0e7 samples
+    nodes = torch.arange(n).repeat_interleave(reps)
+    walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, L, 2024)
+    check_walks_follow_edges(walks, rp, ci, nodes)
+    got = second_order_counts(walks, n)
+    assert sum(got.values()) >= 10_000_000
+    chi2, dof, tv = chi2_and_tv(got, table, n)
+    assert chi2_pvalue(chi2, dof) > 0.01, ("analytic", chi2, dof)
+    assert tv < 1e-2, tv
+    # the oracle (reference algorithm, glibc rand) on a third of the samples
+    ref_walks = orc.walk(rp, ci, torch.arange(n).repeat_interleave(1000), p, q, L, 7)
+    ref_counts = second_order_counts(ref_walks, n)
+    chi2_o, dof_o, tv_o = chi2_and_tv(ref_counts, table, n)
+    assert tv_o < 1e-2  # the oracle itself is a faithful node2vec sampler
+    chi2_2, dof_2 = two_sample_chi2(got, ref_counts, n)
+    assert chi2_pvalue(chi2_2, dof_2) > 0.01, ("vs oracle", chi2_2, dof_2)
+
+
+def test_second_order_statistics_with_table_rows(rw, orc):
+    """Same criterion on a graph whose rows are long enough (>= 16) to go through the hashed
+    membership table, with triangles so that all three acceptance classes occur."""
+    rp, ci = random_csr(11, 60, 30)
+    n = 60
+    assert int((rp[1:] - rp[:-1]).min()) >= 16
+    p, q = 0.5, 2.0
+    table = node2vec_probs(rp, ci, p, q)
+    nodes = torch.arange(n).repeat_interleave(2000)
+    walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, 100, 5)
+    got = second_order_counts(walks, n)
+    chi2, dof, tv = chi2_and_tv(got, table, n)
+    assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
+    assert tv < 1e-2
+    ref_counts = second_order_counts(orc.walk(rp, ci, torch.arange(n).repeat_interleave(300), p, q, 100, 3), n)
+    chi2_2, dof_2 = two_sample_chi2(got, ref_counts, n)
+    assert chi2_pvalue(chi2_2, dof_2) > 0.01, (chi2_2, dof_2)
+
+
+def test_large_graph_structure_and_hubs(rw):
+    """A skewed graph (R-MAT scale 16) at a size where hubs, the table build's tile logic and many
+    CTAs are all exercised; size-independent property: every transition is an edge."""
+    from torch_random_walk_b200 import rmat
+
+    rp, ci = rmat.rmat_csr(16, 16, device="cuda", seed=3)
+    deg = rp[1:] - rp[:-1]
+    assert int(deg.max()) > 1000 and int((deg == 0).sum()) > 0
+    nodes = torch.nonzero(deg > 0).flatten()
+    for p, q in ((1.0, 1.0), (1.0, 0.5), (0.5, 2.0)):
+        w = rw.walk(rp, ci, nodes, p, q, 20, 1)
+        check_walks_follow_edges(w, rp, ci, nodes)
+    # isolated start nodes stay put
+    iso = torch.nonzero(deg == 0).flatten()[:100]
+    w = rw.walk(rp, ci, iso, 1.0, 0.5, 5, 1)
+    assert torch.equal(w, iso[:, None].expand(-1, 6))
+
+
+def test_walk_host_matches_device_path(native):
+    rp, ci = random_csr(8, 3000, 20)
+    nodes = torch.randint(0, 3000, (10000,))
+    native.set_option("host_chunk_walks", 3000)  # force several pipelined chunks
+    try:
+        for p, q in ((1.0, 1.0), (0.5, 2.0)):
+            host = native.walk_host(rp, ci, nodes, p, q, 16, 42, device=0)
+            dev = native.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, 16, 42)
+            assert host.device.type == "cpu" and torch.equal(host, dev.cpu())
+    finally:
+        native.set_option("host_chunk_walks", 1 << 20)

@@ -1,0 +1,142 @@
+"""Window generation on the GPU: positives/targets bit-exact against the oracle and the reference's
+goldens (they are RNG-free); negatives checked for the reference's support and constraints."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rw():
+    from torch_random_walk_b200 import rw as _rw
+
+    return _rw
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def I(rows):
+    return torch.tensor(rows, dtype=torch.int64)
+
+
+def test_known_answers_of_the_reference_gpu_tests(rw):
+    # /root/reference/tests/test_windows.py:58-119 (positives identical to the CPU tests :14-20, :44-51)
+    torch.manual_seed(20)
+    walks = torch.randint(low=0, high=30, size=(3, 10)).cuda()
+    target, pos, neg = rw.to_windows(walks=walks, window_size=5, num_nodes=30, seed=20)
+    assert target.size(0) == 6 * 3
+    pos_expected = I([[11, 10, 13, 24], [10, 27, 24, 20], [27, 13, 20, 13], [13, 24, 13, 6], [24, 20, 6, 27],
+                      [20, 13, 27, 0]]).cuda()
+    assert torch.equal(target[:6], I([27, 13, 24, 20, 13, 6]).cuda())
+    assert torch.equal(pos[:6], pos_expected)
+    assert neg.shape == pos.shape and int(neg.min()) >= 0 and int(neg.max()) < 30
+    pos_nodes, neg_nodes, windows = rw.to_windows_cbow(walks=walks, window_size=5, num_nodes=30, seed=20)
+    assert torch.equal(pos_nodes[:6], I([27, 13, 24, 20, 13, 6]).cuda())
+    assert torch.equal(windows[:6], pos_expected)
+    assert bool((neg_nodes != pos_nodes).all())
+    # :183-240 and :288-329 (triples; [10,10,27] pins the reference's head-slot quirk)
+    torch.manual_seed(20)
+    twalks = torch.randint(low=0, high=30, size=(3, 21)).cuda()
+    triples = torch.randint(low=0, high=30, size=(10, 3)).cuda()
+    tt, tp, tn = rw.to_windows_triples(walks=twalks, window_size=4, num_nodes=30, padding_idx=-1, triples=triples, seed=20)
+    exp_pos = I([[[-1, -1, 11], [-1, -1, -1], [-1, -1, -1], [-1, -1, -1], [27, 13, 24], [24, 20, 13], [13, 6, 27],
+                  [27, 0, 7]],
+                 [[10, 10, 27], [-1, -1, 11], [-1, -1, -1], [-1, -1, -1], [24, 20, 13], [13, 6, 27], [27, 0, 7],
+                  [7, 14, 20]]]).cuda()
+    assert torch.equal(tt[:2], I([[11, 10, 27], [27, 13, 24]]).cuda())
+    assert torch.equal(tp[:2], exp_pos)
+    ct, cn, cp = rw.to_windows_triples_cbow(walks=twalks, window_size=4, num_nodes=30, padding_idx=-1, triples=triples,
+                                            seed=20)
+    assert torch.equal(ct[:2], I([[11, 10, 27], [27, 13, 24]]).cuda())
+    assert torch.equal(cp[:2], exp_pos)
+
+
+def _rows_of(triples, x):
+    key = lambda t: (t[..., 0] * 1_000_003 + t[..., 1]) * 1_000_003 + t[..., 2]  # noqa: E731
+    return torch.isin(key(x.reshape(-1, 3)), key(triples))
+
+
+def _check_all_variants(rw, orc, walks, triples, W, num_nodes, pad, seed):
+    wc, tc = walks.cuda(), triples.cuda()
+    o_t, o_p, o_n = orc.to_windows(walks, W, num_nodes, seed)
+    g_t, g_p, g_n = rw.to_windows(wc, W, num_nodes, seed)
+    assert torch.equal(g_t.cpu(), o_t) and torch.equal(g_p.cpu(), o_p)
+    assert g_n.shape == o_n.shape
+    if g_n.numel():
+        assert int(g_n.min()) >= 0 and int(g_n.max()) < num_nodes
+    c_p, c_n, c_w = rw.to_windows_cbow(wc, W, num_nodes, seed)
+    oc_p, oc_n, oc_w = orc.to_windows_cbow(walks, W, num_nodes, seed)
+    assert torch.equal(c_p.cpu(), oc_p) and torch.equal(c_w.cpu(), oc_w) and c_n.shape == oc_n.shape
+    if c_n.numel():
+        assert int(c_n.min()) >= 0 and int(c_n.max()) < num_nodes and bool((c_n != c_p).all())
+    t_t, t_p, t_n = rw.to_windows_triples(wc, W, num_nodes, pad, tc, seed)
+    ot_t, ot_p, ot_n = orc.to_windows_triples(walks, W, num_nodes, pad, triples, seed)
+    assert torch.equal(t_t.cpu(), ot_t) and torch.equal(t_p.cpu(), ot_p) and t_n.shape == ot_n.shape
+    if t_n.numel():
+        assert bool(_rows_of(tc, t_n).all())
+    b_t, b_n, b_p = rw.to_windows_triples_cbow(wc, W, num_nodes, pad, tc, seed)
+    ob_t, ob_n, ob_p = orc.to_windows_triples_cbow(walks, W, num_nodes, pad, triples, seed)
+    assert torch.equal(b_t.cpu(), ob_t) and torch.equal(b_p.cpu(), ob_p) and b_n.shape == ob_n.shape
+    if b_n.numel():
+        assert bool(_rows_of(tc, b_n).all())
+        assert bool((b_n != b_t).any(dim=1).all())  # never the positive triple itself
+    for t in (g_t, g_p, g_n, c_p, c_n, c_w, t_t, t_p, t_n, b_t, b_n, b_p):
+        assert t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()
+
+
+def test_positives_match_reference_goldens(rw, orc, golden):
+    for case, (n, wl, W) in enumerate(golden["win/rand_shapes"].tolist()):
+        walks, tri = T(golden[f"win/rand{case}/walks"]), T(golden[f"win/rand{case}/triples"])
+        wc, tc = walks.cuda(), tri.cuda()
+        outs = {"skipgram": rw.to_windows(wc, W, 50, case), "cbow": rw.to_windows_cbow(wc, W, 50, case),
+                "triples_sg": rw.to_windows_triples(wc, W, 50, 77, tc, case),
+                "triples_cbow": rw.to_windows_triples_cbow(wc, W, 50, 77, tc, case)}
+        rng_free = {"skipgram": (0, 1), "cbow": (0, 2), "triples_sg": (0, 1), "triples_cbow": (0, 2)}
+        for name, tensors in outs.items():
+            for k, t in enumerate(tensors):
+                ref = golden[f"win/rand{case}/{name}/{k}"]
+                assert tuple(t.shape) == ref.shape, (case, name, k)
+                if k in rng_free[name]:
+                    assert np.array_equal(t.cpu().numpy(), ref), (case, name, k)
+
+
+@pytest.mark.parametrize("n,wl,W", [(1, 5, 5), (2, 7, 1), (33, 81, 5), (1000, 81, 5), (257, 41, 10), (5, 3001, 7),
+                                    (3, 30001, 3), (64, 13, 6), (511, 21, 4)])
+def test_all_variants_against_oracle(rw, orc, n, wl, W):
+    g = torch.Generator().manual_seed(n * 1000 + wl)
+    walks = torch.randint(0, 500, (n, wl), generator=g)
+    triples = torch.randint(0, 500, (97, 3), generator=g)
+    _check_all_variants(rw, orc, walks, triples, W, 500, 777, seed=wl)
+
+
+def test_deterministic_and_seeded(rw):
+    walks = torch.randint(0, 100, (300, 41), device="cuda")
+    a = rw.to_windows(walks, 5, 100, 1)
+    b = rw.to_windows(walks, 5, 100, 1)
+    c = rw.to_windows(walks, 5, 100, 2)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert torch.equal(a[1], c[1]) and not torch.equal(a[2], c[2])
+    # negatives are roughly uniform over [0, num_nodes)
+    hist = torch.bincount(a[2].flatten(), minlength=100).float()
+    assert float(hist.min()) > 0.8 * float(hist.mean()) and float(hist.max()) < 1.2 * float(hist.mean())
+
+
+def test_cbow_single_node_and_degenerate_triples(rw):
+    walks = torch.zeros((4, 9), dtype=torch.int64, device="cuda")
+    pos, neg, win = rw.to_windows_cbow(walks, 3, 1, 5)  # only node 0 exists: 101 redraws, then the same node
+    assert torch.equal(neg, torch.zeros_like(neg)) and torch.equal(pos, neg)
+    triples = torch.zeros((1, 3), dtype=torch.int64, device="cuda")
+    pt, nt, pw = rw.to_windows_triples_cbow(walks, 2, 1, 9, triples, 5)
+    assert torch.equal(nt, torch.zeros_like(nt))
+
+
+def test_non_contiguous_walks_raise_like_reference(rw):
+    walks = torch.randint(0, 10, (6, 20), device="cuda")[:, ::2]
+    with pytest.raises(RuntimeError, match="contigous"):  # csrc/cuda/utils.cuh:9 spelling
+        rw.to_windows(walks, 3, 10, 1)
+    empty = torch.empty((0, 11), dtype=torch.int64, device="cuda")
+    t, p, n = rw.to_windows(empty, 5, 10, 1)
+    assert t.shape == (0,) and p.shape == (0, 4) and n.shape == (0, 4)

@@ -43,6 +43,22 @@ Options& options() {
     return o;
 }
 
+static cudaEvent_t g_ev[2][2];
+static bool g_ev_used[2];
+
+void timing_begin(int slot, cudaStream_t st) {
+    if (!options().time_kernels) return;
+    for (int k = 0; k < 2; ++k)
+        if (!g_ev[slot][k]) cudaEventCreate(&g_ev[slot][k]);
+    cudaEventRecord(g_ev[slot][0], st);
+}
+
+void timing_end(int slot, cudaStream_t st) {
+    if (!options().time_kernels) return;
+    cudaEventRecord(g_ev[slot][1], st);
+    g_ev_used[slot] = true;
+}
+
 int resolve_device(int device) {
     if (device < 0) {
         if (cudaGetDevice(&device) != cudaSuccess) {
@@ -137,9 +153,44 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
     return check_cuda(cudaGetLastError(), "calib_gather launch");
 }
 
+int trw_last_kernel_ms(float* build_ms, float* walk_ms) {
+    float* dst[2] = {build_ms, walk_ms};
+    for (int slot = 0; slot < 2; ++slot) {
+        if (!dst[slot]) continue;
+        *dst[slot] = 0.0f;
+        if (!g_ev_used[slot]) continue;
+        int rc = check_cuda(cudaEventSynchronize(g_ev[slot][1]), "trw_last_kernel_ms");
+        if (rc) return rc;
+        rc = check_cuda(cudaEventElapsedTime(dst[slot], g_ev[slot][0], g_ev[slot][1]), "trw_last_kernel_ms");
+        if (rc) return rc;
+    }
+    g_ev_used[0] = false;  // a uniform walk leaves the build slot unused
+    return TRW_OK;
+}
+
+int trw_device_info(int device, int64_t* out, int n_out) {
+    if (!out || n_out < 6) { set_error("trw_device_info: need room for 6 values"); return TRW_ERR_ARG; }
+    const int d = resolve_device(device);
+    if (d < 0) return TRW_ERR_DEVICE;
+    DeviceGuard g(d);
+    int v = 0;
+    size_t lim = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); out[0] = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, d); out[1] = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, d); out[2] = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, d); out[3] = v;
+    cudaDeviceGetLimit(&lim, cudaLimitMaxL2FetchGranularity); out[4] = (int64_t)lim;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, d); out[5] = v;
+    cudaGetLastError();
+    return TRW_OK;
+}
+
 int trw_set_option(const char* name, int64_t value) {
     if (!name) return TRW_ERR_ARG;
     Options& o = options();
+    if (!strcmp(name, "l2_fetch_granularity")) {  // device-wide hint: 32, 64 or 128 bytes fetched per L2 miss
+        return check_cuda(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value), "cudaLimitMaxL2FetchGranularity");
+    }
 #define TRW_OPT(field) if (!strcmp(name, #field)) { o.field = value; return TRW_OK; }
     TRW_OPTION_LIST
 #undef TRW_OPT

@@ -1,5 +1,6 @@
 // Process-wide tuning knobs (trw_set_option / trw_get_option).  Defaults = shipped configuration.
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace trw {
@@ -11,15 +12,20 @@ struct Options {
     int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
     int64_t host_chunk_walks = 1 << 20;  // walks per pipelined chunk in trw_walk_csr_host
+    int64_t time_kernels = 0;     // 1: bracket the CSR table build and walk kernel with CUDA events (trw_last_kernel_ms)
 };
 
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
-    TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks)
+    TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels)
 
 Options& options();
 void count_launch(int n);
 // Validates `device` (or the current device when < 0) as an sm_100 part; returns its ordinal or -1.
 int resolve_device(int device);
+
+// Event pairs around the last CSR table build (slot 0) and walk kernel (slot 1) when time_kernels is on.
+void timing_begin(int slot, cudaStream_t st);
+void timing_end(int slot, cudaStream_t st);
 
 }  // namespace trw

@@ -374,10 +374,12 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
         set_error("trw_walk_csr: workspace needs %zu bytes at 256-byte alignment (got %zu)", need, workspace_bytes);
         return TRW_ERR_WORKSPACE;
     }
+    timing_begin(0, st);
     int rc = check_cuda(cudaMemsetAsync(workspace, 0xFF, need, st), "table memset");
     if (rc) return rc;
     const unsigned grid = (unsigned)((nnz + kBuildTile - 1) / kBuildTile);
     build_member_table_kernel<<<grid, kBuildThreads, 0, st>>>(row_ptr, col_idx, n_nodes, nnz, (uint32_t*)workspace);
+    timing_end(0, st);
     count_launch(1);
     rc = check_cuda(cudaGetLastError(), "build_member_table launch");
     if (rc) return rc;
@@ -395,6 +397,7 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
     const bool stage = plan.stage && (((uintptr_t)out & 7) == 0);
     if (plan.persist) set_row_ptr_window(st, a.row_ptr, (size_t)(a.n_nodes + 1) * 8, plan.device, true);
     constexpr int BLOCK = 256;
+    timing_begin(1, st);
     if (plan.uniform) {
         if (stage) launch_uniform<BLOCK, true>(a, st); else launch_uniform<BLOCK, false>(a, st);
     } else if (plan.table) {
@@ -402,6 +405,7 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
     } else {
         if (stage) launch_n2v<BLOCK, true, false>(a, plan.speculate, st); else launch_n2v<BLOCK, false, false>(a, plan.speculate, st);
     }
+    timing_end(1, st);
     count_launch(1);
     const int rc = check_cuda(cudaGetLastError(), "walk kernel launch");
     if (plan.persist) set_row_ptr_window(st, nullptr, 0, plan.device, false);

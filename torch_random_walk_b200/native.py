@@ -98,6 +98,13 @@ def get_option(name):
     return int(_lib.trw_get_option(name.encode()))
 
 
+def last_kernel_ms():
+    """(table build ms, walk kernel ms) of the last rw.walk call; needs set_option("time_kernels", 1)."""
+    b, w = ctypes.c_float(0), ctypes.c_float(0)
+    _check(_lib.trw_last_kernel_ms(ctypes.byref(b), ctypes.byref(w)))
+    return b.value, w.value
+
+
 def launch_count():
     return int(_lib.trw_launch_count())
 
