@@ -160,7 +160,7 @@ int trw_windows_triples_cbow(const int64_t* walks, int64_t n_walks, int64_t walk
 /* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py / profiles only; not part of the reference's surface).
  * trw_calib_gather: every thread performs `loads_per_thread` dependent random loads of
- * `bytes_per_load` (8 or 32) from table[0, table_elems) -- the attainable random-sector rate
+ * `bytes_per_load` (8, 32, 64 or 128; the wide ones read adjacent sectors) from table[0, table_elems) -- the attainable random-sector rate
  * the walk kernels are compared against.  sink[>=1] receives a checksum.
  * ------------------------------------------------------------------------------------- */
 int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_threads,

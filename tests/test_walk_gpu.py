@@ -89,29 +89,55 @@ def test_shards_are_bit_identical_to_one_call(native, p, q):
         assert torch.equal(torch.cat(parts), full), world
 
 
+DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 1, "n2v_min_ctas": 4,
+            "build_tiles_per_cta": 2}
+
+
 def test_kernel_variants_agree_bit_for_bit(native):
-    """Hashed membership table vs the reference's linear scan, speculative row fetch on/off and
-    staged vs plain stores must not change a single entry: same draws, same decisions."""
-    rp, ci = random_csr(3, 4000, 60)  # mean degree 60: most rows use the table (>= 16 neighbours)
+    """Hashed membership table vs the reference's linear scan, cooperative vs flat table build,
+    uint32 vs int64 row index, speculative row fetch on/off, staged vs plain stores and every
+    register budget must not change a single entry: same draws, same decisions."""
+    rp, ci = random_csr(3, 4000, 60)  # mean degree 60: most rows use the table (>= 12 neighbours)
     rp, ci = cuda(rp, ci)
     nodes = torch.arange(4000, device="cuda")
+    variants = [{}, {"n2v_table": 0}, {"n2v_speculate": 0}, {"n2v_speculate": 1}, {"stage_output": 0}, {"row32": 0},
+                {"build_mode": 0}, {"n2v_min_ctas": 5}, {"n2v_min_ctas": 6}, {"build_tiles_per_cta": 1},
+                {"n2v_table": 0, "row32": 0, "stage_output": 0}, {"build_mode": 0, "row32": 0, "n2v_min_ctas": 6}]
     base = None
     try:
-        for table in (1, 0):
-            for spec in (1, 0):
-                for stage in (1, 0):
-                    native.set_option("n2v_table", table)
-                    native.set_option("n2v_speculate", spec)
-                    native.set_option("stage_output", stage)
-                    w = native.walk(rp, ci, nodes, 0.5, 2.0, 25, 99)
-                    u = native.walk(rp, ci, nodes, 1.0, 1.0, 25, 99)
-                    if base is None:
-                        base = (w, u)
-                    assert torch.equal(w, base[0]), (table, spec, stage)
-                    assert torch.equal(u, base[1]), (table, spec, stage)
+        for opts in variants:
+            for k, v in {**DEFAULTS, **opts}.items():
+                native.set_option(k, v)
+            w = native.walk(rp, ci, nodes, 0.5, 2.0, 25, 99)
+            w2 = native.walk(rp, ci, nodes, 1.0, 0.5, 25, 99)
+            u = native.walk(rp, ci, nodes, 1.0, 1.0, 25, 99)
+            if base is None:
+                base = (w, w2, u)
+            assert torch.equal(w, base[0]) and torch.equal(w2, base[1]) and torch.equal(u, base[2]), opts
     finally:
-        for k in ("n2v_table", "n2v_speculate", "stage_output"):
-            native.set_option(k, 1)
+        for k, v in DEFAULTS.items():
+            native.set_option(k, v)
+
+
+def test_table_build_on_skewed_graph_matches_scan(native):
+    """The cooperative, chunked table build against the linear scan on a graph with hubs, many
+    empty rows and more tiles than one chunk holds."""
+    from torch_random_walk_b200 import rmat
+
+    rp, ci = rmat.rmat_csr(17, 16, device="cuda", seed=5)
+    deg = rp[1:] - rp[:-1]
+    nodes = torch.nonzero(deg > 0).flatten()[:50000].contiguous()
+    a = native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1)
+    try:
+        native.set_option("build_mode", 0)
+        b = native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1)
+        native.set_option("n2v_table", 0)
+        c = native.walk(rp, ci, nodes[:3000].contiguous(), 0.5, 2.0, 12, 1)
+    finally:
+        native.set_option("build_mode", 1)
+        native.set_option("n2v_table", 1)
+    assert torch.equal(a, b)
+    assert torch.equal(a[:3000], c)
 
 
 def test_unsorted_rows_and_duplicate_edges(native):
@@ -169,8 +195,8 @@ def test_edge_cases(rw, native):
     with pytest.raises(RuntimeError, match="Long"):
         rw.walk(rp.int(), ci, nodes, 1.0, 1.0, 3, 1)
     # non-contiguous inputs are accepted (the reference reads through strided accessors)
-    w = rw.walk(rp, ci, torch.arange(200, device="cuda")[::2], 1.0, 1.0, 4, 1)
-    check_walks_follow_edges(w, rp, ci, torch.arange(200, device="cuda")[::2])
+    w = rw.walk(rp, ci, torch.arange(100, device="cuda")[::2], 1.0, 1.0, 4, 1)
+    check_walks_follow_edges(w, rp, ci, torch.arange(100, device="cuda")[::2])
 
 
 def test_first_order_transitions_are_uniform(rw, golden):
@@ -218,7 +244,7 @@ def test_second_order_statistics_match_analytic_and_oracle(rw, orc, golden, p, q
 def test_second_order_statistics_with_table_rows(rw, orc):
     """Same criterion on a graph whose rows are long enough (>= 16) to go through the hashed
     membership table, with triangles so that all three acceptance classes occur."""
-    rp, ci = random_csr(11, 60, 30)
+    rp, ci = random_csr(11, 60, 40)
     n = 60
     assert int((rp[1:] - rp[:-1]).min()) >= 16
     p, q = 0.5, 2.0

@@ -103,9 +103,15 @@ __global__ void __launch_bounds__(256) calib_gather_kernel(const int64_t* __rest
             acc += v;
             state += v;
         } else {
-            Sector64 s = ldg_sector(table + unit * 4);
-            acc += s.a ^ s.b ^ s.c ^ s.d;
-            state += s.a;
+            // BYTES/32 adjacent sectors of one aligned BYTES-wide granule
+            uint64_t mix = 0;
+#pragma unroll
+            for (int j = 0; j < BYTES / 32; ++j) {
+                Sector64 s = ldg_sector(table + unit * (BYTES / 8) + 4 * j);
+                mix ^= s.a ^ s.b ^ s.c ^ s.d;
+            }
+            acc += mix;
+            state += mix;
         }
     }
     if (acc == 0x9E3779B97F4A7C15ull) sink[0] = (int64_t)acc;  // keeps the loads alive
@@ -130,12 +136,12 @@ int trw_device_check(int device) {
 int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_threads, int loads_per_thread,
                      int bytes_per_load, int64_t seed, int64_t* sink, int device, void* stream) {
     if (!table || !sink || table_elems < 4 || n_threads < 0 || loads_per_thread < 0 ||
-        (bytes_per_load != 8 && bytes_per_load != 32)) {
+        (bytes_per_load != 8 && bytes_per_load != 32 && bytes_per_load != 64 && bytes_per_load != 128)) {
         set_error("trw_calib_gather: bad argument");
         return TRW_ERR_ARG;
     }
-    if (bytes_per_load == 32 && ((uintptr_t)table & 31)) {
-        set_error("trw_calib_gather: table must be 32-byte aligned for sector loads");
+    if (bytes_per_load >= 32 && ((uintptr_t)table & 127)) {
+        set_error("trw_calib_gather: table must be 128-byte aligned for sector loads");
         return TRW_ERR_ARG;
     }
     int d = resolve_device(device);
@@ -147,8 +153,12 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
     uint2 key = philox_key(seed, 0x43414C49u);
     if (bytes_per_load == 8)
         calib_gather_kernel<8><<<grid, 256, 0, st>>>(table, (uint64_t)table_elems, n_threads, loads_per_thread, key, sink);
-    else
+    else if (bytes_per_load == 32)
         calib_gather_kernel<32><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 4), n_threads, loads_per_thread, key, sink);
+    else if (bytes_per_load == 64)
+        calib_gather_kernel<64><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 8), n_threads, loads_per_thread, key, sink);
+    else
+        calib_gather_kernel<128><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 16), n_threads, loads_per_thread, key, sink);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "calib_gather launch");
 }

@@ -100,6 +100,48 @@ __device__ __forceinline__ void stg_sector(void* p, uint64_t a, uint64_t b, uint
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
+// L2 cache policies (createpolicy): evict_last for the small, re-read row index; evict_first
+// for gathers and stores whose sectors are never touched again, so that the stream of random
+// sectors does not displace the index from L2.
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t make_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int64_t ldg32_keep(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return (int64_t)v;
+}
+__device__ __forceinline__ int64_t ldg64_keep(const int64_t* p, uint64_t pol) {
+    int64_t v;
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int64_t ldg64_hint(const int64_t* p, uint64_t pol) {
+    int64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ Sector64 ldg_sector_hint(const void* p, uint64_t pol) {
+    Sector64 s;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=l"(s.a), "=l"(s.b), "=l"(s.c), "=l"(s.d) : "l"(p), "l"(pol));
+    return s;
+}
+__device__ __forceinline__ void stg_sector_hint(void* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u64 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg64_hint(int64_t* p, int64_t v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+
 // Coherent 16-byte load of memory other threads are updating with atomics.
 __device__ __forceinline__ uint4 ld_relaxed_u32x4(const uint32_t* p) {
     uint4 v;
@@ -126,11 +168,12 @@ template <int BLOCK>
 struct RowStager {
     int64_t (*ring)[BLOCK];  // [4][BLOCK] in shared memory
     int64_t* row;            // this thread's output row
+    uint64_t policy;         // L2 policy of the stores (evict_first: written once, never re-read)
     uint32_t phase;          // (address of row[0] / 8) & 3
     int tid;
 
-    __device__ __forceinline__ void init(int64_t (*smem)[BLOCK], int64_t* row_, int tid_) {
-        ring = smem; row = row_; tid = tid_;
+    __device__ __forceinline__ void init(int64_t (*smem)[BLOCK], int64_t* row_, int tid_, uint64_t policy_) {
+        ring = smem; row = row_; tid = tid_; policy = policy_;
         phase = (uint32_t)(((uintptr_t)row_ >> 3) & 3);
     }
     // Store element s (0-based, strictly increasing calls); `last` marks the final element.
@@ -140,11 +183,11 @@ struct RowStager {
         if (slot == 3u || last) {
             int first = s - (int)slot;  // element index that sits in slot 0 of this sector
             if (slot == 3u && first >= 0) {
-                stg_sector(row + first, (uint64_t)ring[0][tid], (uint64_t)ring[1][tid],
-                           (uint64_t)ring[2][tid], (uint64_t)ring[3][tid]);
+                stg_sector_hint(row + first, (uint64_t)ring[0][tid], (uint64_t)ring[1][tid],
+                                (uint64_t)ring[2][tid], (uint64_t)ring[3][tid], policy);
             } else {
                 int lo = first < 0 ? 0 : first;
-                for (int e = lo; e <= s; ++e) row[e] = ring[(phase + (uint32_t)e) & 3u][tid];
+                for (int e = lo; e <= s; ++e) stg64_hint(row + e, ring[(phase + (uint32_t)e) & 3u][tid], policy);
             }
         }
     }

@@ -7,15 +7,25 @@
 //   * node2vec: step 1 uniform, then propose x ~ U(adj(v)), accept with probability
 //     prob_0 (x == t), prob_1 (x in adj(t)), prob_2 (otherwise), prob_k = {1/p,1,1/q}/max
 //     (rw_cuda.cu:119-123, 146-179).
-// Design: both kernels are latency-bound dependent gathers, so one
-// thread owns one walk and the SM is kept full of them.  The node2vec loop is flattened to
-// one *trial* per iteration so that lanes whose proposal was accepted move on to their next
-// step instead of idling until the slowest lane of the warp is accepted.  "x in adj(t)" is
-// answered with one 32-byte sector from a hashed copy of the adjacency built per call into
-// caller-provided workspace (build_member_table), not by scanning or searching adj(t).
+//
+// Design.  Both kernels are dependent random gathers whose cost is the
+// number of random DRAM fetches per step, so
+//   * one thread owns one walk and the SMs are kept full of them;
+//   * the node2vec loop is flattened to one rejection *trial* per iteration, so lanes whose
+//     proposal was accepted move on instead of idling until the slowest lane is accepted;
+//   * "x in adj(t)" is one 32-byte sector of a hashed copy of the adjacency that is built per
+//     call into caller-provided workspace, not a scan or search of adj(t);
+//   * row_ptr is re-encoded per call as uint32 offsets (half the bytes, fits the 126 MB L2 for
+//     16 M nodes) and read with an L2 evict_last policy, while the never-reused gathers
+//     (proposals, table buckets) and the output stores carry evict_first, so the stream of
+//     random sectors does not wash the row index out of L2.
+#include <cooperative_groups.h>
+
 #include "trw_common.cuh"
 #include "trw_options.h"
 #include "walk_csr.h"
+
+namespace cg = cooperative_groups;
 
 namespace trw {
 
@@ -24,12 +34,12 @@ namespace trw {
 // table as large as col_idx; the 32-byte buckets wholly inside that span hold the row's
 // neighbour ids as uint32 (8 slots per bucket, EMPTY = 0xFFFFFFFF), open addressing over
 // buckets.  A row of degree d >= kMinTableDeg owns >= (d-6)/4 buckets = 2d-12 >= d slots, so
-// inserts always find room; shorter rows are scanned directly (<= 15 ids, <= 5 sectors).
-// No per-row pointer is needed: the bucket range follows from the row_ptr pair the walk
-// already holds.  Lookup: hash -> bucket -> one sector; a hit, or any EMPTY slot (the bucket
-// never overflowed), ends the probe.
+// inserts always find room; shorter rows are scanned directly (<= 11 ids).  No per-row
+// pointer is needed: the bucket range follows from the row_ptr pair the walk already holds.
+// Lookup: hash -> bucket -> one sector; a hit, or any EMPTY slot (the bucket never
+// overflowed), ends the probe.
 // ------------------------------------------------------------------------------------------
-constexpr int64_t kMinTableDeg = 16;
+constexpr int64_t kMinTableDeg = 12;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
 __device__ __forceinline__ void table_span(int64_t b, int64_t e, int64_t& first, int64_t& nb) {
@@ -51,29 +61,82 @@ __device__ __forceinline__ int64_t row_of_entry(const int64_t* __restrict__ row_
     return lo;
 }
 
-__global__ void __launch_bounds__(kBuildThreads)
-build_member_table_kernel(const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ col_idx,
-                          int64_t n_nodes, int64_t nnz, uint32_t* __restrict__ table) {
-    __shared__ uint32_t head[kBuildTile];  // row offset (relative to r0) that starts at this entry
-    __shared__ uint32_t warp_max[kBuildThreads / 32];
-    __shared__ int64_t s_r0, s_r1;
+struct BuildArgs {
+    const int64_t* row_ptr;
+    const int64_t* col_idx;
+    int64_t n_nodes, nnz;
+    uint32_t* table;
+    int64_t* tile_row0;          // [n_tiles + 1]: row holding the first entry of each tile
+    unsigned long long* maxdeg;  // largest row length (decides how far ahead buckets are cleared)
+    uint32_t* row32;             // optional compact copy of row_ptr
+    int64_t n_tiles, n_buckets;
+    int chunk_tiles;             // tiles per L2-resident chunk
+};
 
+// Pre-pass (ordinary launch): first row of every tile, the maximum degree, and the uint32 copy
+// of row_ptr.  All three are embarrassingly parallel.
+__global__ void __launch_bounds__(256) csr_prepass_kernel(const BuildArgs a) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    if (a.tile_row0) {
+        for (int64_t j = gtid; j <= a.n_tiles; j += gsz) {
+            const int64_t e = j * kBuildTile;
+            a.tile_row0[j] = e < a.nnz ? row_of_entry(a.row_ptr, a.n_nodes, e) : a.n_nodes;
+        }
+    }
+    unsigned long long best = 0;
+    for (int64_t r = gtid; r <= a.n_nodes; r += gsz) {
+        const int64_t b = __ldg(a.row_ptr + r);
+        if (a.row32) a.row32[r] = (uint32_t)b;
+        if (a.maxdeg && r < a.n_nodes) best = max(best, (unsigned long long)(__ldg(a.row_ptr + r + 1) - b));
+    }
+    if (a.maxdeg) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, d));
+        if ((threadIdx.x & 31) == 0 && best) atomicMax(a.maxdeg, best);
+    }
+}
+
+__device__ __forceinline__ void clear_buckets(const BuildArgs& a, int64_t lo, int64_t hi, int64_t gtid, int64_t gsz) {
+    for (int64_t b = lo + gtid; b < hi; b += gsz) stg_sector(a.table + b * 8, ~0ull, ~0ull, ~0ull, ~0ull);
+}
+
+__device__ __forceinline__ void table_insert(uint32_t* __restrict__ table, int64_t first, int64_t nb, uint32_t x) {
+    int64_t bkt = (int64_t)__umul64hi((uint64_t)mix32(x) << 32, (uint64_t)nb);
+    for (;;) {
+        uint32_t* slots = table + (first + bkt) * 8;
+        // Snapshot the bucket, then claim the first EMPTY slot seen; a lost race just moves on.
+        const uint4 lo4 = ld_relaxed_u32x4(slots), hi4 = ld_relaxed_u32x4(slots + 4);
+        const uint32_t snap[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (snap[j] == x) return;
+            if (snap[j] == kEmpty) {
+                const uint32_t old = atomicCAS(slots + j, kEmpty, x);
+                if (old == kEmpty || old == x) return;
+            }
+        }
+        if (++bkt == nb) bkt = 0;
+    }
+}
+
+// One tile = kBuildTile consecutive CSR entries.  The rows they belong to are recovered with a
+// shared-memory max-scan over "a row starts here" marks (edge-balanced: hubs and short rows cost
+// the same per entry), then every entry is inserted into its row's buckets.
+__device__ __forceinline__ void build_tile(const BuildArgs& a, int64_t tile, uint32_t* head, uint32_t* warp_max) {
     const int tid = threadIdx.x;
-    const int64_t e0 = (int64_t)blockIdx.x * kBuildTile;
-    const int64_t e1 = min(e0 + (int64_t)kBuildTile, nnz);
-    if (tid == 0) s_r0 = row_of_entry(row_ptr, n_nodes, e0);
-    if (tid == 32) s_r1 = row_of_entry(row_ptr, n_nodes, e1 - 1);
+    const int64_t e0 = tile * kBuildTile;
+    const int64_t e1 = min(e0 + (int64_t)kBuildTile, a.nnz);
+    const int64_t r0 = a.tile_row0[tile];
+    const int64_t r1 = min(a.tile_row0[tile + 1], a.n_nodes - 1);
 #pragma unroll
     for (int k = 0; k < kBuildPerThread; ++k) head[k * kBuildThreads + tid] = 0;
     __syncthreads();
-    const int64_t r0 = s_r0, r1 = s_r1;
-    // Mark the first entry of every non-empty row that starts inside the tile.
     for (int64_t r = r0 + 1 + tid; r <= r1; r += kBuildThreads) {
-        int64_t b = __ldg(row_ptr + r), e = __ldg(row_ptr + r + 1);
-        if (e > b) head[b - e0] = (uint32_t)(r - r0);
+        const int64_t b = __ldg(a.row_ptr + r), e = __ldg(a.row_ptr + r + 1);
+        if (e > b && b < e1) head[b - e0] = (uint32_t)(r - r0);
     }
     __syncthreads();
-    // Inclusive max-scan: entry j belongs to row r0 + max(head[0..j]).
     uint32_t own[kBuildPerThread];
     uint32_t run = 0;
 #pragma unroll
@@ -84,7 +147,7 @@ build_member_table_kernel(const int64_t* __restrict__ row_ptr, const int64_t* __
     uint32_t incl = run;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if ((tid & 31) >= d) incl = max(incl, o);
     }
     if ((tid & 31) == 31) warp_max[tid >> 5] = incl;
@@ -93,54 +156,82 @@ build_member_table_kernel(const int64_t* __restrict__ row_ptr, const int64_t* __
     if ((tid & 31) == 0) before = 0;
     for (int w = 0; w < (tid >> 5); ++w) before = max(before, warp_max[w]);
 
+    // This thread's eight consecutive entries: fetch them first (two 256-bit loads when the
+    // span is whole and aligned) so that the inserts below do not wait on them one by one.
+    const int64_t mine = e0 + (int64_t)tid * kBuildPerThread;
+    uint64_t x[kBuildPerThread];
+    if (mine + kBuildPerThread <= e1 && (((uintptr_t)(a.col_idx + mine)) & 31) == 0) {
+        const Sector64 s0 = ldg_sector(a.col_idx + mine), s1 = ldg_sector(a.col_idx + mine + 4);
+        x[0] = s0.a; x[1] = s0.b; x[2] = s0.c; x[3] = s0.d;
+        x[4] = s1.a; x[5] = s1.b; x[6] = s1.c; x[7] = s1.d;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kBuildPerThread; ++k) x[k] = mine + k < e1 ? (uint64_t)ldg64_stream(a.col_idx + mine + k) : 0;
+    }
     int64_t cur_row = -1, first = 0, nb = 0;
 #pragma unroll
     for (int k = 0; k < kBuildPerThread; ++k) {
-        const int64_t e = e0 + tid * kBuildPerThread + k;
-        if (e >= e1) break;
+        if (mine + k >= e1) break;
         const int64_t r = r0 + max(before, own[k]);
         if (r != cur_row) {
             cur_row = r;
-            int64_t b = __ldg(row_ptr + r), en = __ldg(row_ptr + r + 1);
+            const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
             if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
         }
-        if (nb <= 0) continue;
-        const uint32_t x = (uint32_t)ldg64_stream(col_idx + e);
-        const uint32_t h = mix32(x);
-        int64_t bkt = (int64_t)__umul64hi((uint64_t)h << 32, (uint64_t)nb);
-        bool done = false;
-        while (!done) {
-            uint32_t* slots = table + (first + bkt) * 8;
-            // Snapshot the bucket, then claim the first EMPTY slot seen; a lost race just moves on.
-            uint4 lo4 = ld_relaxed_u32x4(slots);
-            uint4 hi4 = ld_relaxed_u32x4(slots + 4);
-            uint32_t snap[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-#pragma unroll
-            for (int j = 0; j < 8 && !done; ++j) {
-                if (snap[j] == x) done = true;
-                else if (snap[j] == kEmpty) {
-                    uint32_t old = atomicCAS(slots + j, kEmpty, x);
-                    if (old == kEmpty || old == x) done = true;
-                }
-            }
-            if (++bkt == nb) bkt = 0;
-        }
+        if (nb > 0) table_insert(a.table, first, nb, (uint32_t)x[k]);
+    }
+    __syncthreads();  // head/warp_max are reused by the next tile
+}
+
+// Table build, cooperative and persistent.  The table is filled in chunks small enough to stay
+// in L2: the CTAs clear the buckets of the chunk ahead with full-sector stores, synchronise the
+// grid, then insert the current chunk's entries with L2-resident atomics, so each table byte
+// goes to DRAM once (write-back) instead of once for a memset and again for every random CAS.
+// Inserts of chunk k can reach at most max-degree entries past the chunk (the row of its last
+// entry), which is how far ahead buckets are cleared before the chunk starts.
+__global__ void __launch_bounds__(kBuildThreads, 5) build_member_table_coop_kernel(const BuildArgs a) {
+    __shared__ uint32_t head[kBuildTile];
+    __shared__ uint32_t warp_max[kBuildThreads / 32];
+    cg::grid_group grid = cg::this_grid();
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    const int64_t chunk_entries = (int64_t)a.chunk_tiles * kBuildTile;
+    const int64_t chunk_buckets = chunk_entries / 4;
+    const int64_t n_chunks = (a.n_tiles + a.chunk_tiles - 1) / a.chunk_tiles;
+    const int64_t ahead = (int64_t)(*a.maxdeg / (unsigned long long)chunk_entries) + 1;
+
+    clear_buckets(a, 0, min((ahead + 1) * chunk_buckets, a.n_buckets), gtid, gsz);
+    grid.sync();
+    for (int64_t k = 0; k < n_chunks; ++k) {
+        const int64_t t_end = min((k + 1) * a.chunk_tiles, a.n_tiles);
+        for (int64_t tile = k * a.chunk_tiles + blockIdx.x; tile < t_end; tile += gridDim.x) build_tile(a, tile, head, warp_max);
+        const int64_t c = k + 1 + ahead;
+        if (c * chunk_buckets < a.n_buckets) clear_buckets(a, c * chunk_buckets, min((c + 1) * chunk_buckets, a.n_buckets), gtid, gsz);
+        grid.sync();
     }
 }
 
-// x in adj(t)?  (b,e) = row_ptr[t], row_ptr[t+1].
+// Same build as one ordinary launch over a table cleared by cudaMemsetAsync (used when a
+// cooperative launch is not possible, and as the A/B baseline: option build_mode = 0).
+__global__ void __launch_bounds__(kBuildThreads, 5) build_member_table_flat_kernel(const BuildArgs a) {
+    __shared__ uint32_t head[kBuildTile];
+    __shared__ uint32_t warp_max[kBuildThreads / 32];
+    build_tile(a, blockIdx.x, head, warp_max);
+}
+
+// x in adj(t)?  (b,e) = row span of t.
 template <bool TABLE>
 __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const int64_t* __restrict__ col_idx,
-                                          const uint32_t* __restrict__ table) {
+                                          const uint32_t* __restrict__ table, uint64_t pol_stream) {
     if (TABLE && e - b >= kMinTableDeg) {
         int64_t first, nb;
         table_span(b, e, first, nb);
         const uint32_t x32 = (uint32_t)x;
         int64_t bkt = (int64_t)__umul64hi((uint64_t)mix32(x32) << 32, (uint64_t)nb);
         for (int64_t probes = 0; probes < nb; ++probes) {
-            Sector64 s = ldg_sector(table + (first + bkt) * 8);
-            uint32_t w[8] = {(uint32_t)s.a, (uint32_t)(s.a >> 32), (uint32_t)s.b, (uint32_t)(s.b >> 32),
-                             (uint32_t)s.c, (uint32_t)(s.c >> 32), (uint32_t)s.d, (uint32_t)(s.d >> 32)};
+            const Sector64 s = ldg_sector_hint(table + (first + bkt) * 8, pol_stream);
+            const uint32_t w[8] = {(uint32_t)s.a, (uint32_t)(s.a >> 32), (uint32_t)s.b, (uint32_t)(s.b >> 32),
+                                   (uint32_t)s.c, (uint32_t)(s.c >> 32), (uint32_t)s.d, (uint32_t)(s.d >> 32)};
             bool hit = false, open = false;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { hit |= (w[j] == x32); open |= (w[j] == kEmpty); }
@@ -150,24 +241,29 @@ __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const
         }
         return false;
     }
-    // Short (or table-less) row: the reference's scan, csrc/cuda/rw_cuda.cu:48-53.
-    // Eight independent loads per round so the scan is not one dependent chain.
+    // Short (or table-less) row: the reference's scan, csrc/cuda/rw_cuda.cu:48-53, eight
+    // independent loads per round so that it is not one dependent chain.
     for (int64_t i = b; i < e; i += 8) {
         bool found = false;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (i + j < e) found |= (ldg64_stream(col_idx + i + j) == x);
+            if (i + j < e) found |= (ldg64_hint(col_idx + i + j, pol_stream) == x);
         if (found) return true;
     }
     return false;
 }
 
 // ------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ void load_row(const WalkArgs& a, int64_t v, int64_t& b, int64_t& e) {
+template <bool ROW32>
+__device__ __forceinline__ void load_row(const WalkArgs& a, int64_t v, int64_t& b, int64_t& e, uint64_t pol_keep) {
     if ((uint64_t)v < (uint64_t)a.n_nodes) {
-        b = __ldg(a.row_ptr + v);
-        e = __ldg(a.row_ptr + v + 1);
+        if (ROW32) {
+            b = ldg32_keep(a.row32 + v, pol_keep);
+            e = ldg32_keep(a.row32 + v + 1, pol_keep);
+        } else {
+            b = ldg64_keep(a.row_ptr + v, pol_keep);
+            e = ldg64_keep(a.row_ptr + v + 1, pol_keep);
+        }
     } else {
         b = e = 0;  // id outside the graph: treated as a node without out-edges
     }
@@ -175,37 +271,38 @@ __device__ __forceinline__ void load_row(const WalkArgs& a, int64_t v, int64_t& 
 
 // Neighbour of v at a uniformly random position, or v itself when it has none (rw_cuda.cu:8-31).
 __device__ __forceinline__ int64_t pick_neighbor(const WalkArgs& a, int64_t v, int64_t b, int64_t e, uint32_t r0,
-                                                 uint32_t r1) {
+                                                 uint32_t r1, uint64_t pol_stream) {
     const int64_t deg = e - b;
     if (deg <= 0) return v;
     const int64_t idx = b + bounded(r0, r1, deg);
     if ((uint64_t)idx >= (uint64_t)a.nnz) return v;
-    return ldg64_stream(a.col_idx + idx);
+    return ldg64_hint(a.col_idx + idx, pol_stream);
 }
 
 template <int BLOCK, bool STAGE>
 struct RowOut {
     RowStager<BLOCK> st;
     int64_t* row;
-    __device__ __forceinline__ void init(int64_t (*ring)[BLOCK], int64_t* r, int tid) {
+    __device__ __forceinline__ void init(int64_t (*ring)[BLOCK], int64_t* r, int tid, uint64_t pol) {
         row = r;
-        if (STAGE) st.init(ring, r, tid);
+        if (STAGE) st.init(ring, r, tid, pol);
     }
     __device__ __forceinline__ void put(int s, int64_t v, bool last) {
         if (STAGE) st.put(s, v, last); else row[s] = v;
     }
 };
 
-// First-order walk: one thread per walk, two dependent gathers per step (row_ptr pair, then
-// the chosen col_idx entry), one Philox block per four steps.
-template <int BLOCK, bool STAGE>
-__global__ void __launch_bounds__(BLOCK) uniform_walk_kernel(const WalkArgs a) {
+// First-order walk: one thread per walk, two dependent gathers per step (row span, then the
+// chosen col_idx entry), one Philox block per four steps.
+template <int BLOCK, bool STAGE, bool ROW32>
+__global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a) {
     __shared__ int64_t ring[STAGE ? 4 : 1][BLOCK];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= a.n_walks) return;
+    const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowOut<BLOCK, STAGE> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x);
+    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, pol_stream);
 
     int64_t v = __ldg(a.targets + i);
     const int L = a.walk_length;
@@ -218,21 +315,22 @@ __global__ void __launch_bounds__(BLOCK) uniform_walk_kernel(const WalkArgs a) {
         const uint32_t r = rnd.x;
         rnd.x = rnd.y; rnd.y = rnd.z; rnd.z = rnd.w;
         int64_t b, e;
-        load_row(a, v, b, e);
-        v = pick_neighbor(a, v, b, e, r, r * 0x9E3779B1u + (uint32_t)s);
+        load_row<ROW32>(a, v, b, e, pol_keep);
+        v = pick_neighbor(a, v, b, e, r, r * 0x9E3779B1u + (uint32_t)s, pol_stream);
         o.put(s, v, s == L);
     }
 }
 
 // Second-order walk.  One iteration of the loop = one rejection trial of this thread's walk.
-template <int BLOCK, bool STAGE, bool TABLE, bool SPECULATE>
-__global__ void __launch_bounds__(BLOCK) node2vec_walk_kernel(const WalkArgs a) {
+template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const WalkArgs a) {
     __shared__ int64_t ring[STAGE ? 4 : 1][BLOCK];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= a.n_walks) return;
+    const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowOut<BLOCK, STAGE> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x);
+    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, pol_stream);
     const int L = a.walk_length;
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
 
@@ -240,13 +338,13 @@ __global__ void __launch_bounds__(BLOCK) node2vec_walk_kernel(const WalkArgs a) 
     o.put(0, t, L == 0);
     if (L == 0) return;
     int64_t tb, te;
-    load_row(a, t, tb, te);
+    load_row<ROW32>(a, t, tb, te, pol_keep);
     uint4 rnd = philox4x32_10(make_uint4(wlo, whi, 1u, 0u), a.key);
-    int64_t v = pick_neighbor(a, t, tb, te, rnd.x, rnd.z);  // first step is uniform (rw_cuda.cu:138)
+    int64_t v = pick_neighbor(a, t, tb, te, rnd.x, rnd.z, pol_stream);  // first step is uniform (rw_cuda.cu:138)
     o.put(1, v, L == 1);
     if (L == 1) return;
     int64_t vb, ve;
-    load_row(a, v, vb, ve);
+    load_row<ROW32>(a, v, vb, ve, pol_keep);
 
     const uint64_t thr_any = min(a.thr0, min(a.thr1, a.thr2));  // below this every class accepts
     const uint64_t thr_far = max(a.thr1, a.thr2);               // at or above this only x == t can accept
@@ -260,20 +358,20 @@ __global__ void __launch_bounds__(BLOCK) node2vec_walk_kernel(const WalkArgs a) 
         } else {
             r = rnd.z; u = rnd.w; r_hi = rnd.x;
         }
-        const int64_t x = pick_neighbor(a, v, vb, ve, r, r_hi);
+        const int64_t x = pick_neighbor(a, v, vb, ve, r, r_hi, pol_stream);
         const bool back = (x == t);
         const bool possible = back ? (u < a.thr0) : (u < thr_far);
         int64_t xb = 0, xe = 0;
-        if (SPECULATE && possible && s < L) load_row(a, x, xb, xe);
+        if (SPECULATE && possible && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
         bool accept;
         if (u < thr_any) accept = true;
         else if (back) accept = u < a.thr0;
         else if (!possible) accept = false;
         else if (a.thr1 == a.thr2) accept = true;  // q == 1: membership cannot change the answer
-        else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, a.table) ? a.thr1 : a.thr2);
+        else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, a.table, pol_stream) ? a.thr1 : a.thr2);
         if (accept) {
             o.put(s, x, s == L);
-            if (!SPECULATE && s < L) load_row(a, x, xb, xe);
+            if (!SPECULATE && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
             t = v; tb = vb; te = ve;
             v = x; vb = xb; ve = xe;
             ++s;
@@ -284,17 +382,42 @@ __global__ void __launch_bounds__(BLOCK) node2vec_walk_kernel(const WalkArgs a) 
     }
 }
 
-template <int BLOCK, bool STAGE>
+// ------------------------------------------------------------------------------------------ launchers
+template <bool STAGE, bool ROW32>
 static void launch_uniform(const WalkArgs& a, cudaStream_t st) {
+    constexpr int BLOCK = 256;
     const unsigned grid = (unsigned)((a.n_walks + BLOCK - 1) / BLOCK);
-    uniform_walk_kernel<BLOCK, STAGE><<<grid, BLOCK, 0, st>>>(a);
+    uniform_walk_kernel<BLOCK, STAGE, ROW32><<<grid, BLOCK, 0, st>>>(a);
 }
 
-template <int BLOCK, bool STAGE, bool TABLE>
-static void launch_n2v(const WalkArgs& a, bool speculate, cudaStream_t st) {
+template <int MIN_CTAS, bool STAGE, bool TABLE, bool ROW32>
+static void launch_n2v3(const WalkArgs& a, bool speculate, cudaStream_t st) {
+    constexpr int BLOCK = 256;
     const unsigned grid = (unsigned)((a.n_walks + BLOCK - 1) / BLOCK);
-    if (speculate) node2vec_walk_kernel<BLOCK, STAGE, TABLE, true><<<grid, BLOCK, 0, st>>>(a);
-    else node2vec_walk_kernel<BLOCK, STAGE, TABLE, false><<<grid, BLOCK, 0, st>>>(a);
+    if (speculate) node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, true, ROW32><<<grid, BLOCK, 0, st>>>(a);
+    else node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32><<<grid, BLOCK, 0, st>>>(a);
+}
+
+template <bool STAGE, bool TABLE, bool ROW32>
+static void launch_n2v2(const WalkArgs& a, bool speculate, int min_ctas, cudaStream_t st) {
+    if (min_ctas >= 6) launch_n2v3<6, STAGE, TABLE, ROW32>(a, speculate, st);
+    else if (min_ctas == 5) launch_n2v3<5, STAGE, TABLE, ROW32>(a, speculate, st);
+    else launch_n2v3<4, STAGE, TABLE, ROW32>(a, speculate, st);
+}
+
+static void launch_n2v(const WalkArgs& a, bool stage, bool table, bool row32, bool speculate, int min_ctas, cudaStream_t st) {
+    if (!stage) {  // plain 8-byte stores: A/B path only, kept to one variant per table mode
+        if (table) launch_n2v3<4, false, true, false>(a, speculate, st);
+        else launch_n2v3<4, false, false, false>(a, speculate, st);
+        return;
+    }
+    if (table) {
+        if (row32) launch_n2v2<true, true, true>(a, speculate, min_ctas, st);
+        else launch_n2v2<true, true, false>(a, speculate, min_ctas, st);
+    } else {
+        if (row32) launch_n2v2<true, false, true>(a, speculate, min_ctas, st);
+        else launch_n2v2<true, false, false>(a, speculate, min_ctas, st);
+    }
 }
 
 static uint64_t threshold(double prob) {
@@ -304,10 +427,36 @@ static uint64_t threshold(double prob) {
     return (uint64_t)t;
 }
 
-static size_t table_bytes(int64_t nnz) { return (size_t)((nnz + 3) / 4) * 32 + 256; }
+// Workspace layout (all offsets 256-byte aligned).
+struct WsLayout {
+    size_t table, tile_row0, maxdeg, row32, total;
+    int64_t n_tiles, n_buckets;
+};
 
-// Optional persisting-L2 window over row_ptr (the small, degree-skewed array every step reads).
-static void set_row_ptr_window(cudaStream_t st, const void* base, size_t bytes, int device, bool on) {
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static WsLayout ws_layout(int64_t n_nodes, int64_t nnz, bool uniform) {
+    WsLayout w{};
+    const bool ids_fit = (uint64_t)n_nodes < 0xFFFFFFFFull;    // neighbour ids must fit the uint32 table slots
+    const bool offsets_fit = (uint64_t)nnz <= 0xFFFFFFFFull;    // row offsets must fit the uint32 row index
+    const bool want_table = !uniform && ids_fit && nnz > 0;
+    w.n_tiles = (nnz + kBuildTile - 1) / kBuildTile;
+    w.n_buckets = (nnz + 3) / 4;
+    size_t off = 0;
+    w.table = off;
+    if (want_table) off += align256((size_t)w.n_buckets * 32);
+    w.tile_row0 = off;
+    if (want_table) off += align256((size_t)(w.n_tiles + 1) * 8);
+    w.maxdeg = off;
+    if (want_table) off += 256;
+    w.row32 = off;
+    if (offsets_fit && n_nodes > 0) off += align256((size_t)(n_nodes + 1) * 4);
+    w.total = off;
+    return w;
+}
+
+// Optional persisting-L2 window over the row index (experiment: option persist_row_ptr).
+static void set_row_window(cudaStream_t st, const void* base, size_t bytes, int device, bool on) {
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof(attr));
     if (on) {
@@ -323,26 +472,17 @@ static void set_row_ptr_window(cudaStream_t st, const void* base, size_t bytes, 
         attr.accessPolicyWindow.hitRatio = (float)min(1.0, (double)carve / (double)win);
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    } else {
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);  // give the set-aside lines back
     }
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
     cudaGetLastError();
 }
 
-}  // namespace trw
-
-using namespace trw;
-
-extern "C" size_t trw_walk_csr_workspace_bytes(int64_t n_nodes, int64_t nnz, double p, double q) {
-    if (p == 1.0 && q == 1.0) return 0;
-    if (n_nodes < 0 || nnz <= 0 || (uint64_t)n_nodes >= 0xFFFFFFFFull) return 0;  // ids must fit uint32 slots
-    return table_bytes(nnz);
-}
-
-namespace trw {
-
-// Validates the graph-side arguments, derives the acceptance thresholds and (node2vec only)
-// builds the membership table into `workspace`.  After this the plan can launch any number of
-// shards of start nodes (trw_walk_csr launches one; trw_walk_csr_host one per chunk).
+// Validates the graph-side arguments, derives the acceptance thresholds, re-encodes row_ptr and
+// (node2vec only) builds the membership table into `workspace`.  After this the plan can launch
+// any number of shards of start nodes (trw_walk_csr launches one; trw_walk_csr_host one per chunk).
 int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                      double p, double q, int walk_length, int64_t seed, void* workspace, size_t workspace_bytes,
                      int device, cudaStream_t st) {
@@ -354,37 +494,77 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
     a.row_ptr = row_ptr; a.col_idx = col_idx; a.n_nodes = n_nodes; a.nnz = nnz;
     a.targets = nullptr; a.n_walks = 0; a.walk_id_offset = 0;
     a.walk_length = walk_length; a.key = philox_key(seed, kTagWalkCsr);
-    a.out = nullptr; a.out_row_stride = 0; a.table = nullptr;
+    a.out = nullptr; a.out_row_stride = 0; a.table = nullptr; a.row32 = nullptr;
     a.thr0 = a.thr1 = a.thr2 = 0;
     plan->device = device;
     plan->uniform = (p == 1.0 && q == 1.0);  // rw_cuda.cu:226
     plan->table = false;
-    plan->speculate = opt.n2v_speculate != 0;
     plan->stage = opt.stage_output != 0;
     plan->persist = opt.persist_row_ptr != 0;
-    if (plan->uniform) return TRW_OK;
-    const double mx = fmax(fmax(1.0 / p, 1.0), 1.0 / q);  // rw_cuda.cu:119-123
-    a.thr0 = threshold(1.0 / p / mx);
-    a.thr1 = threshold(1.0 / mx);
-    a.thr2 = threshold(1.0 / q / mx);
-    const size_t need = trw_walk_csr_workspace_bytes(n_nodes, nnz, p, q);
-    const bool table = opt.n2v_table != 0 && workspace != nullptr && need > 0 && a.thr1 != a.thr2;
-    if (!table) return TRW_OK;
-    if (workspace_bytes < need || ((uintptr_t)workspace & 255)) {
-        set_error("trw_walk_csr: workspace needs %zu bytes at 256-byte alignment (got %zu)", need, workspace_bytes);
+    plan->min_ctas = (int)opt.n2v_min_ctas;
+    plan->speculate = false;
+    if (!plan->uniform) {
+        const double mx = fmax(fmax(1.0 / p, 1.0), 1.0 / q);  // rw_cuda.cu:119-123
+        const double p0 = 1.0 / p / mx, p1 = 1.0 / mx, p2 = 1.0 / q / mx;
+        a.thr0 = threshold(p0); a.thr1 = threshold(p1); a.thr2 = threshold(p2);
+        // Fetch row_ptr[x] before the verdict only when most proposals are accepted anyway.
+        plan->speculate = opt.n2v_speculate < 0 ? (fmin(p1, p2) >= 0.5) : (opt.n2v_speculate != 0);
+    }
+    if (workspace == nullptr) return TRW_OK;  // reference-style path: int64 row_ptr, linear-scan membership
+    const WsLayout w = ws_layout(n_nodes, nnz, plan->uniform);
+    if (w.total == 0) return TRW_OK;
+    if (workspace_bytes < w.total || ((uintptr_t)workspace & 255)) {
+        set_error("trw_walk_csr: workspace needs %zu bytes at 256-byte alignment (got %zu)", w.total, workspace_bytes);
         return TRW_ERR_WORKSPACE;
     }
+    char* ws = (char*)workspace;
+    const bool want_table = !plan->uniform && opt.n2v_table != 0 && w.tile_row0 > w.table && a.thr1 != a.thr2;
+    const bool want_row32 = opt.row32 != 0 && w.total > w.row32;
+    if (!want_table && !want_row32) return TRW_OK;
+
+    BuildArgs b{};
+    b.row_ptr = row_ptr; b.col_idx = col_idx; b.n_nodes = n_nodes; b.nnz = nnz;
+    b.n_tiles = w.n_tiles; b.n_buckets = w.n_buckets;
+    b.row32 = want_row32 ? (uint32_t*)(ws + w.row32) : nullptr;
+    if (want_table) {
+        b.table = (uint32_t*)(ws + w.table);
+        b.tile_row0 = (int64_t*)(ws + w.tile_row0);
+        b.maxdeg = (unsigned long long*)(ws + w.maxdeg);
+    }
     timing_begin(0, st);
-    int rc = check_cuda(cudaMemsetAsync(workspace, 0xFF, need, st), "table memset");
-    if (rc) return rc;
-    const unsigned grid = (unsigned)((nnz + kBuildTile - 1) / kBuildTile);
-    build_member_table_kernel<<<grid, kBuildThreads, 0, st>>>(row_ptr, col_idx, n_nodes, nnz, (uint32_t*)workspace);
-    timing_end(0, st);
+    int rc;
+    if (want_table) {
+        rc = check_cuda(cudaMemsetAsync(b.maxdeg, 0, 8, st), "maxdeg memset");
+        if (rc) return rc;
+    }
+    const int sms = sm_count(device);
+    csr_prepass_kernel<<<sms * 8, 256, 0, st>>>(b);
     count_launch(1);
-    rc = check_cuda(cudaGetLastError(), "build_member_table launch");
+    rc = check_cuda(cudaGetLastError(), "csr_prepass launch");
     if (rc) return rc;
-    a.table = (const uint32_t*)workspace;
-    plan->table = true;
+    if (want_table) {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_member_table_coop_kernel, kBuildThreads, 0);
+        if (opt.build_mode != 0 && coop && per_sm > 0) {
+            const int grid = sms * per_sm;
+            b.chunk_tiles = grid * (int)(opt.build_tiles_per_cta > 0 ? opt.build_tiles_per_cta : 2);
+            void* args[] = {&b};
+            rc = check_cuda(cudaLaunchCooperativeKernel((void*)build_member_table_coop_kernel, dim3(grid), dim3(kBuildThreads),
+                                                        args, 0, st), "build_member_table (cooperative) launch");
+        } else {
+            rc = check_cuda(cudaMemsetAsync(b.table, 0xFF, (size_t)w.n_buckets * 32, st), "table memset");
+            if (rc) return rc;
+            build_member_table_flat_kernel<<<(unsigned)w.n_tiles, kBuildThreads, 0, st>>>(b);
+            rc = check_cuda(cudaGetLastError(), "build_member_table launch");
+        }
+        count_launch(1);
+        if (rc) return rc;
+        a.table = b.table;
+        plan->table = true;
+    }
+    timing_end(0, st);
+    a.row32 = b.row32;
     return TRW_OK;
 }
 
@@ -395,24 +575,34 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
     a.targets = targets; a.n_walks = n_walks; a.walk_id_offset = walk_id_offset;
     a.out = out; a.out_row_stride = out_row_stride;
     const bool stage = plan.stage && (((uintptr_t)out & 7) == 0);
-    if (plan.persist) set_row_ptr_window(st, a.row_ptr, (size_t)(a.n_nodes + 1) * 8, plan.device, true);
-    constexpr int BLOCK = 256;
+    const bool row32 = a.row32 != nullptr;
+    if (plan.persist) {
+        if (row32) set_row_window(st, a.row32, (size_t)(a.n_nodes + 1) * 4, plan.device, true);
+        else set_row_window(st, a.row_ptr, (size_t)(a.n_nodes + 1) * 8, plan.device, true);
+    }
     timing_begin(1, st);
     if (plan.uniform) {
-        if (stage) launch_uniform<BLOCK, true>(a, st); else launch_uniform<BLOCK, false>(a, st);
-    } else if (plan.table) {
-        if (stage) launch_n2v<BLOCK, true, true>(a, plan.speculate, st); else launch_n2v<BLOCK, false, true>(a, plan.speculate, st);
+        if (!stage) launch_uniform<false, false>(a, st);
+        else if (row32) launch_uniform<true, true>(a, st);
+        else launch_uniform<true, false>(a, st);
     } else {
-        if (stage) launch_n2v<BLOCK, true, false>(a, plan.speculate, st); else launch_n2v<BLOCK, false, false>(a, plan.speculate, st);
+        launch_n2v(a, stage, plan.table, row32 && stage, plan.speculate, plan.min_ctas, st);
     }
     timing_end(1, st);
     count_launch(1);
     const int rc = check_cuda(cudaGetLastError(), "walk kernel launch");
-    if (plan.persist) set_row_ptr_window(st, nullptr, 0, plan.device, false);
+    if (plan.persist) set_row_window(st, nullptr, 0, plan.device, false);
     return rc;
 }
 
 }  // namespace trw
+
+using namespace trw;
+
+extern "C" size_t trw_walk_csr_workspace_bytes(int64_t n_nodes, int64_t nnz, double p, double q) {
+    if (n_nodes < 0 || nnz < 0) return 0;
+    return ws_layout(n_nodes, nnz, p == 1.0 && q == 1.0).total;
+}
 
 extern "C" int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                             const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, double p, double q,

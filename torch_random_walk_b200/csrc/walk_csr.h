@@ -15,12 +15,14 @@ struct WalkArgs {
     int64_t* out;
     int64_t out_row_stride;
     const uint32_t* table;
+    const uint32_t* row32;  // uint32 copy of row_ptr (nullptr: read the int64 row_ptr)
     uint64_t thr0, thr1, thr2;  // acceptance thresholds on a 32-bit uniform, scaled by 2^32
 };
 
 struct CsrWalkPlan {
     WalkArgs a;  // graph side filled by csr_walk_prepare; shard side by csr_walk_launch
     int device;
+    int min_ctas;
     bool uniform, table, speculate, stage, persist;
 };
 

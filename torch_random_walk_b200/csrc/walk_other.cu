@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(BLOCK) edge_list_uniform_kernel(const IndexedW
     if (i >= a.n_walks) return;
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowStager<BLOCK> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x);
+    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, make_policy_evict_first());
     const int64_t start = __ldg(a.targets + i);
     const int64_t jump = a.restart ? start : a.pad;
     const int L = a.walk_length;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(BLOCK) edge_list_biased_kernel(const IndexedWa
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
     RowStager<BLOCK> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x);
+    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, make_policy_evict_first());
     const int64_t start = __ldg(a.targets + i);
     const int64_t jump = a.restart ? start : a.pad;
     const int L = a.walk_length;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(BLOCK) triples_walk_kernel(const IndexedWalkAr
     if (i >= a.n_walks) return;
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowStager<BLOCK> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x);
+    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, make_policy_evict_first());
     const int L = a.walk_length;
     int64_t v = __ldg(a.targets + i);
     o.put(0, v, L == 0);
