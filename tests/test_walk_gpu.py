@@ -89,7 +89,7 @@ def test_shards_are_bit_identical_to_one_call(native, p, q):
         assert torch.equal(torch.cat(parts), full), world
 
 
-DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 1, "n2v_min_ctas": 4,
+DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": 4,
             "build_tiles_per_cta": 2}
 
 
@@ -101,7 +101,7 @@ def test_kernel_variants_agree_bit_for_bit(native):
     rp, ci = cuda(rp, ci)
     nodes = torch.arange(4000, device="cuda")
     variants = [{}, {"n2v_table": 0}, {"n2v_speculate": 0}, {"n2v_speculate": 1}, {"stage_output": 0}, {"row32": 0},
-                {"build_mode": 0}, {"n2v_min_ctas": 5}, {"n2v_min_ctas": 6}, {"build_tiles_per_cta": 1},
+                {"build_mode": 0}, {"build_mode": 1}, {"n2v_min_ctas": 5}, {"n2v_min_ctas": 6}, {"build_tiles_per_cta": 1},
                 {"n2v_table": 0, "row32": 0, "stage_output": 0}, {"build_mode": 0, "row32": 0, "n2v_min_ctas": 6}]
     base = None
     try:
@@ -120,23 +120,26 @@ def test_kernel_variants_agree_bit_for_bit(native):
 
 
 def test_table_build_on_skewed_graph_matches_scan(native):
-    """The cooperative, chunked table build against the linear scan on a graph with hubs, many
-    empty rows and more tiles than one chunk holds."""
+    """The three table builds (tiled shared-memory, cooperative chunks, flat) against each other and
+    against the linear scan, on a graph with hubs, many empty rows and many tiles."""
     from torch_random_walk_b200 import rmat
 
     rp, ci = rmat.rmat_csr(17, 16, device="cuda", seed=5)
     deg = rp[1:] - rp[:-1]
     nodes = torch.nonzero(deg > 0).flatten()[:50000].contiguous()
+    assert int(deg.max()) >= 2048  # hub rows take the global-CAS path of the tiled build
     a = native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1)
     try:
         native.set_option("build_mode", 0)
         b = native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1)
+        native.set_option("build_mode", 1)
+        b1 = native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1)
         native.set_option("n2v_table", 0)
         c = native.walk(rp, ci, nodes[:3000].contiguous(), 0.5, 2.0, 12, 1)
     finally:
-        native.set_option("build_mode", 1)
+        native.set_option("build_mode", 2)
         native.set_option("n2v_table", 1)
-    assert torch.equal(a, b)
+    assert torch.equal(a, b) and torch.equal(a, b1)
     assert torch.equal(a[:3000], c)
 
 
@@ -241,20 +244,47 @@ def test_second_order_statistics_match_analytic_and_oracle(rw, orc, golden, p, q
     assert chi2_pvalue(chi2_2, dof_2) > 0.01, ("vs oracle", chi2_2, dof_2)
 
 
+def _class_tv(counts, row_ptr, col_idx, p, q, n):
+    """Count-weighted mean TV over the three acceptance classes (return / common neighbour / far)
+    per (t,v) context: the quantity the rejection rule controls, and far less noisy than the
+    per-neighbour TV when a context has ~30 outcomes."""
+    from collections import defaultdict
+
+    rp, ci = row_ptr.numpy(), col_idx.numpy()
+    adj = [set(ci[rp[i]:rp[i + 1]].tolist()) for i in range(n)]
+    ctx = defaultdict(lambda: [0, 0, 0])
+    for key, c in counts.items():
+        tv_, x = divmod(key, n)
+        t, v = divmod(tv_, n)
+        ctx[(t, v)][0 if x == t else (1 if x in adj[t] else 2)] += c
+    tv_sum, total = 0.0, 0
+    for (t, v), obs in ctx.items():
+        nb = ci[rp[v]:rp[v + 1]].tolist()
+        w = [sum(1.0 / p for x in nb if x == t), sum(1.0 for x in nb if x != t and x in adj[t]),
+             sum(1.0 / q for x in nb if x != t and x not in adj[t])]
+        m, z = sum(obs), sum(w)
+        tv_sum += 0.5 * sum(abs(o / m - e / z) for o, e in zip(obs, w)) * m
+        total += m
+    return tv_sum / total
+
+
 def test_second_order_statistics_with_table_rows(rw, orc):
-    """Same criterion on a graph whose rows are long enough (>= 16) to go through the hashed
-    membership table, with triangles so that all three acceptance classes occur."""
+    """Same criterion on a graph whose rows are long enough (>= 12) to go through the hashed
+    membership table, with triangles so that all three acceptance classes occur.  With ~30
+    outcomes per context the per-neighbour TV at 1e7 samples is dominated by sampling noise
+    (~0.02), so the TV bound is applied to the acceptance classes; chi-square stays per neighbour."""
     rp, ci = random_csr(11, 60, 40)
     n = 60
     assert int((rp[1:] - rp[:-1]).min()) >= 16
     p, q = 0.5, 2.0
     table = node2vec_probs(rp, ci, p, q)
-    nodes = torch.arange(n).repeat_interleave(2000)
+    nodes = torch.arange(n).repeat_interleave(3000)
     walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, 100, 5)
     got = second_order_counts(walks, n)
     chi2, dof, tv = chi2_and_tv(got, table, n)
     assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
-    assert tv < 1e-2
+    assert tv < 4e-2
+    assert _class_tv(got, rp, ci, p, q, n) < 1e-2
     ref_counts = second_order_counts(orc.walk(rp, ci, torch.arange(n).repeat_interleave(300), p, q, 100, 3), n)
     chi2_2, dof_2 = two_sample_chi2(got, ref_counts, n)
     assert chi2_pvalue(chi2_2, dof_2) > 0.01, (chi2_2, dof_2)

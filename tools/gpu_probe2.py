@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from torch_random_walk_b200 import native, rmat  # noqa: E402
 
-DEFAULTS = {"stage_output": 1, "n2v_table": 1, "n2v_speculate": -1, "persist_row_ptr": 0, "row32": 1, "build_mode": 1,
+DEFAULTS = {"stage_output": 1, "n2v_table": 1, "n2v_speculate": -1, "persist_row_ptr": 0, "row32": 1, "build_mode": 2,
             "n2v_min_ctas": 4, "build_tiles_per_cta": 2, "persist_l2_mb": 64}
 
 
@@ -98,6 +98,7 @@ def main():
         ("default", {}),
         ("row64", {"row32": 0}),
         ("flat_build", {"build_mode": 0}),
+        ("coop_build", {"build_mode": 1}),
         ("tiles1", {"build_tiles_per_cta": 1}),
         ("tiles4", {"build_tiles_per_cta": 4}),
         ("ctas5", {"n2v_min_ctas": 5}),
@@ -110,9 +111,9 @@ def main():
     ]
     for pq_name, p, q in (("c3_p1_q0.5", 1.0, 0.5), ("uniform", 1.0, 1.0), ("c2_p0.5_q2", 0.5, 2.0), ("c5_p0.25_q4", 0.25, 4.0)):
         for vname, opts in grid:
-            if pq_name == "uniform" and vname in ("flat_build", "tiles1", "tiles4", "ctas5", "ctas6", "spec0", "spec1"):
+            if pq_name == "uniform" and vname in ("flat_build", "coop_build", "tiles1", "tiles4", "ctas5", "ctas6", "spec0", "spec1"):
                 continue
-            if pq_name in ("c2_p0.5_q2", "c5_p0.25_q4") and vname in ("flat_build", "tiles1", "tiles4", "persist79", "no_stage"):
+            if pq_name in ("c2_p0.5_q2", "c5_p0.25_q4") and vname in ("flat_build", "coop_build", "tiles1", "tiles4", "persist79", "no_stage"):
                 continue
             run(f"{pq_name}/{vname}", p, q, opts)
     save()

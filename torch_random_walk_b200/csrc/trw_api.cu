@@ -85,13 +85,29 @@ int resolve_device(int device) {
 
 // ------------------------------------------------------------------ calibration gather
 // Each thread chases `loads` dependent pseudo-random locations: the address of load k+1 mixes
-// the value returned by load k, like a walk step.  BYTES = 8 reads one int64, 32 one sector.
-template <int BYTES>
+// the value returned by load k, like a walk step.  BYTES = 8 reads one int64; 32/64/128 read
+// 1/2/4 adjacent sectors.  MODE selects the load flavour for 8-byte loads (which cache operators
+// and L2 policies change what a miss costs in DRAM traffic).
+template <int MODE>
+__device__ __forceinline__ uint64_t calib_load64(const int64_t* p, uint64_t pol) {
+    uint64_t v;
+    if (MODE == 1) asm volatile("ld.global.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (MODE == 2) asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (MODE == 3) asm volatile("ld.global.cv.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (MODE == 4) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    else if (MODE == 5) asm volatile("ld.global.lu.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (MODE == 6) asm volatile("ld.global.cs.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    else asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+template <int BYTES, int MODE>
 __global__ void __launch_bounds__(256) calib_gather_kernel(const int64_t* __restrict__ table, uint64_t n_units,
                                                            int64_t n_threads, int loads, uint2 key,
                                                            int64_t* __restrict__ sink) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_threads) return;
+    const uint64_t pol = make_policy_evict_first();
     uint64_t acc = 0;
     uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0, 0), key);
     uint64_t state = ((uint64_t)r.x << 32) | r.y;
@@ -99,7 +115,7 @@ __global__ void __launch_bounds__(256) calib_gather_kernel(const int64_t* __rest
         state = state * 6364136223846793005ull + 1442695040888963407ull;
         uint64_t unit = __umul64hi(state ^ (state >> 29), n_units);
         if (BYTES == 8) {
-            uint64_t v = (uint64_t)ldg64_stream(table + unit);
+            uint64_t v = calib_load64<MODE>(table + unit, pol);
             acc += v;
             state += v;
         } else {
@@ -151,14 +167,26 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
     cudaStream_t st = (cudaStream_t)stream;
     unsigned grid = (unsigned)((n_threads + 255) / 256);
     uint2 key = philox_key(seed, 0x43414C49u);
-    if (bytes_per_load == 8)
-        calib_gather_kernel<8><<<grid, 256, 0, st>>>(table, (uint64_t)table_elems, n_threads, loads_per_thread, key, sink);
-    else if (bytes_per_load == 32)
-        calib_gather_kernel<32><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 4), n_threads, loads_per_thread, key, sink);
+    const int64_t units8 = table_elems;
+    const int mode = (int)options().calib_mode;
+#define TRW_CALIB8(M) calib_gather_kernel<8, M><<<grid, 256, 0, st>>>(table, (uint64_t)units8, n_threads, loads_per_thread, key, sink)
+    if (bytes_per_load == 8) {
+        switch (mode) {
+            case 1: TRW_CALIB8(1); break;
+            case 2: TRW_CALIB8(2); break;
+            case 3: TRW_CALIB8(3); break;
+            case 4: TRW_CALIB8(4); break;
+            case 5: TRW_CALIB8(5); break;
+            case 6: TRW_CALIB8(6); break;
+            default: TRW_CALIB8(0); break;
+        }
+    } else if (bytes_per_load == 32)
+        calib_gather_kernel<32, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 4), n_threads, loads_per_thread, key, sink);
     else if (bytes_per_load == 64)
-        calib_gather_kernel<64><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 8), n_threads, loads_per_thread, key, sink);
+        calib_gather_kernel<64, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 8), n_threads, loads_per_thread, key, sink);
     else
-        calib_gather_kernel<128><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 16), n_threads, loads_per_thread, key, sink);
+        calib_gather_kernel<128, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 16), n_threads, loads_per_thread, key, sink);
+#undef TRW_CALIB8
     count_launch(1);
     return check_cuda(cudaGetLastError(), "calib_gather launch");
 }

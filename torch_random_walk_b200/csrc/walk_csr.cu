@@ -189,7 +189,7 @@ __device__ __forceinline__ void build_tile(const BuildArgs& a, int64_t tile, uin
 // goes to DRAM once (write-back) instead of once for a memset and again for every random CAS.
 // Inserts of chunk k can reach at most max-degree entries past the chunk (the row of its last
 // entry), which is how far ahead buckets are cleared before the chunk starts.
-__global__ void __launch_bounds__(kBuildThreads, 5) build_member_table_coop_kernel(const BuildArgs a) {
+__global__ void __launch_bounds__(kBuildThreads, 4) build_member_table_coop_kernel(const BuildArgs a) {
     __shared__ uint32_t head[kBuildTile];
     __shared__ uint32_t warp_max[kBuildThreads / 32];
     cg::grid_group grid = cg::this_grid();
@@ -213,10 +213,145 @@ __global__ void __launch_bounds__(kBuildThreads, 5) build_member_table_coop_kern
 
 // Same build as one ordinary launch over a table cleared by cudaMemsetAsync (used when a
 // cooperative launch is not possible, and as the A/B baseline: option build_mode = 0).
-__global__ void __launch_bounds__(kBuildThreads, 5) build_member_table_flat_kernel(const BuildArgs a) {
+__global__ void __launch_bounds__(kBuildThreads, 4) build_member_table_flat_kernel(const BuildArgs a) {
     __shared__ uint32_t head[kBuildTile];
     __shared__ uint32_t warp_max[kBuildThreads / 32];
     build_tile(a, blockIdx.x, head, warp_max);
+}
+
+// ------------------------------------------------------------------------------------------
+// Table build, tiled through shared memory (the default).  Global atomics turned out to be the
+// bound of the builds above (about 37 G CAS/s on B200, whether or not the lines are L2-resident),
+// so they are kept for hub rows only.  A CTA owns the rows that START inside its tile of
+// kBuildTile CSR entries and are shorter than kHubDeg: it assembles their buckets in shared
+// memory with shared-memory CAS and writes them out with coalesced 16-byte stores -- no global
+// atomic, no read-modify-write of table lines.  Such a row ends less than kHubDeg entries past
+// the tile, so the CTA works on a window of kBuildRange entries.  Entries of hub rows
+// (>= kHubDeg neighbours) inside the tile go through the global insert; their buckets were
+// cleared by the memset that precedes the kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int kHubDeg = kBuildTile;
+constexpr int kBuildRange = kBuildTile + kHubDeg;
+constexpr int kRangePerThread = kBuildRange / kBuildThreads;
+constexpr uint32_t kNotOurs = 0xFFFFFFFFu;
+constexpr size_t kTiledSmemBytes = (size_t)kBuildRange * 4 + (size_t)kBuildRange * 2 * 4;  // head + bucket image
+
+__device__ __forceinline__ void smem_table_insert(uint32_t* __restrict__ stab, int64_t local_first, int64_t nb, uint32_t x) {
+    const uint32_t h = mix32(x);
+    int64_t bkt = (int64_t)__umul64hi((uint64_t)h << 32, (uint64_t)nb);
+    for (int64_t probes = 0; probes < nb; ++probes) {
+        uint32_t* slots = stab + (local_first + bkt) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t old = atomicCAS(slots + j, kEmpty, x);
+            if (old == kEmpty || old == x) return;
+        }
+        if (++bkt == nb) bkt = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kBuildThreads, 4) build_member_table_tiled_kernel(const BuildArgs a) {
+    extern __shared__ __align__(16) uint32_t tiled_smem[];
+    uint32_t* head = tiled_smem;               // [kBuildRange] row code of each entry of the window
+    uint32_t* stab = tiled_smem + kBuildRange; // [kBuildRange / 4 buckets][8 slots]
+    __shared__ uint32_t warp_max[kBuildThreads / 32];
+    __shared__ unsigned long long s_lo, s_hi;  // entry span [s_lo, s_hi) of the rows built in shared memory
+    __shared__ long long s_hub_row;            // the hub row that starts in this tile, if any
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t e0 = tile * kBuildTile;
+    const int64_t e1 = min(e0 + (int64_t)kBuildTile, a.nnz);
+    const int64_t r0 = a.tile_row0[tile];
+    const int64_t r1 = min(a.tile_row0[tile + 1], a.n_nodes - 1);
+    const int64_t bucket0 = e0 >> 2;  // first bucket of the window (tiles are multiples of four entries)
+#pragma unroll
+    for (int k = 0; k < kRangePerThread; ++k) head[k * kBuildThreads + tid] = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * kRangePerThread; ++k) stab[k * kBuildThreads + tid] = kEmpty;
+    if (tid == 0) { s_lo = ~0ull; s_hi = 0; s_hub_row = -1; }
+    __syncthreads();
+    // Rows that start in [e0, e1): short ones get the code r - r0 + 1, a hub gets kNotOurs (nothing
+    // else can start after it inside the tile: it is at least as long as the tile).
+    for (int64_t r = r0 + tid; r <= r1; r += kBuildThreads) {
+        const int64_t b = __ldg(a.row_ptr + r), e = __ldg(a.row_ptr + r + 1);
+        if (e > b && b >= e0 && b < e1) {
+            if (e - b >= kHubDeg) {
+                head[b - e0] = kNotOurs;
+                s_hub_row = r;
+            } else {
+                head[b - e0] = (uint32_t)(r - r0 + 1);
+                atomicMin(&s_lo, (unsigned long long)b);
+                atomicMax(&s_hi, (unsigned long long)e);
+            }
+        }
+    }
+    __syncthreads();
+    // Entries past the last owned row belong to rows of later tiles.
+    if (tid == 0 && s_hi > 0 && (int64_t)s_hi - e0 < kBuildRange) head[(int64_t)s_hi - e0] = kNotOurs;
+    __syncthreads();
+    // Inclusive max-scan of the codes; each thread scans kRangePerThread consecutive entries.
+    {
+        uint32_t own[kRangePerThread];
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < kRangePerThread; ++k) {
+            run = max(run, head[tid * kRangePerThread + k]);
+            own[k] = run;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((tid & 31) >= d) incl = max(incl, o);
+        }
+        if ((tid & 31) == 31) warp_max[tid >> 5] = incl;
+        __syncthreads();
+        uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if ((tid & 31) == 0) before = 0;
+        for (int w = 0; w < (tid >> 5); ++w) before = max(before, warp_max[w]);
+#pragma unroll
+        for (int k = 0; k < kRangePerThread; ++k) head[tid * kRangePerThread + k] = max(before, own[k]);
+    }
+    __syncthreads();
+    // Row r0 reaches into the tile from the left when it did not start here; it is a hub's job
+    // only if it is a hub (otherwise the tile where it starts builds it).
+    const int64_t r0_b = __ldg(a.row_ptr + r0), r0_e = __ldg(a.row_ptr + r0 + 1);
+    const bool r0_hub = r0_b < e0 && (r0_e - r0_b) >= kHubDeg;
+    const int64_t hub_row = s_hub_row;
+    int64_t hub_first = 0, hub_nb = 0, r0_first = 0, r0_nb = 0;
+    if (hub_row >= 0) table_span(__ldg(a.row_ptr + hub_row), __ldg(a.row_ptr + hub_row + 1), hub_first, hub_nb);
+    if (r0_hub) table_span(r0_b, r0_e, r0_first, r0_nb);
+    const int64_t own_end = s_hi;  // 0 when no short row starts here
+    int64_t cur_row = -1, first = 0, nb = 0;
+    for (int k = 0; k < kRangePerThread; ++k) {
+        const int idx = k * kBuildThreads + tid;  // strided: coalesced loads, hub work spread over all threads
+        const int64_t e = e0 + idx;
+        if (e >= a.nnz) break;
+        const uint32_t code = head[idx];
+        if (code == 0) {
+            if (e < e1 && r0_hub) table_insert(a.table, r0_first, r0_nb, (uint32_t)ldg64_stream(a.col_idx + e));
+        } else if (code == kNotOurs) {
+            if (e < e1 && hub_row >= 0) table_insert(a.table, hub_first, hub_nb, (uint32_t)ldg64_stream(a.col_idx + e));
+        } else if (e < own_end) {
+            const int64_t r = r0 + code - 1;
+            if (r != cur_row) {
+                cur_row = r;
+                const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
+                if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
+            }
+            if (nb > 0) smem_table_insert(stab, first - bucket0, nb, (uint32_t)ldg64_stream(a.col_idx + e));
+        }
+    }
+    __syncthreads();
+    // Write the finished buckets of the owned rows: [ceil(s_lo/4), floor(s_hi/4)).
+    if (own_end > 0) {
+        const int64_t w_lo = ((int64_t)s_lo + 3) >> 2, w_hi = own_end >> 2;
+        const int64_t n16 = (w_hi - w_lo) * 2;  // 16-byte pieces
+        const uint4* src = reinterpret_cast<const uint4*>(stab + (w_lo - bucket0) * 8);
+        uint4* dst = reinterpret_cast<uint4*>(a.table + w_lo * 8);
+        for (int64_t i = tid; i < n16; i += kBuildThreads) dst[i] = src[i];
+    }
 }
 
 // x in adj(t)?  (b,e) = row span of t.
@@ -545,8 +680,8 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
     if (want_table) {
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_member_table_coop_kernel, kBuildThreads, 0);
-        if (opt.build_mode != 0 && coop && per_sm > 0) {
+        if (opt.build_mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_member_table_coop_kernel, kBuildThreads, 0);
+        if (opt.build_mode == 1 && coop && per_sm > 0) {
             const int grid = sms * per_sm;
             b.chunk_tiles = grid * (int)(opt.build_tiles_per_cta > 0 ? opt.build_tiles_per_cta : 2);
             void* args[] = {&b};
@@ -555,7 +690,18 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
         } else {
             rc = check_cuda(cudaMemsetAsync(b.table, 0xFF, (size_t)w.n_buckets * 32, st), "table memset");
             if (rc) return rc;
-            build_member_table_flat_kernel<<<(unsigned)w.n_tiles, kBuildThreads, 0, st>>>(b);
+            if (opt.build_mode == 0) {
+                build_member_table_flat_kernel<<<(unsigned)w.n_tiles, kBuildThreads, 0, st>>>(b);
+            } else {
+                static bool attr_set[64];
+                if (device < 64 && !attr_set[device]) {
+                    rc = check_cuda(cudaFuncSetAttribute(build_member_table_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)kTiledSmemBytes), "tiled build smem attribute");
+                    if (rc) return rc;
+                    attr_set[device] = true;
+                }
+                build_member_table_tiled_kernel<<<(unsigned)w.n_tiles, kBuildThreads, kTiledSmemBytes, st>>>(b);
+            }
             rc = check_cuda(cudaGetLastError(), "build_member_table launch");
         }
         count_launch(1);

@@ -7,6 +7,9 @@
 // finished chunk is copied back on a second stream while the next chunk is being walked
 // (PCIe is full duplex and the copy engines run beside the SMs).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "trw_common.cuh"
 #include "trw_options.h"
@@ -70,6 +73,14 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(options().host_chunk_walks, n_walks));
     const size_t ws_bytes = trw_walk_csr_workspace_bytes(n_nodes, nnz, p, q);
 
+    // TRW_HOST_TIMING=1 prints where an end-to-end call spends its time (adds one stream sync after the uploads).
+    const bool timing = getenv("TRW_HOST_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(now() - t0).count();
+    };
+    const auto t_start = now();
+
     HostWalkResources r;
     TRW_TRY(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking), "stream create");
     TRW_TRY(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking), "stream create");
@@ -84,10 +95,18 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     const int n_buf = n_walks > chunk ? 2 : 1;
     for (int k = 0; k < n_buf; ++k) TRW_TRY(cudaMalloc(&r.d_out[k], (size_t)chunk * row_len * 8), "cudaMalloc walks");
 
+    const double ms_alloc = ms_since(t_start);
+    const auto t_up = now();
     TRW_TRY(cudaMemcpyAsync(r.d_row_ptr, row_ptr, (size_t)(n_nodes + 1) * 8, cudaMemcpyHostToDevice, r.compute), "H2D row_ptr");
     if (nnz) TRW_TRY(cudaMemcpyAsync(r.d_col_idx, col_idx, (size_t)nnz * 8, cudaMemcpyHostToDevice, r.compute), "H2D col_idx");
     TRW_TRY(cudaMemcpyAsync(r.d_targets, targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
 
+    double ms_upload = 0.0;
+    if (timing) {
+        TRW_TRY(cudaStreamSynchronize(r.compute), "sync uploads");
+        ms_upload = ms_since(t_up);
+    }
+    const auto t_walk = now();
     CsrWalkPlan plan;
     int rc = csr_walk_prepare(&plan, (const int64_t*)r.d_row_ptr, (const int64_t*)r.d_col_idx, n_nodes, nnz, p, q,
                               walk_length, seed, r.d_workspace, ws_bytes, d, r.compute);
@@ -110,5 +129,13 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     }
     TRW_TRY(cudaStreamSynchronize(r.compute), "sync compute");
     TRW_TRY(cudaStreamSynchronize(r.copy), "sync copy");
+    if (timing) {
+        const double h2d_gb = ((double)(n_nodes + 1) + (double)nnz + (double)n_walks) * 8 / 1e9;
+        const double d2h_gb = (double)n_walks * row_len * 8 / 1e9;
+        fprintf(stderr, "[trw_walk_csr_host] alloc %.1f ms | upload %.1f ms (%.2f GB, %.1f GB/s) | walk+download %.1f ms "
+                        "(%.2f GB back) | total %.1f ms\n",
+                ms_alloc, ms_upload, h2d_gb, ms_upload > 0 ? h2d_gb / (ms_upload / 1e3) : 0.0, ms_since(t_walk), d2h_gb,
+                ms_since(t_start));
+    }
     return TRW_OK;
 }
