@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from torch_random_walk_b200 import native, rmat  # noqa: E402
 
 DEFAULTS = {"stage_output": 1, "n2v_table": 1, "n2v_speculate": -1, "persist_row_ptr": 0, "row32": 1, "build_mode": 2,
-            "n2v_min_ctas": 4, "build_tiles_per_cta": 2, "persist_l2_mb": 64}
+            "n2v_min_ctas": 4, "persist_l2_mb": 64}
 
 
 def timed(fn, reps=3, warm=1):
@@ -98,9 +98,6 @@ def main():
         ("default", {}),
         ("row64", {"row32": 0}),
         ("flat_build", {"build_mode": 0}),
-        ("coop_build", {"build_mode": 1}),
-        ("tiles1", {"build_tiles_per_cta": 1}),
-        ("tiles4", {"build_tiles_per_cta": 4}),
         ("ctas5", {"n2v_min_ctas": 5}),
         ("ctas6", {"n2v_min_ctas": 6}),
         ("spec0", {"n2v_speculate": 0}),

@@ -1,0 +1,427 @@
+// Per-call preparation of a CSR graph for the walk kernels: the uint32 row index and the hashed
+// membership table (layout and lookup in member_table.cuh).
+//
+// Global atomics turned out to be the bound of a straightforward build (about 37-45 G CAS/s on
+// B200 whether or not the lines are L2-resident; profiles/), so the shipped build has none on the
+// data path.  Every bucket is assembled in shared memory by exactly one CTA and written once with
+// coalesced 16-byte stores, which also removes the need to clear the table first:
+//   * short rows (< kHubDeg neighbours): the CTA that owns the tile of kBuildTile CSR entries in
+//     which a row STARTS builds all of that row's buckets (build_tiled_kernel);
+//   * hub rows: one CTA per segment of kSegBuckets buckets scans the whole row and keeps the ids
+//     whose home bucket falls into its segment (build_hub_kernel).  The row is re-read once per
+//     segment, from L2.
+// A pre-pass finds the first row of every tile (edge-balanced tiling of a power-law graph), lists
+// the hub rows and their segments, and writes the uint32 row index.
+#include "member_table.cuh"
+#include "trw_options.h"
+
+namespace trw {
+
+constexpr int kBuildThreads = 256;
+constexpr int kBuildPerThread = 8;
+constexpr int kBuildTile = kBuildThreads * kBuildPerThread;  // CSR entries per tile
+constexpr int kHubDeg = kBuildTile;                          // rows at least this long are hubs
+constexpr int kBuildRange = kBuildTile + kHubDeg;            // entries a tile's CTA may touch
+constexpr int kRangePerThread = kBuildRange / kBuildThreads;
+constexpr uint32_t kNotOurs = 0xFFFFFFFFu;
+constexpr size_t kTiledSmemBytes = (size_t)kBuildRange * 4 + (size_t)kBuildRange * 2 * 4;  // codes + bucket image
+constexpr size_t kHubSmemBytes = (size_t)(2 * kSegBuckets) * 32;                             // one segment image
+
+struct HubEntry {
+    int64_t row;
+    uint32_t first_segment;  // index of its first segment in the global segment list
+    uint32_t n_segments;
+};
+struct SegmentWork {
+    int64_t row;
+    int64_t segment;
+};
+
+struct BuildArgs {
+    const int64_t* row_ptr;
+    const int64_t* col_idx;
+    int64_t n_nodes, nnz;
+    uint32_t* table;
+    int64_t* tile_row0;              // [n_tiles + 1]: row holding the first entry of each tile
+    HubEntry* hubs;                  // [max_hubs]
+    SegmentWork* segments;           // [max_segs]
+    unsigned long long* hub_counter; // (number of hubs << 32) | number of hub segments
+    int* failed;                     // set when a segment had no room (see member_table.cuh)
+    uint32_t* row32;                 // optional uint32 copy of row_ptr
+    int64_t n_tiles, n_buckets, max_hubs, max_segs;
+};
+
+// Largest r with row_ptr[r] <= e (the non-empty row that holds CSR entry e).
+__device__ __forceinline__ int64_t row_of_entry(const int64_t* __restrict__ row_ptr, int64_t n_nodes, int64_t e) {
+    int64_t lo = 0, hi = n_nodes;  // invariant: row_ptr[lo] <= e < row_ptr[hi]
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(row_ptr + mid) <= e) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Pre-pass: first row of every tile, the uint32 row index, and the list of hub rows.
+__global__ void __launch_bounds__(256) csr_prepass_kernel(const BuildArgs a) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    if (a.tile_row0) {
+        for (int64_t j = gtid; j <= a.n_tiles; j += gsz) {
+            const int64_t e = j * kBuildTile;
+            a.tile_row0[j] = e < a.nnz ? row_of_entry(a.row_ptr, a.n_nodes, e) : a.n_nodes;
+        }
+    }
+    for (int64_t r = gtid; r <= a.n_nodes; r += gsz) {
+        const int64_t b = __ldg(a.row_ptr + r);
+        if (a.row32) a.row32[r] = (uint32_t)b;
+        if (a.hubs && r < a.n_nodes) {
+            const int64_t e = __ldg(a.row_ptr + r + 1);
+            if (e - b >= kHubDeg) {
+                int64_t first, nb;
+                table_span(b, e, first, nb);
+                const unsigned long long nseg = (unsigned long long)segment_count(nb);
+                const unsigned long long got = atomicAdd(a.hub_counter, (1ull << 32) + nseg);
+                const uint64_t slot = got >> 32;
+                if (slot < (uint64_t)a.max_hubs) a.hubs[slot] = HubEntry{r, (uint32_t)got, (uint32_t)nseg};
+                else *a.failed = 1;
+            }
+        }
+    }
+}
+
+// Expands the hub list into one work item per segment.
+__global__ void __launch_bounds__(256) hub_segments_kernel(const BuildArgs a) {
+    const unsigned long long counter = *a.hub_counter;
+    const int64_t n_hubs = min((int64_t)(counter >> 32), a.max_hubs);
+    if ((int64_t)(counter & 0xFFFFFFFFull) > a.max_segs) { *a.failed = 1; return; }
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n_hubs; h += (int64_t)gridDim.x * blockDim.x) {
+        const HubEntry hub = a.hubs[h];
+        for (uint32_t j = 0; j < hub.n_segments; ++j) a.segments[hub.first_segment + j] = SegmentWork{hub.row, (int64_t)j};
+    }
+}
+
+// Insert into a bucket image in shared memory; probing wraps inside [0, n_buckets).
+__device__ __forceinline__ bool smem_insert(uint32_t* __restrict__ image, int64_t n_buckets, int64_t start, uint32_t x) {
+    int64_t bkt = start;
+    for (int64_t probes = 0; probes < n_buckets; ++probes) {
+        uint32_t* slots = image + bkt * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t old = atomicCAS(slots + j, kEmpty, x);
+            if (old == kEmpty || old == x) return true;
+        }
+        if (++bkt == n_buckets) bkt = 0;
+    }
+    return false;
+}
+
+// Short rows.  A CTA owns the rows that start inside its tile and are shorter than kHubDeg; such
+// a row ends less than kHubDeg entries past the tile, so the CTA works on a window of kBuildRange
+// entries.  The row of every entry is recovered with a max-scan over "a row starts here" codes.
+__global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const BuildArgs a) {
+    extern __shared__ __align__(16) uint32_t tiled_smem[];
+    uint32_t* head = tiled_smem;                // [kBuildRange] row code of each entry of the window
+    uint32_t* image = tiled_smem + kBuildRange; // [kBuildRange / 4 buckets][8 slots]
+    __shared__ uint32_t warp_max[kBuildThreads / 32];
+    __shared__ unsigned long long s_lo, s_hi;   // entry span [s_lo, s_hi) of the rows built here
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t e0 = tile * kBuildTile;
+    const int64_t e1 = min(e0 + (int64_t)kBuildTile, a.nnz);
+    const int64_t r0 = a.tile_row0[tile];
+    const int64_t r1 = min(a.tile_row0[tile + 1], a.n_nodes - 1);
+    const int64_t bucket0 = e0 >> 2;  // first bucket of the window (tiles are multiples of four entries)
+#pragma unroll
+    for (int k = 0; k < kRangePerThread; ++k) head[k * kBuildThreads + tid] = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * kRangePerThread; ++k) image[k * kBuildThreads + tid] = kEmpty;
+    if (tid == 0) { s_lo = ~0ull; s_hi = 0; }
+    __syncthreads();
+    // Rows that start in [e0, e1): short ones get the code r - r0 + 1; a hub gets kNotOurs (nothing
+    // else can start after it inside the tile: it is at least as long as the tile).
+    for (int64_t r = r0 + tid; r <= r1; r += kBuildThreads) {
+        const int64_t b = __ldg(a.row_ptr + r), e = __ldg(a.row_ptr + r + 1);
+        if (e > b && b >= e0 && b < e1) {
+            if (e - b >= kHubDeg) {
+                head[b - e0] = kNotOurs;
+            } else {
+                head[b - e0] = (uint32_t)(r - r0 + 1);
+                atomicMin(&s_lo, (unsigned long long)b);
+                atomicMax(&s_hi, (unsigned long long)e);
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t own_end = (int64_t)s_hi;  // 0 when no short row starts here
+    if (own_end == 0) return;
+    // Entries past the last owned row belong to rows of later tiles.
+    if (tid == 0 && own_end - e0 < kBuildRange) head[own_end - e0] = kNotOurs;
+    __syncthreads();
+    {   // inclusive max-scan of the codes; each thread scans kRangePerThread consecutive entries
+        uint32_t own[kRangePerThread];
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < kRangePerThread; ++k) {
+            run = max(run, head[tid * kRangePerThread + k]);
+            own[k] = run;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((tid & 31) >= d) incl = max(incl, o);
+        }
+        if ((tid & 31) == 31) warp_max[tid >> 5] = incl;
+        __syncthreads();
+        uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if ((tid & 31) == 0) before = 0;
+        for (int w = 0; w < (tid >> 5); ++w) before = max(before, warp_max[w]);
+#pragma unroll
+        for (int k = 0; k < kRangePerThread; ++k) head[tid * kRangePerThread + k] = max(before, own[k]);
+    }
+    __syncthreads();
+    // Fetch all of this thread's entries before the first insert (strided: coalesced), so the
+    // window costs one DRAM latency, not one per entry.
+    uint32_t xs[kRangePerThread];
+#pragma unroll
+    for (int k = 0; k < kRangePerThread; ++k) {
+        const int idx = k * kBuildThreads + tid;
+        const uint32_t code = head[idx];
+        const bool ours = code != 0 && code != kNotOurs && e0 + idx < own_end;
+        xs[k] = ours ? (uint32_t)ldg64_stream(a.col_idx + e0 + idx) : kEmpty;
+    }
+    int64_t cur_row = -1, first = 0, nb = 0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < kRangePerThread; ++k) {
+        if (xs[k] == kEmpty) continue;  // not ours (ids never equal the EMPTY marker in table mode)
+        const int64_t r = r0 + head[k * kBuildThreads + tid] - 1;
+        if (r != cur_row) {
+            cur_row = r;
+            const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
+            if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
+        }
+        // a short row is a single segment: probing wraps over the whole row, capacity is guaranteed
+        if (nb > 0) ok &= smem_insert(image + (first - bucket0) * 8, nb, home_bucket(xs[k], nb), xs[k]);
+    }
+    if (!ok) *a.failed = 1;
+    __syncthreads();
+    // Write the finished buckets of the owned rows: [ceil(s_lo/4), floor(s_hi/4)).
+    const int64_t w_lo = ((int64_t)s_lo + 3) >> 2, w_hi = own_end >> 2;
+    const int64_t n16 = (w_hi - w_lo) * 2;  // 16-byte pieces
+    const uint4* src = reinterpret_cast<const uint4*>(image + (w_lo - bucket0) * 8);
+    uint4* dst = reinterpret_cast<uint4*>(a.table + w_lo * 8);
+    for (int64_t i = tid; i < n16; i += kBuildThreads) dst[i] = src[i];
+}
+
+// Hub rows: persistent CTAs, one segment at a time.
+__global__ void __launch_bounds__(kBuildThreads, 3) build_hub_kernel(const BuildArgs a) {
+    extern __shared__ __align__(16) uint32_t hub_image[];  // up to 2*kSegBuckets-1 buckets
+    const int tid = threadIdx.x;
+    const int64_t n_segments = (int64_t)(*a.hub_counter & 0xFFFFFFFFull);
+    if (n_segments > a.max_segs) return;  // flagged by hub_segments_kernel
+    for (int64_t c = blockIdx.x; c < n_segments; c += gridDim.x) {
+        const SegmentWork work = a.segments[c];
+        const int64_t b = __ldg(a.row_ptr + work.row), e = __ldg(a.row_ptr + work.row + 1);
+        int64_t first, nb;
+        table_span(b, e, first, nb);
+        const int64_t nseg = segment_count(nb);
+        const int64_t lo = work.segment << kSegShift;
+        const int64_t hi = (work.segment == nseg - 1) ? nb : lo + kSegBuckets;
+        const int64_t size = hi - lo;
+        for (int64_t i = tid; i < size * 8; i += kBuildThreads) hub_image[i] = kEmpty;
+        __syncthreads();
+        bool ok = true;
+        // four independent loads in flight per thread; the row comes from L2 after its first reader
+        for (int64_t i = b + tid; i < e; i += 4 * kBuildThreads) {
+            uint32_t x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t idx = i + (int64_t)u * kBuildThreads;
+                x[u] = idx < e ? (uint32_t)__ldg(a.col_idx + idx) : kEmpty;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (x[u] == kEmpty) continue;
+                const int64_t home = home_bucket(x[u], nb);
+                if (home >= lo && home < hi) ok &= smem_insert(hub_image, size, home - lo, x[u]);
+            }
+        }
+        if (!ok) *a.failed = 1;
+        __syncthreads();
+        const uint4* src = reinterpret_cast<const uint4*>(hub_image);
+        uint4* dst = reinterpret_cast<uint4*>(a.table + (first + lo) * 8);
+        for (int64_t i = tid; i < size * 2; i += kBuildThreads) dst[i] = src[i];
+        __syncthreads();  // the image is reused by the next segment
+    }
+}
+
+// Reference build (option build_mode = 0): every entry is inserted with a global CAS into a table
+// cleared by cudaMemsetAsync.  Same placement rule, kept as the A/B baseline of the tiled build.
+__device__ __forceinline__ bool global_insert(uint32_t* __restrict__ table, int64_t first, int64_t nb, uint32_t x) {
+    int64_t bkt = home_bucket(x, nb), lo, hi;
+    probe_segment(nb, bkt, lo, hi);
+    for (int64_t probes = lo; probes < hi; ++probes) {
+        uint32_t* slots = table + (first + bkt) * 8;
+        // Snapshot the bucket, then claim the first EMPTY slot seen; a lost race just moves on.
+        const uint4 lo4 = ld_relaxed_u32x4(slots), hi4 = ld_relaxed_u32x4(slots + 4);
+        const uint32_t snap[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (snap[j] == x) return true;
+            if (snap[j] == kEmpty) {
+                const uint32_t old = atomicCAS(slots + j, kEmpty, x);
+                if (old == kEmpty || old == x) return true;
+            }
+        }
+        if (++bkt == hi) bkt = lo;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kBuildThreads, 4) build_flat_kernel(const BuildArgs a) {
+    __shared__ uint32_t head[kBuildTile];
+    __shared__ uint32_t warp_max[kBuildThreads / 32];
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t e0 = tile * kBuildTile;
+    const int64_t e1 = min(e0 + (int64_t)kBuildTile, a.nnz);
+    const int64_t r0 = a.tile_row0[tile];
+    const int64_t r1 = min(a.tile_row0[tile + 1], a.n_nodes - 1);
+#pragma unroll
+    for (int k = 0; k < kBuildPerThread; ++k) head[k * kBuildThreads + tid] = 0;
+    __syncthreads();
+    for (int64_t r = r0 + 1 + tid; r <= r1; r += kBuildThreads) {
+        const int64_t b = __ldg(a.row_ptr + r), e = __ldg(a.row_ptr + r + 1);
+        if (e > b && b < e1) head[b - e0] = (uint32_t)(r - r0);
+    }
+    __syncthreads();
+    uint32_t own[kBuildPerThread];
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < kBuildPerThread; ++k) {
+        run = max(run, head[tid * kBuildPerThread + k]);
+        own[k] = run;
+    }
+    uint32_t incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((tid & 31) >= d) incl = max(incl, o);
+    }
+    if ((tid & 31) == 31) warp_max[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if ((tid & 31) == 0) before = 0;
+    for (int w = 0; w < (tid >> 5); ++w) before = max(before, warp_max[w]);
+
+    const int64_t mine = e0 + (int64_t)tid * kBuildPerThread;
+    int64_t cur_row = -1, first = 0, nb = 0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < kBuildPerThread; ++k) {
+        if (mine + k >= e1) break;
+        const int64_t r = r0 + max(before, own[k]);
+        if (r != cur_row) {
+            cur_row = r;
+            const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
+            if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
+        }
+        if (nb > 0) ok &= global_insert(a.table, first, nb, (uint32_t)ldg64_stream(a.col_idx + mine + k));
+    }
+    if (!ok) *a.failed = 1;
+}
+
+// ------------------------------------------------------------------------------------------ host
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform) {
+    CsrWorkspace w{};
+    const bool ids_fit = (uint64_t)n_nodes < 0xFFFFFFFFull;   // neighbour ids must fit the uint32 table slots
+    const bool offsets_fit = (uint64_t)nnz <= 0xFFFFFFFFull;   // row offsets must fit the uint32 row index
+    w.has_table = !uniform && ids_fit && nnz > 0;
+    w.has_row32 = offsets_fit && n_nodes > 0;
+    w.n_tiles = (nnz + kBuildTile - 1) / kBuildTile;
+    w.n_buckets = (nnz + 3) / 4;
+    w.max_hubs = nnz / kHubDeg + 1;
+    w.max_segs = w.n_buckets / 500 + w.max_hubs + 1;  // every segment of a hub has >= 510 buckets
+    size_t off = 0;
+    w.table = off;
+    if (w.has_table) off += align256((size_t)w.n_buckets * 32);
+    w.tile_row0 = off;
+    if (w.has_table) off += align256((size_t)(w.n_tiles + 1) * 8);
+    w.hub_list = off;
+    if (w.has_table) off += align256((size_t)w.max_hubs * sizeof(HubEntry));
+    w.seg_work = off;
+    if (w.has_table) off += align256((size_t)w.max_segs * sizeof(SegmentWork));
+    w.cells = off;
+    if (w.has_table) off += 256;
+    w.row32 = off;
+    if (w.has_row32) off += align256((size_t)(n_nodes + 1) * 4);
+    w.total = off;
+    return w;
+}
+
+int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
+                       const CsrWorkspace& w, bool want_table, bool want_row32, int build_mode, int device,
+                       cudaStream_t st, CsrPrepared* out) {
+    want_table = want_table && w.has_table;
+    want_row32 = want_row32 && w.has_row32;
+    *out = CsrPrepared{};
+    if (!want_table && !want_row32) return TRW_OK;
+    char* ws = (char*)workspace;
+    BuildArgs b{};
+    b.row_ptr = row_ptr; b.col_idx = col_idx; b.n_nodes = n_nodes; b.nnz = nnz;
+    b.n_tiles = w.n_tiles; b.n_buckets = w.n_buckets; b.max_hubs = w.max_hubs; b.max_segs = w.max_segs;
+    b.row32 = want_row32 ? (uint32_t*)(ws + w.row32) : nullptr;
+    int rc;
+    if (want_table) {
+        b.table = (uint32_t*)(ws + w.table);
+        b.tile_row0 = (int64_t*)(ws + w.tile_row0);
+        b.hub_counter = (unsigned long long*)(ws + w.cells);
+        b.failed = (int*)(ws + w.cells + 64);
+        if (build_mode != 0) {
+            b.hubs = (HubEntry*)(ws + w.hub_list);
+            b.segments = (SegmentWork*)(ws + w.seg_work);
+        }
+        rc = check_cuda(cudaMemsetAsync(ws + w.cells, 0, 256, st), "cells memset");
+        if (rc) return rc;
+    }
+    const int sms = sm_count(device);
+    csr_prepass_kernel<<<sms * 8, 256, 0, st>>>(b);
+    count_launch(1);
+    rc = check_cuda(cudaGetLastError(), "csr_prepass launch");
+    if (rc) return rc;
+    if (want_table) {
+        if (build_mode == 0) {
+            rc = check_cuda(cudaMemsetAsync(b.table, 0xFF, (size_t)w.n_buckets * 32, st), "table memset");
+            if (rc) return rc;
+            build_flat_kernel<<<(unsigned)w.n_tiles, kBuildThreads, 0, st>>>(b);
+            count_launch(1);
+        } else {
+            static bool attr_set[64];
+            if (device >= 64 || !attr_set[device]) {
+                rc = check_cuda(cudaFuncSetAttribute(build_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)kTiledSmemBytes), "tiled build smem attribute");
+                if (rc) return rc;
+                rc = check_cuda(cudaFuncSetAttribute(build_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)kHubSmemBytes), "hub build smem attribute");
+                if (rc) return rc;
+                if (device < 64) attr_set[device] = true;
+            }
+            hub_segments_kernel<<<sms, 256, 0, st>>>(b);
+            build_tiled_kernel<<<(unsigned)w.n_tiles, kBuildThreads, kTiledSmemBytes, st>>>(b);
+            build_hub_kernel<<<sms * 3, kBuildThreads, kHubSmemBytes, st>>>(b);
+            count_launch(3);
+        }
+        rc = check_cuda(cudaGetLastError(), "membership table build launch");
+        if (rc) return rc;
+        out->table = b.table;
+        out->table_failed = b.failed;
+    }
+    out->row32 = b.row32;
+    return TRW_OK;
+}
+
+}  // namespace trw

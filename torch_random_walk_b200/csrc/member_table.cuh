@@ -1,0 +1,108 @@
+// Hashed adjacency-membership table of the node2vec walk: layout, device-side lookup, and the
+// host entry that builds it (member_table.cu).
+//
+// The reference answers "is x a neighbour of t?" by scanning adj(t) (csrc/cuda/rw_cuda.cu:33-57),
+// O(deg) per rejection trial.  Here it is one 32-byte sector.  Row t of the CSR owns the bytes
+// [8*row_ptr[t], 8*row_ptr[t+1]) of a table as large as col_idx; the 32-byte buckets wholly inside
+// that span hold the row's neighbour ids as uint32 (8 slots per bucket, EMPTY = 0xFFFFFFFF), with
+// open addressing over buckets.  No per-row pointer is needed: the bucket range follows from the
+// row span the walk already holds.  A row of degree d >= kMinTableDeg owns nb >= (d-6)/4 buckets,
+// i.e. at least 2d-12 >= d slots; shorter rows are scanned directly (<= 11 ids).
+//
+// Probing stays inside a *segment* of the row's buckets: rows with fewer than 2*kSegBuckets
+// buckets are one segment (so the capacity bound above is a guarantee); longer rows (hubs) are cut
+// into segments of kSegBuckets buckets (the last one up to 2*kSegBuckets-1), which is what lets a
+// CTA assemble one segment in shared memory.  A hub segment holds on average <= 0.67 * capacity
+// entries with a standard deviation of a few dozen, so it cannot fill up short of an adversarial
+// hash collision set; if it ever does, the build raises a flag and the walk falls back to the scan.
+// Lookup: hash -> home bucket -> one sector; a hit, or any EMPTY slot (that bucket never
+// overflowed), ends the probe.
+#pragma once
+
+#include "trw_common.cuh"
+
+namespace trw {
+
+constexpr int64_t kMinTableDeg = 12;
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr int kSegShift = 10;
+constexpr int64_t kSegBuckets = 1ll << kSegShift;
+
+__host__ __device__ __forceinline__ void table_span(int64_t b, int64_t e, int64_t& first, int64_t& nb) {
+    first = (b + 3) >> 2;
+    nb = (e >> 2) - first;
+}
+
+// Home bucket of x in a row of nb buckets, and the segment [lo, hi) probing is confined to.
+__device__ __forceinline__ int64_t home_bucket(uint32_t x, int64_t nb) {
+    return (int64_t)__umul64hi((uint64_t)mix32(x) << 32, (uint64_t)nb);
+}
+__host__ __device__ __forceinline__ int64_t segment_count(int64_t nb) {
+    const int64_t n = nb >> kSegShift;
+    return n > 1 ? n : 1;
+}
+__device__ __forceinline__ void probe_segment(int64_t nb, int64_t home, int64_t& lo, int64_t& hi) {
+    const int64_t nseg = segment_count(nb);
+    int64_t j = home >> kSegShift;
+    if (j > nseg - 1) j = nseg - 1;
+    lo = j << kSegShift;
+    hi = (j == nseg - 1) ? nb : lo + kSegBuckets;
+}
+
+// x in adj(t)?  (b,e) = row span of t.  table == nullptr (or TABLE == false) selects the scan.
+template <bool TABLE>
+__device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const int64_t* __restrict__ col_idx,
+                                          const uint32_t* __restrict__ table, uint64_t pol_stream) {
+    if (TABLE && table != nullptr && e - b >= kMinTableDeg) {
+        int64_t first, nb, lo, hi;
+        table_span(b, e, first, nb);
+        const uint32_t x32 = (uint32_t)x;
+        int64_t bkt = home_bucket(x32, nb);
+        probe_segment(nb, bkt, lo, hi);
+        for (int64_t probes = lo; probes < hi; ++probes) {
+            const Sector64 s = ldg_sector_hint(table + (first + bkt) * 8, pol_stream);
+            const uint32_t w[8] = {(uint32_t)s.a, (uint32_t)(s.a >> 32), (uint32_t)s.b, (uint32_t)(s.b >> 32),
+                                   (uint32_t)s.c, (uint32_t)(s.c >> 32), (uint32_t)s.d, (uint32_t)(s.d >> 32)};
+            bool hit = false, open = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { hit |= (w[j] == x32); open |= (w[j] == kEmpty); }
+            if (hit) return true;
+            if (open) return false;
+            if (++bkt == hi) bkt = lo;
+        }
+        return false;
+    }
+    // Short (or table-less) row: the reference's scan, csrc/cuda/rw_cuda.cu:48-53, eight
+    // independent loads per round so that it is not one dependent chain.
+    for (int64_t i = b; i < e; i += 8) {
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (i + j < e) found |= (ldg64_hint(col_idx + i + j, pol_stream) == x);
+        if (found) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- host side (member_table.cu)
+// Offsets of the per-call scratch inside the caller's workspace (all 256-byte aligned).
+struct CsrWorkspace {
+    size_t table, tile_row0, hub_list, seg_work, cells, row32, total;
+    int64_t n_tiles, n_buckets, max_hubs, max_segs;
+    bool has_table, has_row32;
+};
+CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform);
+
+struct CsrPrepared {
+    const uint32_t* table = nullptr;     // membership table, or nullptr
+    const uint32_t* row32 = nullptr;     // uint32 copy of row_ptr, or nullptr
+    const int* table_failed = nullptr;   // device flag: non-zero when a hub segment overflowed
+};
+
+// Enqueues on `st` the per-call preparation of a CSR graph: the uint32 row index and (node2vec)
+// the membership table.  build_mode: 2 = tiled through shared memory (default), 0 = global CAS.
+int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
+                       const CsrWorkspace& w, bool want_table, bool want_row32, int build_mode, int device,
+                       cudaStream_t st, CsrPrepared* out);
+
+}  // namespace trw

@@ -11,8 +11,7 @@ struct Options {
     int64_t n2v_speculate = -1;   // fetch row_ptr[x] before the membership answer is known: 1 yes, 0 no, -1 by (p,q)
     int64_t n2v_min_ctas = 4;     // __launch_bounds__ min CTAs/SM of the node2vec kernel (4, 5 or 6)
     int64_t row32 = 1;            // 1: re-encode row_ptr as uint32 offsets per call (needs workspace)
-    int64_t build_mode = 2;       // table build: 2 tiled through shared memory (hubs: global CAS); 1 cooperative L2-resident chunks; 0 flat global CAS
-    int64_t build_tiles_per_cta = 2;  // chunk size of the cooperative build, in tiles per CTA
+    int64_t build_mode = 2;       // table build: 2 assembled in shared memory (tiles + hub segments); 0 global CAS (A/B baseline)
     int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
     int64_t host_chunk_walks = 1 << 20;  // walks per pipelined chunk in trw_walk_csr_host
@@ -23,7 +22,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(build_tiles_per_cta) TRW_OPT(calib_mode)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode)
 
 Options& options();
 void count_launch(int n);

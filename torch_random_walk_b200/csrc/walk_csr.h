@@ -15,6 +15,7 @@ struct WalkArgs {
     int64_t* out;
     int64_t out_row_stride;
     const uint32_t* table;
+    const int* table_failed;  // device flag raised by the build when a hub segment overflowed
     const uint32_t* row32;  // uint32 copy of row_ptr (nullptr: read the int64 row_ptr)
     uint64_t thr0, thr1, thr2;  // acceptance thresholds on a 32-bit uniform, scaled by 2^32
 };
