@@ -24,8 +24,8 @@ constexpr int kHubDeg = kBuildTile;                          // rows at least th
 constexpr int kBuildRange = kBuildTile + kHubDeg;            // entries a tile's CTA may touch
 constexpr int kRangePerThread = kBuildRange / kBuildThreads;
 constexpr uint32_t kNotOurs = 0xFFFFFFFFu;
-constexpr size_t kTiledSmemBytes = (size_t)kBuildRange * 4 + (size_t)kBuildRange * 2 * 4;  // codes + bucket image
-constexpr size_t kHubSmemBytes = (size_t)(2 * kSegBuckets) * 32;                             // one segment image
+constexpr size_t kTiledSmemBytes = (size_t)kBuildRange * 4 + (size_t)kBuildRange * 2 * 4 + (size_t)kBuildRange;  // codes + bucket image + counters
+constexpr size_t kHubSmemBytes = (size_t)(2 * kSegBuckets) * 32 + (size_t)(2 * kSegBuckets) * 4;                  // one segment image + counters
 
 struct HubEntry {
     int64_t row;
@@ -100,15 +100,18 @@ __global__ void __launch_bounds__(256) hub_segments_kernel(const BuildArgs a) {
     }
 }
 
-// Insert into a bucket image in shared memory; probing wraps inside [0, n_buckets).
-__device__ __forceinline__ bool smem_insert(uint32_t* __restrict__ image, int64_t n_buckets, int64_t start, uint32_t x) {
+// Insert into a bucket image in shared memory; probing wraps inside [0, n_buckets).  A per-bucket
+// arrival counter hands out the slot, so an insert costs one shared-memory atomicAdd and one plain
+// store (a CAS walk over the slots costs one atomic per occupied slot, and shared-memory atomics
+// are what bounds these kernels).  Counters may run past 8; slots 0..7 are the bucket.
+__device__ __forceinline__ bool smem_insert(uint32_t* __restrict__ image, uint32_t* __restrict__ count, int64_t n_buckets,
+                                            int64_t start, uint32_t x) {
     int64_t bkt = start;
     for (int64_t probes = 0; probes < n_buckets; ++probes) {
-        uint32_t* slots = image + bkt * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t old = atomicCAS(slots + j, kEmpty, x);
-            if (old == kEmpty || old == x) return true;
+        const uint32_t pos = atomicAdd(count + bkt, 1u);
+        if (pos < 8u) {
+            image[bkt * 8 + pos] = x;
+            return true;
         }
         if (++bkt == n_buckets) bkt = 0;
     }
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
     extern __shared__ __align__(16) uint32_t tiled_smem[];
     uint32_t* head = tiled_smem;                // [kBuildRange] row code of each entry of the window
     uint32_t* image = tiled_smem + kBuildRange; // [kBuildRange / 4 buckets][8 slots]
+    uint32_t* count = image + 2 * kBuildRange;  // [kBuildRange / 4] arrivals per bucket
     __shared__ uint32_t warp_max[kBuildThreads / 32];
     __shared__ unsigned long long s_lo, s_hi;   // entry span [s_lo, s_hi) of the rows built here
 
@@ -136,6 +140,8 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
     for (int k = 0; k < kRangePerThread; ++k) head[k * kBuildThreads + tid] = 0;
 #pragma unroll
     for (int k = 0; k < 2 * kRangePerThread; ++k) image[k * kBuildThreads + tid] = kEmpty;
+#pragma unroll
+    for (int k = 0; k < kRangePerThread / 4; ++k) count[k * kBuildThreads + tid] = 0;
     if (tid == 0) { s_lo = ~0ull; s_hi = 0; }
     __syncthreads();
     // Rows that start in [e0, e1): short ones get the code r - r0 + 1; a hub gets kNotOurs (nothing
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
             if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
         }
         // a short row is a single segment: probing wraps over the whole row, capacity is guaranteed
-        if (nb > 0) ok &= smem_insert(image + (first - bucket0) * 8, nb, home_bucket(xs[k], nb), xs[k]);
+        if (nb > 0) ok &= smem_insert(image + (first - bucket0) * 8, count + (first - bucket0), nb, home_bucket(xs[k], nb), xs[k]);
     }
     if (!ok) *a.failed = 1;
     __syncthreads();
@@ -218,6 +224,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
 // Hub rows: persistent CTAs, one segment at a time.
 __global__ void __launch_bounds__(kBuildThreads, 3) build_hub_kernel(const BuildArgs a) {
     extern __shared__ __align__(16) uint32_t hub_image[];  // up to 2*kSegBuckets-1 buckets
+    uint32_t* hub_count = hub_image + 2 * kSegBuckets * 8;
     const int tid = threadIdx.x;
     const int64_t n_segments = (int64_t)(*a.hub_counter & 0xFFFFFFFFull);
     if (n_segments > a.max_segs) return;  // flagged by hub_segments_kernel
@@ -231,21 +238,22 @@ __global__ void __launch_bounds__(kBuildThreads, 3) build_hub_kernel(const Build
         const int64_t hi = (work.segment == nseg - 1) ? nb : lo + kSegBuckets;
         const int64_t size = hi - lo;
         for (int64_t i = tid; i < size * 8; i += kBuildThreads) hub_image[i] = kEmpty;
+        for (int64_t i = tid; i < size; i += kBuildThreads) hub_count[i] = 0;
         __syncthreads();
         bool ok = true;
-        // four independent loads in flight per thread; the row comes from L2 after its first reader
-        for (int64_t i = b + tid; i < e; i += 4 * kBuildThreads) {
-            uint32_t x[4];
+        // eight independent loads in flight per thread; the row comes from L2 after its first reader
+        for (int64_t i = b + tid; i < e; i += 8 * kBuildThreads) {
+            uint32_t x[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int64_t idx = i + (int64_t)u * kBuildThreads;
                 x[u] = idx < e ? (uint32_t)__ldg(a.col_idx + idx) : kEmpty;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 if (x[u] == kEmpty) continue;
                 const int64_t home = home_bucket(x[u], nb);
-                if (home >= lo && home < hi) ok &= smem_insert(hub_image, size, home - lo, x[u]);
+                if (home >= lo && home < hi) ok &= smem_insert(hub_image, hub_count, size, home - lo, x[u]);
             }
         }
         if (!ok) *a.failed = 1;
