@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary (first-order, c2) measurements")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--option", action="append", default=[], help="library option name=value (experiments)")
     args = ap.parse_args()
@@ -298,7 +299,9 @@ def main():
                 "traffic": None, "kernel": "uniform_walk_kernel" if uniform else "node2vec_walk_kernel",
                 "kernel_ms": kernel_ms, "table_build_ms": sum(build_ms) / max(len(build_ms), 1),
                 "algorithmic_bytes_per_step": bps, "steps_per_launch": steps_per_call, "peak_source": peak_src,
-                "whole_call_frac": (value / world) * bps / 1e9 / peak}
+                "whole_call_frac": (value / world) * bps / 1e9 / peak,
+                "note": "on this part a gather that misses L2 moves a full 128-byte line of HBM traffic (profiles/r01_summary.md): "
+                        "measured line traffic, not the 32-byte-sector model behind algorithmic_bytes_per_step, is what the kernel is bound by"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
     if os.path.exists(traffic_file):
         try:
@@ -360,6 +363,42 @@ def main():
                             "sample": f"{kind} csrc/cpu walk on a random sample of degree>0 start nodes, ~8 s per thread "
                                       f"count, same graph/p/q/L; steps/s by threads: { {k: round(v) for k, v in res.items()} }"}
 
+    # ---- secondary lines (N=1 only): the first-order kernel on the same graph and BASELINE configs[1] (c2)
+    others = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        others = {}
+
+        def quick(name, rp_, ci_, tg_, p_, q_, L_):
+            o_ = out[: tg_.numel()] if (L_ == L and tg_.numel() <= n_walks) else torch.empty((tg_.numel(), L_ + 1), dtype=torch.int64, device=dev)
+            for k in range(2):
+                native.walk(rp_, ci_, tg_, p_, q_, L_, 50 + k, out=o_)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(3):
+                native.walk(rp_, ci_, tg_, p_, q_, L_, 60 + k, out=o_)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            b_, w_ = native.last_kernel_ms()
+            first = (p_ == 1.0 and q_ == 1.0)
+            sps = tg_.numel() * L_ / (ms / 1e3)
+            others[name] = {"steps_per_s": sps, "ms_per_call": ms, "kernel_ms": w_, "table_build_ms": b_,
+                            "n_nodes": rp_.numel() - 1, "nnz": ci_.numel(), "walks": tg_.numel(), "p": p_, "q": q_, "walk_length": L_,
+                            "roofline_frac_kernel": tg_.numel() * L_ * BYTES_PER_STEP[first] / (w_ / 1e3) / 1e9 / peak if w_ > 0 else None}
+            log(f"extra {name}: {sps:.3e} steps/s ({ms:.2f} ms/call, kernel {w_:.2f} ms, build {b_:.2f} ms)")
+
+        try:
+            quick("c3_first_order_p1_q1", row_ptr, col_idx, targets, 1.0, 1.0, L)
+            if args.workload != "c2":
+                w2 = WORKLOADS["c2"]
+                rp2, ci2 = build_graph(w2, dev)
+                quick("c2_products_shaped_p0.5_q2", rp2, ci2, start_nodes(rp2), w2["p"], w2["q"], w2["L"])
+                del rp2, ci2
+        except Exception as exc:  # noqa: BLE001
+            log(f"extras failed: {exc!r}")
+            others["error"] = repr(exc)
+
     if rank == 0:
         line = {
             "metric": "walk_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
@@ -371,7 +410,7 @@ def main():
                        "l2_policy": "inputs (CSR %.1f GB) and output (%.1f GB) exceed the 126 MB L2; no flush needed"
                                     % ((nnz + n_nodes) * 8 / 1e9, n_walks * (L + 1) * 8 / 1e9),
                        "options": overrides},
-            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "output_valid": valid, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "output_valid": valid, "roofline": roofline, "cpu_baseline": cpu_baseline, "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

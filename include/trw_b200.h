@@ -80,12 +80,16 @@ int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes
 
 /* Same computation with every buffer in HOST memory (pinned or pageable): stages the graph and
  * the start nodes to the device, walks in chunks and streams finished chunks back while the
- * next ones run.  Allocates and frees its own device memory and returns after `out` is
- * complete.  This is the end-to-end path a caller holding CPU tensors uses. */
+ * next ones run.  Allocates its own device memory (kept between calls, grow-only, until
+ * trw_release_cached_buffers) and returns after `out` is complete.  This is the end-to-end
+ * path a caller holding CPU tensors uses. */
 int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                       const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
                       double p, double q, int walk_length, int64_t seed,
                       int64_t* out, int device);
+
+/* Frees the device buffers, streams and events trw_walk_csr_host keeps between calls. */
+void trw_release_cached_buffers(void);
 
 /* ---------------------------------------------------------------------------------------
  * Edge-list walks.   Replaces walk_edge_list() -> walk_edge_list_gpu():

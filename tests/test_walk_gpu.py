@@ -89,7 +89,7 @@ def test_shards_are_bit_identical_to_one_call(native, p, q):
         assert torch.equal(torch.cat(parts), full), world
 
 
-DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": 4}
+DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": 4, "n2v_fold": 1}
 
 
 def test_kernel_variants_agree_bit_for_bit(native):
@@ -158,6 +158,39 @@ def test_unsorted_rows_and_duplicate_edges(native):
         native.set_option("n2v_table", 1)
     assert torch.equal(a, b)
     check_walks_follow_edges(a, rp, ci, nodes)
+    # return-edge folding needs duplicate-free rows: the prepare step must have switched it off here
+    native.set_option("n2v_fold", 0)
+    try:
+        c = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+    finally:
+        native.set_option("n2v_fold", 1)
+    assert torch.equal(a, c)
+
+
+def test_folding_changes_the_draws_not_the_law(native, golden):
+    """With strictly increasing rows and 1/p > max(1, 1/q) the folded envelope is used: other draws,
+    same distribution (the statistical tests below run with it); switching it off restores the
+    plain-rejection stream bit for bit."""
+    rp, ci = cuda(*random_csr(6, 2000, 20))
+    nodes = torch.arange(2000, device="cuda")
+    folded = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+    native.set_option("n2v_fold", 0)
+    try:
+        plain = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+        plain2 = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+    finally:
+        native.set_option("n2v_fold", 1)
+    assert torch.equal(plain, plain2) and not torch.equal(folded, plain)
+    check_walks_follow_edges(folded, rp, ci, nodes)
+    check_walks_follow_edges(plain, rp, ci, nodes)
+    # p >= min(1, q): nothing to fold, the option is inert
+    a = native.walk(rp, ci, nodes, 1.0, 0.5, 30, 5)
+    native.set_option("n2v_fold", 0)
+    try:
+        b = native.walk(rp, ci, nodes, 1.0, 0.5, 30, 5)
+    finally:
+        native.set_option("n2v_fold", 1)
+    assert torch.equal(a, b)
 
 
 def test_dead_end_and_isolated_nodes_stay(rw):
@@ -215,8 +248,8 @@ def test_first_order_transitions_are_uniform(rw, golden):
     assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
 
 
-@pytest.mark.parametrize("p,q", [(0.5, 2.0), (0.25, 4.0), (1.0, 0.5)])
-def test_second_order_statistics_match_analytic_and_oracle(rw, orc, golden, p, q):
+@pytest.mark.parametrize("p,q,fold", [(0.5, 2.0, 1), (0.25, 4.0, 1), (1.0, 0.5, 1), (0.25, 4.0, 0), (0.5, 0.25, 1)])
+def test_second_order_statistics_match_analytic_and_oracle(rw, native, orc, golden, p, q, fold):
     """North-star criterion: chi-square p > 0.01 and pooled TV < 1e-2 at 1e7 samples, against the
     analytic node2vec probabilities and against the reference algorithm's own empirical counts."""
     rp, ci = T(golden["utils/karate/row_ptr"]), T(golden["utils/karate/col_idx"])
@@ -225,7 +258,11 @@ def test_second_order_statistics_match_analytic_and_oracle(rw, orc, golden, p, q
     L = 100
     reps = 3000  # 34 * 3000 walks * 99 second-order transitions = 1.0e7 samples
     nodes = torch.arange(n).repeat_interleave(reps)
-    walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, L, 2024)
+    native.set_option("n2v_fold", fold)
+    try:
+        walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, L, 2024)
+    finally:
+        native.set_option("n2v_fold", 1)
     check_walks_follow_edges(walks, rp, ci, nodes)
     got = second_order_counts(walks, n)
     assert sum(got.values()) >= 10_000_000

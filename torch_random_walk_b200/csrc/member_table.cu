@@ -341,6 +341,34 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_flat_kernel(const Buil
     if (!ok) *a.failed = 1;
 }
 
+// Are all rows strictly increasing (sorted, no edge stored twice)?  Two counts decide it without
+// knowing which row an entry belongs to: descents anywhere in col_idx (col[i] >= col[i+1]) can only
+// sit on row boundaries of such a graph, so the rows are strict iff the number of descents equals
+// the number of descents found AT row boundaries.
+__global__ void __launch_bounds__(256) strict_descents_kernel(const int64_t* __restrict__ col_idx, int64_t nnz,
+                                                              unsigned long long* counts) {
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long n = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < nnz; i += gsz)
+        n += ldg64_stream(col_idx + i) >= __ldg(col_idx + i + 1) ? 1 : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counts, n);
+}
+__global__ void __launch_bounds__(256) strict_boundaries_kernel(const int64_t* __restrict__ row_ptr,
+                                                                const int64_t* __restrict__ col_idx, int64_t n_nodes,
+                                                                int64_t nnz, unsigned long long* counts) {
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long n = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_nodes; r += gsz) {
+        const int64_t b = __ldg(row_ptr + r), e = __ldg(row_ptr + r + 1);
+        if (e > b && e < nnz) n += __ldg(col_idx + e - 1) >= __ldg(col_idx + e) ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counts + 1, n);
+}
+
 // ------------------------------------------------------------------------------------------ host
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -364,7 +392,7 @@ CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform) {
     w.seg_work = off;
     if (w.has_table) off += align256((size_t)w.max_segs * sizeof(SegmentWork));
     w.cells = off;
-    if (w.has_table) off += 256;
+    if (nnz > 0) off += 256;
     w.row32 = off;
     if (w.has_row32) off += align256((size_t)(n_nodes + 1) * 4);
     w.total = off;
@@ -372,12 +400,13 @@ CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform) {
 }
 
 int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
-                       const CsrWorkspace& w, bool want_table, bool want_row32, int build_mode, int device,
-                       cudaStream_t st, CsrPrepared* out) {
+                       const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, int build_mode,
+                       int device, cudaStream_t st, CsrPrepared* out) {
     want_table = want_table && w.has_table;
     want_row32 = want_row32 && w.has_row32;
+    want_strict = want_strict && nnz > 0;
     *out = CsrPrepared{};
-    if (!want_table && !want_row32) return TRW_OK;
+    if (!want_table && !want_row32 && !want_strict) return TRW_OK;
     char* ws = (char*)workspace;
     BuildArgs b{};
     b.row_ptr = row_ptr; b.col_idx = col_idx; b.n_nodes = n_nodes; b.nnz = nnz;
@@ -393,10 +422,22 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
             b.hubs = (HubEntry*)(ws + w.hub_list);
             b.segments = (SegmentWork*)(ws + w.seg_work);
         }
+    }
+    if (want_table || want_strict) {
         rc = check_cuda(cudaMemsetAsync(ws + w.cells, 0, 256, st), "cells memset");
         if (rc) return rc;
     }
     const int sms = sm_count(device);
+    if (want_strict) {
+        unsigned long long* counts = (unsigned long long*)(ws + w.cells + 128);
+        strict_descents_kernel<<<sms * 8, 256, 0, st>>>(col_idx, nnz, counts);
+        strict_boundaries_kernel<<<sms * 8, 256, 0, st>>>(row_ptr, col_idx, n_nodes, nnz, counts);
+        count_launch(2);
+        rc = check_cuda(cudaGetLastError(), "strict-rows check launch");
+        if (rc) return rc;
+        out->strict_counts = counts;
+    }
+    if (!want_table && !want_row32) return TRW_OK;
     csr_prepass_kernel<<<sms * 8, 256, 0, st>>>(b);
     count_launch(1);
     rc = check_cuda(cudaGetLastError(), "csr_prepass launch");

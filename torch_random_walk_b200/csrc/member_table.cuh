@@ -97,12 +97,14 @@ struct CsrPrepared {
     const uint32_t* table = nullptr;     // membership table, or nullptr
     const uint32_t* row32 = nullptr;     // uint32 copy of row_ptr, or nullptr
     const int* table_failed = nullptr;   // device flag: non-zero when a hub segment overflowed
+    const unsigned long long* strict_counts = nullptr;  // [descents in col_idx, descents at row boundaries]
 };
 
 // Enqueues on `st` the per-call preparation of a CSR graph: the uint32 row index and (node2vec)
-// the membership table.  build_mode: 2 = tiled through shared memory (default), 0 = global CAS.
+// the membership table, and (want_strict) the two counters that tell whether every row is strictly
+// increasing, i.e. sorted without duplicate edges.  build_mode: 2 = shared memory (default), 0 = global CAS.
 int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
-                       const CsrWorkspace& w, bool want_table, bool want_row32, int build_mode, int device,
-                       cudaStream_t st, CsrPrepared* out);
+                       const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, int build_mode,
+                       int device, cudaStream_t st, CsrPrepared* out);
 
 }  // namespace trw

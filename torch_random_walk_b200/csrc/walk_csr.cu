@@ -96,7 +96,18 @@ __global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a
 }
 
 // Second-order walk.  One iteration of the loop = one rejection trial of this thread's walk.
-template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32>
+//
+// FOLD (used when the return edge carries the largest weight, 1/p > max(1, 1/q)): plain rejection
+// needs an envelope of 1/p over every neighbour although only the return edge reaches it, which
+// costs max(1,1/q)*p times more trials than necessary (4x at p=0.25).  Following KnightKing
+// (Yang et al., SOSP'19) the excess of the return edge, e = 1/p - M' with M' = max(1, 1/q), is
+// folded out of the envelope: a trial draws a point uniformly from deg(v) bars of height M' plus
+// one extra bar of height e that belongs to t.  The extra bar is accepted iff t is a neighbour of
+// v (one membership probe, needed only when the point lands there: probability e/(deg*M'+e));
+// a point in bar x at height h is accepted iff h < min(w(x), M').  Every neighbour is therefore
+// still drawn with probability proportional to its node2vec weight (t: M' + e = 1/p).  This is
+// only exact when no edge is stored twice, which the prepare step verifies (strict_counts).
+template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32, bool FOLD>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const WalkArgs a) {
     __shared__ int64_t ring[STAGE ? 4 : 1][BLOCK];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -122,10 +133,49 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
     int64_t vb, ve;
     load_row<ROW32>(a, v, vb, ve, pol_keep);
 
-    const uint64_t thr_any = min(a.thr0, min(a.thr1, a.thr2));  // below this every class accepts
-    const uint64_t thr_far = max(a.thr1, a.thr2);               // at or above this only x == t can accept
     int s = 2;
     uint32_t trial = 0;
+    if (FOLD && a.strict_counts[0] == a.strict_counts[1]) {
+        // rows are strictly increasing (no duplicate edges): the folded envelope is exact
+        const uint64_t fthr_any = min(a.fthr1, a.fthr2), fthr_top = max(a.fthr1, a.fthr2);
+        uint32_t thr_extra = 0;  // P(point lands in the extra bar) for the current v, scaled by 2^32
+        bool have_extra = false;
+        while (s <= L) {
+            if (!have_extra) {
+                const double area = (double)(ve - vb) * a.fold_env + a.fold_excess;
+                thr_extra = (uint32_t)fmin(a.fold_excess / area * 4294967296.0, 4294967295.0);
+                have_extra = true;
+            }
+            rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
+            int64_t x;
+            bool accept;
+            if (rnd.z < thr_extra) {
+                x = t;
+                accept = (ve > vb) && is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
+            } else {
+                x = pick_neighbor(a, v, vb, ve, rnd.x, rnd.w, pol_stream);
+                const uint32_t u = rnd.y;
+                if (x == t || u < fthr_any) accept = true;
+                else if (u >= fthr_top) accept = false;
+                else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream) ? a.fthr1 : a.fthr2);
+            }
+            if (accept) {
+                o.put(s, x, s == L);
+                int64_t xb = 0, xe = 0;
+                if (s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
+                t = v; tb = vb; te = ve;
+                v = x; vb = xb; ve = xe;
+                ++s;
+                trial = 0;
+                have_extra = false;
+            } else {
+                ++trial;
+            }
+        }
+        return;
+    }
+    const uint64_t thr_any = min(a.thr0, min(a.thr1, a.thr2));  // below this every class accepts
+    const uint64_t thr_far = max(a.thr1, a.thr2);               // at or above this only x == t can accept
     while (s <= L) {
         uint32_t r, u, r_hi;
         if ((trial & 1u) == 0u) {
@@ -167,32 +217,34 @@ static void launch_uniform(const WalkArgs& a, cudaStream_t st) {
 }
 
 template <int MIN_CTAS, bool STAGE, bool TABLE, bool ROW32>
-static void launch_n2v3(const WalkArgs& a, bool speculate, cudaStream_t st) {
+static void launch_n2v3(const WalkArgs& a, bool speculate, bool fold, cudaStream_t st) {
     constexpr int BLOCK = 256;
     const unsigned grid = (unsigned)((a.n_walks + BLOCK - 1) / BLOCK);
-    if (speculate) node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, true, ROW32><<<grid, BLOCK, 0, st>>>(a);
-    else node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32><<<grid, BLOCK, 0, st>>>(a);
+    if (fold) node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, true><<<grid, BLOCK, 0, st>>>(a);
+    else if (speculate) node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, true, ROW32, false><<<grid, BLOCK, 0, st>>>(a);
+    else node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, false><<<grid, BLOCK, 0, st>>>(a);
 }
 
 template <bool STAGE, bool TABLE, bool ROW32>
-static void launch_n2v2(const WalkArgs& a, bool speculate, int min_ctas, cudaStream_t st) {
-    if (min_ctas >= 6) launch_n2v3<6, STAGE, TABLE, ROW32>(a, speculate, st);
-    else if (min_ctas == 5) launch_n2v3<5, STAGE, TABLE, ROW32>(a, speculate, st);
-    else launch_n2v3<4, STAGE, TABLE, ROW32>(a, speculate, st);
+static void launch_n2v2(const WalkArgs& a, bool speculate, bool fold, int min_ctas, cudaStream_t st) {
+    if (min_ctas >= 6) launch_n2v3<6, STAGE, TABLE, ROW32>(a, speculate, fold, st);
+    else if (min_ctas == 5) launch_n2v3<5, STAGE, TABLE, ROW32>(a, speculate, fold, st);
+    else launch_n2v3<4, STAGE, TABLE, ROW32>(a, speculate, fold, st);
 }
 
-static void launch_n2v(const WalkArgs& a, bool stage, bool table, bool row32, bool speculate, int min_ctas, cudaStream_t st) {
+static void launch_n2v(const WalkArgs& a, bool stage, bool table, bool row32, bool speculate, bool fold, int min_ctas,
+                       cudaStream_t st) {
     if (!stage) {  // plain 8-byte stores: A/B path only, kept to one variant per table mode
-        if (table) launch_n2v3<4, false, true, false>(a, speculate, st);
-        else launch_n2v3<4, false, false, false>(a, speculate, st);
+        if (table) launch_n2v3<4, false, true, false>(a, speculate, fold, st);
+        else launch_n2v3<4, false, false, false>(a, speculate, fold, st);
         return;
     }
     if (table) {
-        if (row32) launch_n2v2<true, true, true>(a, speculate, min_ctas, st);
-        else launch_n2v2<true, true, false>(a, speculate, min_ctas, st);
+        if (row32) launch_n2v2<true, true, true>(a, speculate, fold, min_ctas, st);
+        else launch_n2v2<true, true, false>(a, speculate, fold, min_ctas, st);
     } else {
-        if (row32) launch_n2v2<true, false, true>(a, speculate, min_ctas, st);
-        else launch_n2v2<true, false, false>(a, speculate, min_ctas, st);
+        if (row32) launch_n2v2<true, false, true>(a, speculate, fold, min_ctas, st);
+        else launch_n2v2<true, false, false>(a, speculate, fold, min_ctas, st);
     }
 }
 
@@ -245,6 +297,8 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
     a.walk_length = walk_length; a.key = philox_key(seed, kTagWalkCsr);
     a.out = nullptr; a.out_row_stride = 0; a.table = nullptr; a.table_failed = nullptr; a.row32 = nullptr;
     a.thr0 = a.thr1 = a.thr2 = 0;
+    a.fthr1 = a.fthr2 = 0; a.fold_env = a.fold_excess = 0.0; a.strict_counts = nullptr;
+    plan->fold = false;
     plan->device = device;
     plan->uniform = (p == 1.0 && q == 1.0);  // rw_cuda.cu:226
     plan->table = false;
@@ -258,8 +312,20 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
         a.thr0 = threshold(p0); a.thr1 = threshold(p1); a.thr2 = threshold(p2);
         // Fetch row_ptr[x] before the verdict only when most proposals are accepted anyway.
         plan->speculate = opt.n2v_speculate < 0 ? (fmin(p1, p2) >= 0.5) : (opt.n2v_speculate != 0);
+        // Return-edge folding applies when 1/p is the strict maximum of the three weights.
+        const double env = fmax(1.0, 1.0 / q);
+        if (opt.n2v_fold != 0 && 1.0 / p > env) {
+            plan->fold = true;
+            a.fold_env = env;
+            a.fold_excess = 1.0 / p - env;
+            a.fthr1 = threshold(1.0 / env);
+            a.fthr2 = threshold(1.0 / q / env);
+        }
     }
-    if (workspace == nullptr) return TRW_OK;  // reference-style path: int64 row_ptr, linear-scan membership
+    if (workspace == nullptr) {  // reference-style path: int64 row_ptr, linear-scan membership, plain rejection
+        plan->fold = false;
+        return TRW_OK;
+    }
     const CsrWorkspace w = csr_workspace_layout(n_nodes, nnz, plan->uniform);
     if (w.total == 0) return TRW_OK;
     if (workspace_bytes < w.total || ((uintptr_t)workspace & 255)) {
@@ -270,14 +336,16 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
     const bool want_row32 = opt.row32 != 0;
     CsrPrepared prepared;
     timing_begin(0, st);
-    const int rc = csr_prepare_device(row_ptr, col_idx, n_nodes, nnz, workspace, w, want_table, want_row32,
+    const int rc = csr_prepare_device(row_ptr, col_idx, n_nodes, nnz, workspace, w, want_table, want_row32, plan->fold,
                                       (int)opt.build_mode, device, st, &prepared);
     timing_end(0, st);
     if (rc) return rc;
     a.table = prepared.table;
     a.table_failed = prepared.table_failed;
     a.row32 = prepared.row32;
+    a.strict_counts = prepared.strict_counts;
     plan->table = prepared.table != nullptr;
+    plan->fold = plan->fold && prepared.strict_counts != nullptr;
     return TRW_OK;
 }
 
@@ -299,7 +367,7 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
         else if (row32) launch_uniform<true, true>(a, st);
         else launch_uniform<true, false>(a, st);
     } else {
-        launch_n2v(a, stage, plan.table, row32 && stage, plan.speculate, plan.min_ctas, st);
+        launch_n2v(a, stage, plan.table, row32 && stage, plan.speculate, plan.fold, plan.min_ctas, st);
     }
     timing_end(1, st);
     count_launch(1);

@@ -18,13 +18,17 @@ struct WalkArgs {
     const int* table_failed;  // device flag raised by the build when a hub segment overflowed
     const uint32_t* row32;  // uint32 copy of row_ptr (nullptr: read the int64 row_ptr)
     uint64_t thr0, thr1, thr2;  // acceptance thresholds on a 32-bit uniform, scaled by 2^32
+    // return-edge folding (see node2vec_walk_kernel): envelope M', excess 1/p - M', thresholds 1/M', (1/q)/M'
+    uint64_t fthr1, fthr2;
+    double fold_env, fold_excess;
+    const unsigned long long* strict_counts;  // [descents in col_idx, descents at row boundaries]; equal = rows strictly increasing
 };
 
 struct CsrWalkPlan {
     WalkArgs a;  // graph side filled by csr_walk_prepare; shard side by csr_walk_launch
     int device;
     int min_ctas;
-    bool uniform, table, speculate, stage, persist;
+    bool uniform, table, speculate, stage, persist, fold;
 };
 
 int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "trw_common.cuh"
 #include "trw_options.h"
@@ -17,30 +18,46 @@
 
 namespace trw {
 
-struct HostWalkResources {
-    void* d_row_ptr = nullptr;
-    void* d_col_idx = nullptr;
-    void* d_targets = nullptr;
-    void* d_workspace = nullptr;
-    void* d_out[2] = {nullptr, nullptr};
+// Device buffers, streams and events of the host path are kept between calls (per device,
+// grow-only): cudaMalloc/cudaFree of ~15 GB cost more than the walk itself.  Released by
+// trw_release_cached_buffers() or with option host_cache_buffers = 0.
+enum { kBufRowPtr = 0, kBufColIdx, kBufTargets, kBufWorkspace, kBufOut0, kBufOut1, kNumBufs };
+struct HostWalkCache {
+    void* ptr[kNumBufs] = {};
+    size_t cap[kNumBufs] = {};
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t walked[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
-    ~HostWalkResources() {
+    void release() {
         if (compute) cudaStreamSynchronize(compute);
         if (copy) cudaStreamSynchronize(copy);
+        for (int k = 0; k < kNumBufs; ++k) {
+            if (ptr[k]) cudaFree(ptr[k]);
+            ptr[k] = nullptr;
+            cap[k] = 0;
+        }
         for (int k = 0; k < 2; ++k) {
             if (walked[k]) cudaEventDestroy(walked[k]);
             if (copied[k]) cudaEventDestroy(copied[k]);
-            if (d_out[k]) cudaFree(d_out[k]);
+            walked[k] = copied[k] = nullptr;
         }
-        if (d_workspace) cudaFree(d_workspace);
-        if (d_targets) cudaFree(d_targets);
-        if (d_col_idx) cudaFree(d_col_idx);
-        if (d_row_ptr) cudaFree(d_row_ptr);
         if (compute) cudaStreamDestroy(compute);
         if (copy) cudaStreamDestroy(copy);
+        compute = copy = nullptr;
+        cudaGetLastError();
+    }
+    int reserve(int slot, size_t bytes, const char* what) {
+        if (bytes == 0) bytes = 8;
+        if (cap[slot] >= bytes) return TRW_OK;
+        if (ptr[slot]) cudaFree(ptr[slot]);
+        ptr[slot] = nullptr;
+        cap[slot] = 0;
+        int rc = check_cuda(cudaMalloc(&ptr[slot], bytes), what);
+        if (rc == TRW_OK) cap[slot] = bytes;
+        return rc;
     }
 };
+static HostWalkCache g_host_cache[64];
+static std::mutex g_host_mutex;
 
 #define TRW_TRY(expr, what)                       \
     do {                                          \
@@ -81,25 +98,40 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     };
     const auto t_start = now();
 
-    HostWalkResources r;
-    TRW_TRY(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking), "stream create");
-    TRW_TRY(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking), "stream create");
-    for (int k = 0; k < 2; ++k) {
-        TRW_TRY(cudaEventCreateWithFlags(&r.walked[k], cudaEventDisableTiming), "event create");
-        TRW_TRY(cudaEventCreateWithFlags(&r.copied[k], cudaEventDisableTiming), "event create");
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    HostWalkCache local;  // used (and released on return) when caching is off or the ordinal is unusual
+    const bool cached = options().host_cache_buffers != 0 && d < 64;
+    HostWalkCache& r = cached ? g_host_cache[d] : local;
+    struct Releaser {
+        HostWalkCache* c;
+        ~Releaser() { if (c) c->release(); }
+    } releaser{cached ? nullptr : &local};
+    if (!r.compute) {
+        TRW_TRY(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking), "stream create");
+        TRW_TRY(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking), "stream create");
+        for (int k = 0; k < 2; ++k) {
+            TRW_TRY(cudaEventCreateWithFlags(&r.walked[k], cudaEventDisableTiming), "event create");
+            TRW_TRY(cudaEventCreateWithFlags(&r.copied[k], cudaEventDisableTiming), "event create");
+        }
     }
-    TRW_TRY(cudaMalloc(&r.d_row_ptr, (size_t)(n_nodes + 1) * 8), "cudaMalloc row_ptr");
-    TRW_TRY(cudaMalloc(&r.d_col_idx, std::max<size_t>((size_t)nnz * 8, 8)), "cudaMalloc col_idx");
-    TRW_TRY(cudaMalloc(&r.d_targets, (size_t)n_walks * 8), "cudaMalloc targets");
-    if (ws_bytes) TRW_TRY(cudaMalloc(&r.d_workspace, ws_bytes), "cudaMalloc workspace");
     const int n_buf = n_walks > chunk ? 2 : 1;
-    for (int k = 0; k < n_buf; ++k) TRW_TRY(cudaMalloc(&r.d_out[k], (size_t)chunk * row_len * 8), "cudaMalloc walks");
+    int rc = r.reserve(kBufRowPtr, (size_t)(n_nodes + 1) * 8, "cudaMalloc row_ptr");
+    if (!rc) rc = r.reserve(kBufColIdx, (size_t)nnz * 8, "cudaMalloc col_idx");
+    if (!rc) rc = r.reserve(kBufTargets, (size_t)n_walks * 8, "cudaMalloc targets");
+    if (!rc && ws_bytes) rc = r.reserve(kBufWorkspace, ws_bytes, "cudaMalloc workspace");
+    for (int k = 0; k < n_buf && !rc; ++k) rc = r.reserve(kBufOut0 + k, (size_t)chunk * row_len * 8, "cudaMalloc walks");
+    if (rc) return rc;
+    void* const d_row_ptr = r.ptr[kBufRowPtr];
+    void* const d_col_idx = r.ptr[kBufColIdx];
+    void* const d_targets = r.ptr[kBufTargets];
+    void* const d_workspace = ws_bytes ? r.ptr[kBufWorkspace] : nullptr;
+    void* const d_out[2] = {r.ptr[kBufOut0], r.ptr[kBufOut1]};
 
     const double ms_alloc = ms_since(t_start);
     const auto t_up = now();
-    TRW_TRY(cudaMemcpyAsync(r.d_row_ptr, row_ptr, (size_t)(n_nodes + 1) * 8, cudaMemcpyHostToDevice, r.compute), "H2D row_ptr");
-    if (nnz) TRW_TRY(cudaMemcpyAsync(r.d_col_idx, col_idx, (size_t)nnz * 8, cudaMemcpyHostToDevice, r.compute), "H2D col_idx");
-    TRW_TRY(cudaMemcpyAsync(r.d_targets, targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
+    TRW_TRY(cudaMemcpyAsync(d_row_ptr, row_ptr, (size_t)(n_nodes + 1) * 8, cudaMemcpyHostToDevice, r.compute), "H2D row_ptr");
+    if (nnz) TRW_TRY(cudaMemcpyAsync(d_col_idx, col_idx, (size_t)nnz * 8, cudaMemcpyHostToDevice, r.compute), "H2D col_idx");
+    TRW_TRY(cudaMemcpyAsync(d_targets, targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
 
     double ms_upload = 0.0;
     if (timing) {
@@ -108,8 +140,8 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     }
     const auto t_walk = now();
     CsrWalkPlan plan;
-    int rc = csr_walk_prepare(&plan, (const int64_t*)r.d_row_ptr, (const int64_t*)r.d_col_idx, n_nodes, nnz, p, q,
-                              walk_length, seed, r.d_workspace, ws_bytes, d, r.compute);
+    rc = csr_walk_prepare(&plan, (const int64_t*)d_row_ptr, (const int64_t*)d_col_idx, n_nodes, nnz, p, q,
+                              walk_length, seed, d_workspace, ws_bytes, d, r.compute);
     if (rc) return rc;
 
     int64_t done = 0;
@@ -117,12 +149,12 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         const int b = c & 1;
         const int64_t m = std::min(chunk, n_walks - done);
         if (c >= 2) TRW_TRY(cudaStreamWaitEvent(r.compute, r.copied[b], 0), "wait copied");
-        rc = csr_walk_launch(plan, (const int64_t*)r.d_targets + done, m, walk_id_offset + done, (int64_t*)r.d_out[b],
+        rc = csr_walk_launch(plan, (const int64_t*)d_targets + done, m, walk_id_offset + done, (int64_t*)d_out[b],
                              row_len, r.compute);
         if (rc) return rc;
         TRW_TRY(cudaEventRecord(r.walked[b], r.compute), "record walked");
         TRW_TRY(cudaStreamWaitEvent(r.copy, r.walked[b], 0), "wait walked");
-        TRW_TRY(cudaMemcpyAsync(out + done * row_len, r.d_out[b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy),
+        TRW_TRY(cudaMemcpyAsync(out + done * row_len, d_out[b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy),
                 "D2H walks");
         TRW_TRY(cudaEventRecord(r.copied[b], r.copy), "record copied");
         done += m;
@@ -138,4 +170,20 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
                 ms_since(t_start));
     }
     return TRW_OK;
+}
+
+extern "C" void trw_release_cached_buffers(void) {
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < 64; ++d) {
+        HostWalkCache& c = g_host_cache[d];
+        bool used = c.compute != nullptr;
+        for (int k = 0; k < kNumBufs; ++k) used |= c.ptr[k] != nullptr;
+        if (!used) continue;
+        cudaSetDevice(d);
+        c.release();
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
 }
