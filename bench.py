@@ -38,6 +38,9 @@ WORKLOADS = {
     "c5": dict(desc="Friendster-shaped R-MAT (65.6M nodes, ~1.8B CSR entries), node2vec p=0.25 q=4 L=40 [configs[4]]",
                scale=26, n_nodes=65608366, n_edges=960_000_000, p=0.25, q=4.0, L=40),
     "c3u": dict(desc="R-MAT scale 24, first-order p=q=1 L=80", scale=24, n_nodes=None, edge_factor=16, p=1.0, q=1.0, L=80),
+    "c4": dict(desc="FB15k-237-shaped triples (14,541 entities, 237 relations, 310,116 triples), 10 walks/entity, 40 hops, "
+                    "then to_windows_triples(window_size=5) [BASELINE configs[3]]", kind="triples", n_entities=14541,
+               n_relations=237, n_triples=310116, walks_per_entity=10, L=40, W=5, p=1.0, q=1.0),
     "tiny": dict(desc="R-MAT scale 16 smoke workload, node2vec p=1 q=0.5 L=80", scale=16, n_nodes=None, edge_factor=16,
                  p=1.0, q=0.5, L=80),
 }
@@ -193,6 +196,79 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def run_c4(args, wl):
+    """configs[3]: knowledge-graph triple walks + window generation.  A step = rw.walk_triples over
+    10 walks per entity followed by rw.to_windows_triples on the result; value = hops/s of the whole
+    step, windows/s reported beside it.  Single GPU (the workload is 145k walks)."""
+    from torch_random_walk_b200 import native, rmat, rw
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_ent, pad = wl["n_entities"], wl["n_entities"] + wl["n_relations"]
+    triples = rmat.kg_triples(n_ent, wl["n_relations"], wl["n_triples"], device=dev)
+    index, ts = rmat.relation_tail_index(triples, n_ent)
+    targets = torch.arange(n_ent, device=dev).repeat_interleave(wl["walks_per_entity"])
+    L, W = wl["L"], wl["W"]
+
+    def step(seed):
+        walks = rw.walk_triples(ts, index, targets, walk_length=L, padding_idx=pad, seed=seed)
+        return walks, rw.to_windows_triples(walks, W, n_ent, pad, ts, seed)
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    native.reset_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    walk_ms = win_ms = 0.0
+    with ClockSampler(dev.index) as clocks:
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for k in range(args.steps):
+            ev[0].record()
+            walks = rw.walk_triples(ts, index, targets, walk_length=L, padding_idx=pad, seed=100 + k)
+            ev[1].record()
+            outs = rw.to_windows_triples(walks, W, n_ent, pad, ts, 100 + k)
+            ev[2].record()
+            torch.cuda.synchronize()
+            walk_ms += ev[0].elapsed_time(ev[1]); win_ms += ev[1].elapsed_time(ev[2])
+        t1.record()
+        torch.cuda.synchronize()
+    launches = native.launch_count()
+    total_ms = walk_ms + win_ms
+    hops = targets.numel() * L * args.steps
+    n_win = outs[0].size(0)
+    win_bytes = sum(o.numel() for o in outs) * 8
+    peak, peak_src = measured_peaks()
+    # e2e: CPU tensors in, windows back on the host
+    ts_h, idx_h, tg_h = ts.cpu().pin_memory(), index.cpu().pin_memory(), targets.cpu().pin_memory()
+    torch.cuda.synchronize()
+    t_0 = time.perf_counter()
+    for k in range(args.e2e_steps):
+        w_ = rw.walk_triples(ts_h.to(dev, non_blocking=True), idx_h.to(dev, non_blocking=True), tg_h.to(dev, non_blocking=True),
+                             walk_length=L, padding_idx=pad, seed=k)
+        o_ = rw.to_windows_triples(w_, W, n_ent, pad, ts_h.to(dev, non_blocking=True), k)
+        host = [x.cpu() for x in o_]
+    dt = time.perf_counter() - t_0
+    line = {"metric": "walk_steps_per_sec", "value": hops / (total_ms / 1e3), "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "walks": targets.numel(), "hops_per_walk": L, "window_size": W,
+                       "l2_policy": "window outputs (%.1f GB) exceed the 126 MB L2" % (win_bytes / 1e9)},
+            "clocks": clocks.summary(), "gpu_launches": launches,
+            "e2e": {"value": targets.numel() * L * args.e2e_steps / dt, "unit": "steps/s",
+                    "h2d_bytes_per_step": int((2 * ts_h.numel() + idx_h.numel() + tg_h.numel()) * 8), "d2h_bytes_per_step": int(win_bytes)},
+            "windows_per_sec": n_win * args.steps / (win_ms / 1e3), "walk_hops_per_sec": hops / (walk_ms / 1e3),
+            "roofline": {"bound": "hbm", "kernel": "windows_kernel<triples>", "achieved": win_bytes * args.steps / (win_ms / 1e3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": win_bytes * args.steps / (win_ms / 1e3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_window": 504,
+                         "note": "timed as the whole to_windows_triples call (one kernel launch + three torch.empty)"},
+            "cpu_baseline": None}
+    del host
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -208,8 +284,14 @@ def main():
     ap.add_argument("--option", action="append", default=[], help="library option name=value (experiments)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.impl == "reference" and wl.get("kind") != "triples":
         run_reference_arm(args, wl)
+        return
+    if wl.get("kind") == "triples":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is implemented for the CSR walk workloads (c3, c2, c5)"}))
+            return
+        run_c4(args, wl)
         return
 
     if not torch.cuda.is_available():

@@ -168,3 +168,46 @@ def test_triple_walk_statistics_match_oracle(rw, orc, golden):
         if pad in row[1:]:
             k = list(row[1:]).index(pad) + 1
             assert all(x == pad for x in row[k:])
+
+
+def test_c4_shape_triple_walks_and_windows_full_size(rw, orc):
+    """BASELINE.json configs[3]: FB15k-237-shaped triples (14,541 entities, 237 relations, 310,116
+    triples), 10 walks per entity, 40 hops, then to_windows_triples(window_size=5).  Full size through
+    size-independent properties; a slice of the windows bit-exact against the oracle."""
+    from torch_random_walk_b200 import rmat
+
+    n_ent, n_rel, n_tr = 14541, 237, 310116
+    triples = rmat.kg_triples(n_ent, n_rel, n_tr, seed=7, device="cuda")
+    index, ts = rmat.relation_tail_index(triples, n_ent)
+    pad = n_ent + n_rel
+    targets = torch.arange(n_ent, device="cuda").repeat_interleave(10)
+    L, W = 40, 5
+    walks = rw.walk_triples(ts, index, targets, walk_length=L, padding_idx=pad, seed=10)
+    assert walks.shape == (n_ent * 10, 2 * L + 1)
+    w = walks.cpu()
+    assert torch.equal(w[:, 0], targets.cpu())
+    # every (head, rel, tail) hop is a row of `triples`, or padding after a dead end, and padding absorbs
+    key = lambda h, r, t: (h * (pad + 1) + r) * (pad + 1) + t  # noqa: E731
+    valid = torch.unique(key(ts[:, 0], ts[:, 1], ts[:, 2])).cpu()
+    heads, rels, tails = w[:, 0:-2:2], w[:, 1::2], w[:, 2::2]
+    hop_key = key(heads, rels, tails).reshape(-1)
+    is_pad = ((rels == pad) & (tails == pad)).reshape(-1)
+    has_out = (index[:, 0] >= 0).cpu()
+    head_flat = heads.reshape(-1)
+    head_dead = (head_flat == pad) | ~has_out[head_flat.clamp(max=n_ent - 1)]
+    assert bool((torch.isin(hop_key, valid) | is_pad).all())
+    assert bool((is_pad == head_dead).all())  # padding exactly where the reference pads (rw_cuda_triples.cu:23-43)
+    # windows at full size: shapes, targets are the walk's own triples, negatives are rows of `triples`
+    tt, tp, tn = rw.to_windows_triples(walks, W, n_ent, pad, ts, 3)
+    K = n_ent * 10 * L
+    assert tt.shape == (K, 3) and tp.shape == (K, 2 * W, 3) and tn.shape == (K, 2 * W, 3)
+    assert torch.equal(tt.view(n_ent * 10, L, 3)[:, :, 0], walks[:, 0:-2:2])
+    assert torch.equal(tt.view(n_ent * 10, L, 3)[:, :, 2], walks[:, 2::2])
+    assert bool(torch.isin(key(tn[..., 0], tn[..., 1], tn[..., 2]).reshape(-1), valid.cuda()).all())
+    # right-hand windows of hop j are the targets of hops j+1.. (size-independent shift property)
+    right = tp.view(n_ent * 10, L, 2 * W, 3)[:, :-1, W, :]
+    assert torch.equal(right, tt.view(n_ent * 10, L, 3)[:, 1:, :])
+    # a slice bit-exact against the oracle (positives and targets are RNG-free)
+    sl = walks[:2000].cpu()
+    o_t, o_p, _ = orc.to_windows_triples(sl, W, n_ent, pad, ts.cpu(), 3)
+    assert torch.equal(tt[: 2000 * L].cpu(), o_t) and torch.equal(tp[: 2000 * L].cpu(), o_p)

@@ -24,7 +24,9 @@ constexpr int kHubDeg = kBuildTile;                          // rows at least th
 constexpr int kBuildRange = kBuildTile + kHubDeg;            // entries a tile's CTA may touch
 constexpr int kRangePerThread = kBuildRange / kBuildThreads;
 constexpr uint32_t kNotOurs = 0xFFFFFFFFu;
-constexpr size_t kTiledSmemBytes = (size_t)kBuildRange * 4 + (size_t)kBuildRange * 2 * 4 + (size_t)kBuildRange;  // codes + bucket image + counters
+constexpr int kHeadWords = kBuildRange + kBuildRange / 32;  // row codes, skewed by one word per 32 (bank-conflict-free both ways)
+constexpr size_t kTiledSmemBytes = (size_t)kHeadWords * 4 + (size_t)kBuildRange * 2 * 4 + (size_t)kBuildRange;  // codes + bucket image + counters
+__device__ __forceinline__ int head_at(int i) { return i + (i >> 5); }
 constexpr size_t kHubSmemBytes = (size_t)(2 * kSegBuckets) * 32 + (size_t)(2 * kSegBuckets) * 4;                  // one segment image + counters
 
 struct HubEntry {
@@ -123,8 +125,8 @@ __device__ __forceinline__ bool smem_insert(uint32_t* __restrict__ image, uint32
 // entries.  The row of every entry is recovered with a max-scan over "a row starts here" codes.
 __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const BuildArgs a) {
     extern __shared__ __align__(16) uint32_t tiled_smem[];
-    uint32_t* head = tiled_smem;                // [kBuildRange] row code of each entry of the window
-    uint32_t* image = tiled_smem + kBuildRange; // [kBuildRange / 4 buckets][8 slots]
+    uint32_t* head = tiled_smem;                // [kHeadWords] row code of each entry of the window (index through head_at)
+    uint32_t* image = tiled_smem + kHeadWords;  // [kBuildRange / 4 buckets][8 slots]; kHeadWords is a multiple of 4
     uint32_t* count = image + 2 * kBuildRange;  // [kBuildRange / 4] arrivals per bucket
     __shared__ uint32_t warp_max[kBuildThreads / 32];
     __shared__ unsigned long long s_lo, s_hi;   // entry span [s_lo, s_hi) of the rows built here
@@ -136,12 +138,11 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
     const int64_t r0 = a.tile_row0[tile];
     const int64_t r1 = min(a.tile_row0[tile + 1], a.n_nodes - 1);
     const int64_t bucket0 = e0 >> 2;  // first bucket of the window (tiles are multiples of four entries)
+    for (int i = tid; i < kHeadWords / 4; i += kBuildThreads) reinterpret_cast<uint4*>(head)[i] = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int k = 0; k < kRangePerThread; ++k) head[k * kBuildThreads + tid] = 0;
-#pragma unroll
-    for (int k = 0; k < 2 * kRangePerThread; ++k) image[k * kBuildThreads + tid] = kEmpty;
-#pragma unroll
-    for (int k = 0; k < kRangePerThread / 4; ++k) count[k * kBuildThreads + tid] = 0;
+    for (int k = 0; k < kRangePerThread / 2; ++k)
+        reinterpret_cast<uint4*>(image)[k * kBuildThreads + tid] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+    if (tid < kBuildRange / 16) reinterpret_cast<uint4*>(count)[tid] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { s_lo = ~0ull; s_hi = 0; }
     __syncthreads();
     // Rows that start in [e0, e1): short ones get the code r - r0 + 1; a hub gets kNotOurs (nothing
@@ -150,9 +151,9 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
         const int64_t b = __ldg(a.row_ptr + r), e = __ldg(a.row_ptr + r + 1);
         if (e > b && b >= e0 && b < e1) {
             if (e - b >= kHubDeg) {
-                head[b - e0] = kNotOurs;
+                head[head_at((int)(b - e0))] = kNotOurs;
             } else {
-                head[b - e0] = (uint32_t)(r - r0 + 1);
+                head[head_at((int)(b - e0))] = (uint32_t)(r - r0 + 1);
                 atomicMin(&s_lo, (unsigned long long)b);
                 atomicMax(&s_hi, (unsigned long long)e);
             }
@@ -162,14 +163,14 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
     const int64_t own_end = (int64_t)s_hi;  // 0 when no short row starts here
     if (own_end == 0) return;
     // Entries past the last owned row belong to rows of later tiles.
-    if (tid == 0 && own_end - e0 < kBuildRange) head[own_end - e0] = kNotOurs;
+    if (tid == 0 && own_end - e0 < kBuildRange) head[head_at((int)(own_end - e0))] = kNotOurs;
     __syncthreads();
     {   // inclusive max-scan of the codes; each thread scans kRangePerThread consecutive entries
         uint32_t own[kRangePerThread];
         uint32_t run = 0;
 #pragma unroll
         for (int k = 0; k < kRangePerThread; ++k) {
-            run = max(run, head[tid * kRangePerThread + k]);
+            run = max(run, head[head_at(tid * kRangePerThread + k)]);
             own[k] = run;
         }
         uint32_t incl = run;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
         if ((tid & 31) == 0) before = 0;
         for (int w = 0; w < (tid >> 5); ++w) before = max(before, warp_max[w]);
 #pragma unroll
-        for (int k = 0; k < kRangePerThread; ++k) head[tid * kRangePerThread + k] = max(before, own[k]);
+        for (int k = 0; k < kRangePerThread; ++k) head[head_at(tid * kRangePerThread + k)] = max(before, own[k]);
     }
     __syncthreads();
     // Fetch all of this thread's entries before the first insert (strided: coalesced), so the
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
 #pragma unroll
     for (int k = 0; k < kRangePerThread; ++k) {
         const int idx = k * kBuildThreads + tid;
-        const uint32_t code = head[idx];
+        const uint32_t code = head[head_at(idx)];
         const bool ours = code != 0 && code != kNotOurs && e0 + idx < own_end;
         xs[k] = ours ? (uint32_t)ldg64_stream(a.col_idx + e0 + idx) : kEmpty;
     }
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
 #pragma unroll
     for (int k = 0; k < kRangePerThread; ++k) {
         if (xs[k] == kEmpty) continue;  // not ours (ids never equal the EMPTY marker in table mode)
-        const int64_t r = r0 + head[k * kBuildThreads + tid] - 1;
+        const int64_t r = r0 + head[head_at(k * kBuildThreads + tid)] - 1;
         if (r != cur_row) {
             cur_row = r;
             const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(kBuildThreads, 3) build_hub_kernel(const Build
         const int64_t lo = work.segment << kSegShift;
         const int64_t hi = (work.segment == nseg - 1) ? nb : lo + kSegBuckets;
         const int64_t size = hi - lo;
-        for (int64_t i = tid; i < size * 8; i += kBuildThreads) hub_image[i] = kEmpty;
+        for (int64_t i = tid; i < size * 2; i += kBuildThreads)
+            reinterpret_cast<uint4*>(hub_image)[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
         for (int64_t i = tid; i < size; i += kBuildThreads) hub_count[i] = 0;
         __syncthreads();
         bool ok = true;

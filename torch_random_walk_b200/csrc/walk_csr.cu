@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
             rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
             int64_t x;
             bool accept;
-            if (rnd.z < thr_extra) {
+            if (ve <= vb) {  // no out-edge: the walk stays on v (rw_cuda.cu:25-30), nothing to sample
+                x = v;
+                accept = true;
+            } else if (rnd.z < thr_extra) {
                 x = t;
-                accept = (ve > vb) && is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
+                accept = is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
             } else {
                 x = pick_neighbor(a, v, vb, ve, rnd.x, rnd.w, pol_stream);
                 const uint32_t u = rnd.y;
