@@ -28,6 +28,7 @@ constexpr int kHeadWords = kBuildRange + kBuildRange / 32;  // row codes, skewed
 constexpr size_t kTiledSmemBytes = (size_t)kHeadWords * 4 + (size_t)kBuildRange * 2 * 4 + (size_t)kBuildRange;  // codes + bucket image + counters
 __device__ __forceinline__ int head_at(int i) { return i + (i >> 5); }
 constexpr size_t kHubSmemBytes = (size_t)(2 * kSegBuckets) * 32 + (size_t)(2 * kSegBuckets) * 4;                  // one segment image + counters
+constexpr int kHubThreads = 1024;
 
 struct HubEntry {
     int64_t row;
@@ -48,6 +49,7 @@ struct BuildArgs {
     HubEntry* hubs;                  // [max_hubs]
     SegmentWork* segments;           // [max_segs]
     unsigned long long* hub_counter; // (number of hubs << 32) | number of hub segments
+    unsigned long long* next_segment; // work counter of build_hub_kernel
     int* failed;                     // set when a segment had no room (see member_table.cuh)
     uint32_t* row32;                 // optional uint32 copy of row_ptr
     int64_t n_tiles, n_buckets, max_hubs, max_segs;
@@ -222,14 +224,20 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
     for (int64_t i = tid; i < n16; i += kBuildThreads) dst[i] = src[i];
 }
 
-// Hub rows: persistent CTAs, one segment at a time.
-__global__ void __launch_bounds__(kBuildThreads, 3) build_hub_kernel(const BuildArgs a) {
+// Hub rows: persistent CTAs (one per SM: the segment image takes 144 KB of shared memory), which
+// pull segments from a shared counter so that the few very long rows do not unbalance the grid.
+__global__ void __launch_bounds__(kHubThreads, 1) build_hub_kernel(const BuildArgs a) {
     extern __shared__ __align__(16) uint32_t hub_image[];  // up to 2*kSegBuckets-1 buckets
     uint32_t* hub_count = hub_image + 2 * kSegBuckets * 8;
+    __shared__ unsigned long long s_next;
     const int tid = threadIdx.x;
     const int64_t n_segments = (int64_t)(*a.hub_counter & 0xFFFFFFFFull);
     if (n_segments > a.max_segs) return;  // flagged by hub_segments_kernel
-    for (int64_t c = blockIdx.x; c < n_segments; c += gridDim.x) {
+    for (;;) {
+        if (tid == 0) s_next = atomicAdd(a.next_segment, 1ull);
+        __syncthreads();
+        const int64_t c = (int64_t)s_next;
+        if (c >= n_segments) break;
         const SegmentWork work = a.segments[c];
         const int64_t b = __ldg(a.row_ptr + work.row), e = __ldg(a.row_ptr + work.row + 1);
         int64_t first, nb;
@@ -238,17 +246,17 @@ __global__ void __launch_bounds__(kBuildThreads, 3) build_hub_kernel(const Build
         const int64_t lo = work.segment << kSegShift;
         const int64_t hi = (work.segment == nseg - 1) ? nb : lo + kSegBuckets;
         const int64_t size = hi - lo;
-        for (int64_t i = tid; i < size * 2; i += kBuildThreads)
+        for (int64_t i = tid; i < size * 2; i += kHubThreads)
             reinterpret_cast<uint4*>(hub_image)[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-        for (int64_t i = tid; i < size; i += kBuildThreads) hub_count[i] = 0;
+        for (int64_t i = tid; i < size; i += kHubThreads) hub_count[i] = 0;
         __syncthreads();
         bool ok = true;
         // eight independent loads in flight per thread; the row comes from L2 after its first reader
-        for (int64_t i = b + tid; i < e; i += 8 * kBuildThreads) {
+        for (int64_t i = b + tid; i < e; i += 8 * kHubThreads) {
             uint32_t x[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int64_t idx = i + (int64_t)u * kBuildThreads;
+                const int64_t idx = i + (int64_t)u * kHubThreads;
                 x[u] = idx < e ? (uint32_t)__ldg(a.col_idx + idx) : kEmpty;
             }
 #pragma unroll
@@ -262,8 +270,8 @@ __global__ void __launch_bounds__(kBuildThreads, 3) build_hub_kernel(const Build
         __syncthreads();
         const uint4* src = reinterpret_cast<const uint4*>(hub_image);
         uint4* dst = reinterpret_cast<uint4*>(a.table + (first + lo) * 8);
-        for (int64_t i = tid; i < size * 2; i += kBuildThreads) dst[i] = src[i];
-        __syncthreads();  // the image is reused by the next segment
+        for (int64_t i = tid; i < size * 2; i += kHubThreads) dst[i] = src[i];
+        __syncthreads();  // the image (and s_next) are reused by the next segment
     }
 }
 
@@ -383,7 +391,7 @@ CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform) {
     w.n_tiles = (nnz + kBuildTile - 1) / kBuildTile;
     w.n_buckets = (nnz + 3) / 4;
     w.max_hubs = nnz / kHubDeg + 1;
-    w.max_segs = w.n_buckets / 500 + w.max_hubs + 1;  // every segment of a hub has >= 510 buckets
+    w.max_segs = w.n_buckets / kSegBuckets + w.max_hubs + 1;  // a hub has one segment, or segments of >= kSegBuckets buckets
     size_t off = 0;
     w.table = off;
     if (w.has_table) off += align256((size_t)w.n_buckets * 32);
@@ -420,6 +428,7 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
         b.tile_row0 = (int64_t*)(ws + w.tile_row0);
         b.hub_counter = (unsigned long long*)(ws + w.cells);
         b.failed = (int*)(ws + w.cells + 64);
+        b.next_segment = (unsigned long long*)(ws + w.cells + 32);
         if (build_mode != 0) {
             b.hubs = (HubEntry*)(ws + w.hub_list);
             b.segments = (SegmentWork*)(ws + w.seg_work);
@@ -463,7 +472,7 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
             }
             hub_segments_kernel<<<sms, 256, 0, st>>>(b);
             build_tiled_kernel<<<(unsigned)w.n_tiles, kBuildThreads, kTiledSmemBytes, st>>>(b);
-            build_hub_kernel<<<sms * 3, kBuildThreads, kHubSmemBytes, st>>>(b);
+            build_hub_kernel<<<sms, kHubThreads, kHubSmemBytes, st>>>(b);
             count_launch(3);
         }
         rc = check_cuda(cudaGetLastError(), "membership table build launch");

@@ -25,7 +25,7 @@ namespace trw {
 
 constexpr int64_t kMinTableDeg = 12;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-constexpr int kSegShift = 10;
+constexpr int kSegShift = 11;
 constexpr int64_t kSegBuckets = 1ll << kSegShift;
 
 __host__ __device__ __forceinline__ void table_span(int64_t b, int64_t e, int64_t& first, int64_t& nb) {
