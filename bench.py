@@ -51,6 +51,16 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line.  Libraries (NCCL's version banner, for one) also write to
+# file descriptor 1, so it is pointed at stderr for the whole run and the line goes to the saved one.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -60,7 +70,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi SM clock / throttle-reason samples while the timed region runs."""
+    """SM clock / throttle-reason samples while the timed region runs: one `nvidia-smi -lms 50`
+    process started before the region and stopped after it (the recipe of B200_PROFILING.md)."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -68,35 +79,39 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
-        self._stop = threading.Event()
-        self._thread = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.proc = None
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # let the first sample land before the region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        self._thread.join(timeout=10)
+        if self.proc is None:
+            return
+        try:
+            time.sleep(0.06)
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=10)
+            self.rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, power, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                power.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -105,7 +120,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
 
 
 def build_graph(wl, device):
@@ -193,7 +209,7 @@ def run_reference_arm(args, wl):
                                    f"steps/s by thread count: { {k: round(v) for k, v in results.items()} }"},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_c4(args, wl):
@@ -266,14 +282,14 @@ def run_c4(args, wl):
                          "note": "timed as the whole to_windows_triples call (one kernel launch + three torch.empty)"},
             "cpu_baseline": None}
     del host
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("TRW_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -289,7 +305,7 @@ def main():
         return
     if wl.get("kind") == "triples":
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is implemented for the CSR walk workloads (c3, c2, c5)"}))
+            emit({"impl": "reference", "unavailable": "the reference arm is implemented for the CSR walk workloads (c3, c2, c5)"})
             return
         run_c4(args, wl)
         return
@@ -494,7 +510,7 @@ def main():
                        "options": overrides},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "output_valid": valid, "roofline": roofline, "cpu_baseline": cpu_baseline, "other_workloads": others,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
