@@ -211,3 +211,24 @@ def test_c4_shape_triple_walks_and_windows_full_size(rw, orc):
     sl = walks[:2000].cpu()
     o_t, o_p, _ = orc.to_windows_triples(sl, W, n_ent, pad, ts.cpu(), 3)
     assert torch.equal(tt[: 2000 * L].cpu(), o_t) and torch.equal(tp[: 2000 * L].cpu(), o_p)
+
+
+def test_device_side_index_builders_feed_the_walks(rw, golden):
+    """utils.build_node_edge_index / build_relation_tail_index / csr_from_edge_index on CUDA tensors
+    (SURVEY.md section 8f rank 2): same index as the host path, and the walks accept the result."""
+    el = T(golden["utils/rand_el3/edge_list"])
+    n = int(golden["utils/rand_el3/num_nodes"])
+    idx_gpu, rows_gpu = utils.build_node_edge_index(el.cuda(), torch.arange(n))
+    assert idx_gpu.is_cuda and np.array_equal(idx_gpu.cpu().numpy(), golden["utils/rand_el3/node_edge_index"])
+    walks = rw.walk_edge_list(rows_gpu, idx_gpu, torch.arange(n, device="cuda"), 1.0, 1.0, 8, 3, n)
+    _check_edge_list_walks(walks, rows_gpu.cpu(), idx_gpu.cpu(), torch.arange(n), n, True)
+    tr = T(golden["utils/rand_tr3/triples"])
+    rti_gpu, trs_gpu = utils.build_relation_tail_index(tr.cuda(), torch.arange(n))
+    assert np.array_equal(rti_gpu.cpu().numpy(), golden["utils/rand_tr3/relation_tail_index"])
+    w = rw.walk_triples(trs_gpu, rti_gpu, torch.arange(n, device="cuda"), 4, n + 7, 1)
+    assert w.shape == (n, 9)
+    rp, ci = utils.csr_from_edge_index(el.cuda(), n, symmetric=True)
+    w = rw.walk(rp, ci, torch.arange(n, device="cuda"), 0.5, 2.0, 10, 1)
+    from helpers import check_walks_follow_edges
+
+    check_walks_follow_edges(w, rp, ci, torch.arange(n))

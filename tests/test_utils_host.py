@@ -86,3 +86,55 @@ def test_relation_tail_index_known_answer(golden):
 def test_empty_edge_list_raises_like_reference():
     with pytest.raises(IndexError):
         utils.build_node_edge_index(torch.zeros((0, 2), dtype=torch.int64), torch.arange(3))
+
+
+# ---- vectorised / device-side graph preparation --------------------
+
+def _same_rows_per_head(a, b):
+    """Two row lists sorted by head hold the same rows per head (order inside a head may differ)."""
+    key = lambda t: sorted(map(tuple, t.tolist()))  # noqa: E731
+    return a.shape == b.shape and torch.equal(a[:, 0], b[:, 0]) and key(a) == key(b)
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_torch_index_builders_match_reference(golden, case):
+    from torch_random_walk_b200.utils import _sorted_rows_and_ranges_torch
+
+    n = int(golden[f"utils/rand_el{case}/num_nodes"])
+    index, rows = _sorted_rows_and_ranges_torch(T(golden[f"utils/rand_el{case}/edge_list"]), n)
+    assert np.array_equal(index.numpy(), golden[f"utils/rand_el{case}/node_edge_index"])
+    assert _same_rows_per_head(rows, T(golden[f"utils/rand_el{case}/edge_list_sorted"]))
+    index, rows = _sorted_rows_and_ranges_torch(T(golden[f"utils/rand_tr{case}/triples"]), n)
+    assert np.array_equal(index.numpy(), golden[f"utils/rand_tr{case}/relation_tail_index"])
+    assert _same_rows_per_head(rows, T(golden[f"utils/rand_tr{case}/triples_sorted"]))
+
+
+def test_torch_index_builder_known_answers(golden):
+    from torch_random_walk_b200.utils import _sorted_rows_and_ranges_torch
+
+    # /root/reference/tests/test_rw_edge_list.py:31-35, tests/test_rw_triples.py:47-51
+    el, _ = utils.to_edge_list_indexed(toy_graph(True))
+    index, _ = _sorted_rows_and_ranges_torch(el, 5)
+    assert index.tolist() == [[0, 1], [2, 3], [-1, -1], [4, 4], [5, 6]]
+    index, rows = _sorted_rows_and_ranges_torch(T(golden["utils/toy_triples/triples"]), 5)
+    assert index.tolist() == [[0, 2], [3, 3], [4, 5], [6, 7], [-1, -1]]
+    assert rows.dtype == torch.int64
+    with pytest.raises(IndexError):
+        _sorted_rows_and_ranges_torch(torch.zeros((0, 2), dtype=torch.int64), 3)
+
+
+@pytest.mark.parametrize("name,graph,symmetric", [("toy_undirected", toy_graph(False), True), ("toy_directed", toy_graph(True), False),
+                                                   ("karate", nx.karate_club_graph(), True)])
+def test_csr_from_edge_index_equals_to_csr(golden, name, graph, symmetric):
+    nodes = list(graph.nodes())
+    pos = {v: i for i, v in enumerate(nodes)}
+    edges = torch.tensor([[pos[a], pos[b]] for a, b in graph.edges()], dtype=torch.int64)
+    for layout in (edges, edges.t().contiguous()):
+        row_ptr, col_idx = utils.csr_from_edge_index(layout, len(nodes), symmetric=symmetric)
+        assert np.array_equal(row_ptr.numpy(), golden[f"utils/{name}/row_ptr"])
+        assert np.array_equal(col_idx.numpy(), golden[f"utils/{name}/col_idx"])
+    dup = torch.cat((edges, edges[:3]))  # duplicate edges are merged, as scipy's canonical CSR does
+    row_ptr, col_idx = utils.csr_from_edge_index(dup, len(nodes), symmetric=symmetric)
+    assert np.array_equal(col_idx.numpy(), golden[f"utils/{name}/col_idx"])
+    with pytest.raises(IndexError):
+        utils.csr_from_edge_index(torch.tensor([[0, len(nodes)]]), len(nodes))

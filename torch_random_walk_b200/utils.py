@@ -93,9 +93,35 @@ def _head_ranges(heads: np.ndarray, num_nodes: int) -> torch.Tensor:
     return torch.from_numpy(index).contiguous()
 
 
+def _sorted_rows_and_ranges_torch(rows: torch.Tensor, num_nodes: int):
+    """Device-side (or large-input) twin of _sort_rows_by_head + _head_ranges: one stable sort by
+    head, then segment boundaries with bincount/cumsum -- no Python loop, runs where `rows` lives.
+    Rows that share a head keep their input order (the reference's pandas sort leaves that order
+    unspecified), everything else is identical, including the single-row corner ([0,-1])."""
+    rows = rows.to(torch.int64)
+    if rows.size(0) == 0:
+        raise IndexError("index 0 is out of bounds for dimension 0 with size 0")
+    heads = rows[:, 0]
+    if int(heads.min()) < 0 or int(heads.max()) >= num_nodes:
+        raise IndexError(f"head id out of range for an index with {num_nodes} rows")
+    order = torch.sort(heads, stable=True).indices
+    rows = rows[order].contiguous()
+    counts = torch.bincount(rows[:, 0], minlength=num_nodes)
+    ends = torch.cumsum(counts, 0)
+    index = torch.stack((ends - counts, ends - 1), 1)
+    index[counts == 0] = -1
+    if rows.size(0) == 1:
+        index[rows[0, 0], 1] = -1
+    return index.contiguous(), rows
+
+
 def build_node_edge_index(edge_list_indexed, nodes_tensor):
     """(edge_list_indexed[E,2], node ids) -> (node_edge_index[N,2], edge list sorted by head).
-    Reference: torch_rw/utils.py:58-89.  N = number of distinct ids in nodes_tensor."""
+    Reference: torch_rw/utils.py:58-89.  N = number of distinct ids in nodes_tensor.
+    CUDA inputs are processed on the device (stable sort) and CUDA tensors are returned."""
+    if torch.is_tensor(edge_list_indexed) and edge_list_indexed.is_cuda:
+        num_nodes = int(torch.unique(torch.as_tensor(nodes_tensor)).numel())
+        return _sorted_rows_and_ranges_torch(edge_list_indexed.reshape(-1, 2), num_nodes)
     rows = np.ascontiguousarray(torch.as_tensor(edge_list_indexed).cpu().numpy()).astype(np.int64, copy=False)
     rows = _sort_rows_by_head(rows.reshape(-1, 2))
     num_nodes = int(torch.unique(torch.as_tensor(nodes_tensor)).numel())
@@ -106,9 +132,34 @@ def build_node_edge_index(edge_list_indexed, nodes_tensor):
 def build_relation_tail_index(triples_indexed_tensor, all_entities_tensor):
     """(triples[T,3], entity ids) -> (relation_tail_index[N,2], triples sorted by head).
     Reference: torch_rw/utils.py:91-120.  N = len(all_entities_tensor) (not de-duplicated, as in
-    the reference); float inputs are truncated to int64 after sorting, like `.to(int)` there."""
+    the reference); float inputs are truncated to int64 after sorting, like `.to(int)` there.
+    CUDA inputs are processed on the device (stable sort) and CUDA tensors are returned."""
+    if torch.is_tensor(triples_indexed_tensor) and triples_indexed_tensor.is_cuda:
+        return _sorted_rows_and_ranges_torch(triples_indexed_tensor.reshape(-1, 3), int(torch.as_tensor(all_entities_tensor).numel()))
     raw = np.ascontiguousarray(torch.as_tensor(triples_indexed_tensor).cpu().numpy()).reshape(-1, 3)
     rows = _sort_rows_by_head(raw).astype(np.int64)
     num_nodes = int(torch.as_tensor(all_entities_tensor).numel())
     relation_tail_index = _head_ranges(rows[:, 0], num_nodes)
     return relation_tail_index, torch.from_numpy(np.ascontiguousarray(rows)).contiguous()
+
+
+def csr_from_edge_index(edge_index, num_nodes, symmetric=False):
+    """Tensor edge list -> (row_ptr[n+1], col_idx[nnz]) with the properties of `to_csr` output:
+    rows sorted, duplicate edges merged, int64, contiguous, on the device of `edge_index`
+    ([2,E] or [E,2]).  `symmetric=True` adds the reversed edges (an undirected graph, as
+    `to_csr(nx.Graph)` yields).  Vectorised: one sort (torch.unique) and a bincount."""
+    e = torch.as_tensor(edge_index).to(torch.int64)
+    if e.dim() != 2 or (e.size(0) != 2 and e.size(1) != 2):
+        raise ValueError("edge_index must be [2,E] or [E,2]")
+    src, dst = (e[0], e[1]) if e.size(0) == 2 and e.size(1) != 2 else (e[:, 0], e[:, 1])
+    if src.numel() and (int(torch.min(torch.minimum(src, dst))) < 0 or int(torch.max(torch.maximum(src, dst))) >= num_nodes):
+        raise IndexError(f"node id out of range for a graph with {num_nodes} nodes")
+    key = src * num_nodes + dst
+    if symmetric:
+        key = torch.cat((key, dst * num_nodes + src))
+    key = torch.unique(key)
+    rows = torch.div(key, num_nodes, rounding_mode="floor")
+    col_idx = (key - rows * num_nodes).contiguous()
+    row_ptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=col_idx.device)
+    torch.cumsum(torch.bincount(rows, minlength=num_nodes), 0, out=row_ptr[1:])
+    return row_ptr.contiguous(), col_idx
