@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-Xcompiler", "-fPIC,-O3,-Wall",
     "--use_fast_math",
+    "-Xlinker", "-soname=libtrw_b200.so",
     "-shared",
 ]
 

@@ -84,6 +84,11 @@ __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_
         }
         (void)neg_out;
         if (MODE == kSkipGram) {  // neg_windows: uniform node id (windows_cuda.cu:57-62)
+            if ((uint64_t)a.num_nodes <= 0xFFFFFFFFull) {  // four draws per Philox block, shared by the aligned quad
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(g >> 2), (uint32_t)(g >> 34), 1u, 0x51554144u), a.key);
+                const uint32_t w = (g & 2) ? ((g & 1) ? r.w : r.z) : ((g & 1) ? r.y : r.x);
+                return (int64_t)__umulhi(w, (uint32_t)a.num_nodes);
+            }
             uint2 r = draw64(a.key, g, 1u, 0u);
             return bounded(r.x, r.y, a.num_nodes);
         }
@@ -134,6 +139,110 @@ __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_
     return __ldg(a.triples + idx * 3 + c);
 }
 
+// ------------------------------------------------------------------------------------------
+// Triple modes: 24-byte rows make the per-element index arithmetic (three divisions) and the
+// per-element Philox call the bound, not HBM.  So (a) every thread walks its elements with an
+// odometer -- (component, window row, target, walk) advanced by constant strides with single
+// carries, no division in the loop -- and (b) the negative rows of a chunk are drawn first, four
+// per Philox block, into shared memory, then streamed out.  Stores stay coalesced and 8 bytes wide
+// per lane (a warp writes 256 contiguous bytes per instruction).
+// ------------------------------------------------------------------------------------------
+struct Odometer {  // element e = ((i * K + ti) * R + h) * 3 + c, advanced by a fixed stride
+    uint32_t c, h, ti, i;
+    uint32_t dc, dh, dti, di, R, K;
+    __device__ __forceinline__ void init(uint32_t e, uint32_t stride, uint32_t R_, uint32_t K_) {
+        R = R_; K = K_;
+        c = e % 3u; uint32_t row = e / 3u;
+        h = row % R; uint32_t k = row / R;
+        ti = k % K; i = k / K;
+        dc = stride % 3u; uint32_t drow = stride / 3u;
+        dh = drow % R; uint32_t dk = drow / R;
+        dti = dk % K; di = dk / K;
+    }
+    __device__ __forceinline__ void advance() {
+        c += dc; uint32_t carry = c >= 3u; c -= 3u * carry;
+        h += dh + carry; carry = h >= R; h -= R * carry;
+        ti += dti + carry; carry = ti >= K; ti -= K * carry;
+        i += di + carry;
+    }
+};
+
+constexpr int kNegChunkRows = 4096;  // negative rows drawn per round (16 KiB of row indices)
+
+template <int MODE, int BLOCK>
+__device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* tile, int64_t i0, int tw) {
+    __shared__ uint32_t neg_rows[MODE == kTriples ? kNegChunkRows : 1];
+    const uint32_t K = (uint32_t)a.per_walk, R = (uint32_t)(2 * a.W);
+    const int pos_out = (MODE == kTriples) ? 1 : 2, neg_out = (MODE == kTriples) ? 2 : 1;
+    const int tid = threadIdx.x;
+    // targets / pos_triples: element = (i*K + ti)*3 + c  ->  walk[i][2*ti + c]
+    {
+        int64_t* dst = a.out[0] + (uint64_t)i0 * K * 3u;
+        const uint32_t n = (uint32_t)tw * K * 3u;
+        Odometer o;
+        o.init((uint32_t)tid, BLOCK, 1u, K);
+        for (uint32_t e = tid; e < n; e += BLOCK, o.advance()) dst[e] = tile[(size_t)o.i * a.wl + 2u * o.ti + o.c];
+    }
+    // positive windows: element = ((i*K + ti)*2W + h)*3 + c
+    if (R > 0) {
+        int64_t* dst = a.out[pos_out] + (uint64_t)i0 * K * R * 3u;
+        const uint32_t n = (uint32_t)tw * K * R * 3u;
+        Odometer o;
+        o.init((uint32_t)tid, BLOCK, R, K);
+        for (uint32_t e = tid; e < n; e += BLOCK, o.advance())
+            dst[e] = triple_window_value(tile + (size_t)o.i * a.wl, a.wl, a.W, a.pad, (int)o.ti, (int)o.h, (int)o.c);
+    }
+    if (MODE == kTriples) {
+        // neg_windows: every row a uniformly drawn row of `triples` (windows_cuda.cu:353-365)
+        const uint64_t row0 = (uint64_t)i0 * K * R;  // first global negative row of this tile (a multiple of 4)
+        const uint32_t n_rows = (uint32_t)tw * K * R;
+        int64_t* dst = a.out[neg_out] + row0 * 3u;
+        const bool small = (uint64_t)a.n_triples <= 0xFFFFFFFFull;
+        for (uint32_t base = 0; base < n_rows; base += kNegChunkRows) {
+            const uint32_t rows = min((uint32_t)kNegChunkRows, n_rows - base);
+            for (uint32_t q = tid; q * 4u < rows; q += BLOCK) {
+                const uint64_t gq = (row0 + base) / 4u + q;
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), 3u, 0x51554144u), a.key);
+                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (q * 4u + j < rows) neg_rows[q * 4u + j] = small ? __umulhi(w[j], (uint32_t)a.n_triples) : w[j];
+            }
+            __syncthreads();
+            const uint32_t n = rows * 3u;
+            for (uint32_t e = tid; e < n; e += BLOCK) {
+                const uint32_t row = e / 3u, c = e - row * 3u;
+                int64_t idx = neg_rows[row];
+                if (!small) {  // more than 2^32 triples: widen the draw with a second block (never in practice)
+                    const uint64_t g = row0 + base + row;
+                    const uint2 r = draw64(a.key, g, 3u, 1u);
+                    idx = bounded((uint32_t)idx, r.x, a.n_triples);
+                }
+                dst[(uint64_t)base * 3u + e] = __ldg(a.triples + idx * 3 + c);
+            }
+            __syncthreads();
+        }
+    } else {
+        // neg_triples: one row per target, redrawn while identical to the positive triple (windows_cuda.cu:485-505)
+        int64_t* dst = a.out[neg_out] + (uint64_t)i0 * K * 3u;
+        const uint32_t n = (uint32_t)tw * K * 3u;
+        Odometer o;
+        o.init((uint32_t)tid, BLOCK, 1u, K);
+        for (uint32_t e = tid; e < n; e += BLOCK, o.advance()) {
+            const uint64_t grow = ((uint64_t)i0 + o.i) * K + o.ti;
+            const int64_t* w = tile + (size_t)o.i * a.wl + 2u * o.ti;
+            const int64_t ph = w[0], pr = w[1], pt = w[2];
+            int64_t idx = 0;
+            for (uint32_t attempt = 0; attempt <= 101u; ++attempt) {
+                const uint2 r = draw64(a.key, grow, 4u, attempt);
+                idx = bounded(r.x, r.y, a.n_triples);
+                if (__ldg(a.triples + idx * 3) != ph || __ldg(a.triples + idx * 3 + 1) != pr || __ldg(a.triples + idx * 3 + 2) != pt) break;
+            }
+            dst[e] = __ldg(a.triples + idx * 3 + o.c);
+        }
+    }
+}
+
 template <int MODE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
     extern __shared__ __align__(16) int64_t smem_tile[];
@@ -155,6 +264,9 @@ __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
         __syncthreads();
         tile = smem_tile;
     }
+    if constexpr (MODE == kTriples || MODE == kTriplesCbow) {
+        triple_tile<MODE, BLOCK>(a, tile, i0, tw);
+    } else {
 #pragma unroll
     for (int which = 0; which < 3; ++which) {
         const uint64_t gbase = (uint64_t)i0 * a.epw[which];
@@ -172,6 +284,7 @@ __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
         } else {
             for (uint32_t k = threadIdx.x; k < n; k += BLOCK) dst[k] = window_element<MODE>(a, tile, which, k, gbase + k);
         }
+    }
     }
 }
 
@@ -232,9 +345,15 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     a.use_smem = 1;
     if (smem > 200 * 1024) { a.use_smem = 0; smem = 0; }
     a.tile_walks = (int)tw;
-    if (smem > 48 * 1024) {
-        int rc = check_cuda(cudaFuncSetAttribute(windows_kernel<MODE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-        if (rc) return rc;
+    if (smem > 24 * 1024) {  // static shared memory (the negative-row chunk) counts against the 48 KiB default too
+        // raise the opt-in limit once per device and mode; the call is far too slow to repeat per launch
+        static size_t opted_in[64];
+        if (d >= 64 || opted_in[d] < smem) {
+            int rc = check_cuda(cudaFuncSetAttribute(windows_kernel<MODE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     200 * 1024), name);
+            if (rc) return rc;
+            if (d < 64) opted_in[d] = 200 * 1024;
+        }
     }
     const int64_t tiles = (n_walks + tw - 1) / tw;
     if (tiles > 0x7FFFFFFFll) { set_error("%s: too many tiles", name); return TRW_ERR_ARG; }
