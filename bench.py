@@ -236,23 +236,21 @@ def run_c4(args, wl):
         step(k)
     torch.cuda.synchronize()
     native.reset_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    walk_ms = win_ms = 0.0
-    with ClockSampler(dev.index) as clocks:
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
+    def timed_loop(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for k in range(args.steps):
-            ev[0].record()
-            walks = rw.walk_triples(ts, index, targets, walk_length=L, padding_idx=pad, seed=100 + k)
-            ev[1].record()
-            outs = rw.to_windows_triples(walks, W, n_ent, pad, ts, 100 + k)
-            ev[2].record()
-            torch.cuda.synchronize()
-            walk_ms += ev[0].elapsed_time(ev[1]); win_ms += ev[1].elapsed_time(ev[2])
-        t1.record()
+            out_ = fn(100 + k)
+        e1.record()
         torch.cuda.synchronize()
-    launches = native.launch_count()
-    total_ms = walk_ms + win_ms
+        return e0.elapsed_time(e1), out_
+
+    with ClockSampler(dev.index) as clocks:
+        step_ms, (walks, outs) = timed_loop(step)                                    # the whole step, K times
+        walk_ms, walks = timed_loop(lambda sd: rw.walk_triples(ts, index, targets, walk_length=L, padding_idx=pad, seed=sd))
+        win_ms, outs = timed_loop(lambda sd: rw.to_windows_triples(walks, W, n_ent, pad, ts, sd))
+    launches = native.launch_count() // 2  # the step loop plus its two halves timed separately
+    total_ms = step_ms
     hops = targets.numel() * L * args.steps
     n_win = outs[0].size(0)
     win_bytes = sum(o.numel() for o in outs) * 8
