@@ -232,6 +232,30 @@ def test_edge_cases(rw, native):
     check_walks_follow_edges(w, rp, ci, torch.arange(100, device="cuda")[::2])
 
 
+def test_degenerate_graphs(rw):
+    # no edges at all: every walk stays on its start node, for every (p, q)
+    rp = torch.zeros(11, dtype=torch.int64, device="cuda")
+    ci = torch.empty(0, dtype=torch.int64, device="cuda")
+    nodes = torch.arange(10, device="cuda")
+    for p, q in ((1.0, 1.0), (0.5, 2.0), (1.0, 0.5), (0.25, 4.0)):
+        assert torch.equal(rw.walk(rp, ci, nodes, p, q, 7, 1), nodes[:, None].expand(-1, 8))
+    # a single self-loop and a 2-cycle; long walks; one walk
+    rp = torch.tensor([0, 1, 2, 3], dtype=torch.int64, device="cuda")
+    ci = torch.tensor([0, 2, 1], dtype=torch.int64, device="cuda")
+    for p, q in ((1.0, 1.0), (0.25, 4.0), (4.0, 0.25)):
+        w = rw.walk(rp, ci, torch.tensor([1], device="cuda"), p, q, 1000, 3).cpu()
+        assert w.shape == (1, 1001) and w[0, ::2].eq(1).all() and w[0, 1::2].eq(2).all()
+        w = rw.walk(rp, ci, torch.tensor([0], device="cuda"), p, q, 33, 3)
+        assert bool((w == 0).all())
+    # a star: the hub row (>= 2048 neighbours) goes through the hub-segment builder
+    n = 5000
+    hub_rp = torch.cat((torch.tensor([0, n - 1]), n - 1 + torch.arange(1, n))).cuda()
+    hub_ci = torch.cat((torch.arange(1, n), torch.zeros(n - 1, dtype=torch.int64))).cuda()
+    w = rw.walk(hub_rp, hub_ci, torch.arange(n, device="cuda"), 0.5, 2.0, 9, 1).cpu()
+    assert bool((w[1:, 1] == 0).all()) and bool((w[0, 1] > 0).all())
+    assert bool((w[:, 2:][w[:, 1:-1] == 0] > 0).all()) and bool((w[:, 2:][w[:, 1:-1] > 0] == 0).all())
+
+
 def test_first_order_transitions_are_uniform(rw, golden):
     rp, ci = T(golden["utils/karate/row_ptr"]), T(golden["utils/karate/col_idx"])
     n = 34
