@@ -113,6 +113,19 @@ __device__ __forceinline__ uint64_t make_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t make_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// Store policy of the walk output by experiment mode (option store_mode): 0 evict_first (shipped),
+// 1 evict_normal, 2 evict_last, 3 no stores at all (measures what the output costs; results are lost).
+__device__ __forceinline__ uint64_t output_policy(int mode) {
+    if (mode == 1) return make_policy_evict_normal();
+    if (mode == 2) return make_policy_evict_last();
+    if (mode == 3) return 0;
+    return make_policy_evict_first();
+}
 __device__ __forceinline__ int64_t ldg32_keep(const uint32_t* p, uint64_t pol) {
     uint32_t v;
     asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
@@ -178,6 +191,7 @@ struct RowStager {
     }
     // Store element s (0-based, strictly increasing calls); `last` marks the final element.
     __device__ __forceinline__ void put(int s, int64_t v, bool last) {
+        if (policy == 0) return;  // store_mode 3 (measurement only)
         uint32_t slot = (phase + (uint32_t)s) & 3u;
         ring[slot][tid] = v;
         if (slot == 3u || last) {

@@ -17,6 +17,7 @@ struct Options {
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
     int64_t host_chunk_walks = 1 << 20;  // walks per pipelined chunk in trw_walk_csr_host
     int64_t host_cache_buffers = 1;  // 1: trw_walk_csr_host keeps its device buffers between calls
+    int64_t store_mode = 0;       // output-store L2 policy experiment: 0 evict_first, 1 normal, 2 evict_last, 3 no stores
     int64_t calib_mode = 0;       // load flavour of the 8-byte calibration gather (see calib_load64)
     int64_t time_kernels = 0;     // 1: bracket the CSR table build and walk kernel with CUDA events (trw_last_kernel_ms)
 };
@@ -24,7 +25,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(store_mode)
 
 Options& options();
 void count_launch(int n);

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowOut<BLOCK, STAGE> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, pol_stream);
+    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
 
     int64_t v = __ldg(a.targets + i);
     const int L = a.walk_length;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowOut<BLOCK, STAGE> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, pol_stream);
+    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
     const int L = a.walk_length;
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
     // a table whose build reported an overflowing segment is not trusted: scan instead
@@ -300,6 +300,7 @@ int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* c
     a.walk_length = walk_length; a.key = philox_key(seed, kTagWalkCsr);
     a.out = nullptr; a.out_row_stride = 0; a.table = nullptr; a.table_failed = nullptr; a.row32 = nullptr;
     a.thr0 = a.thr1 = a.thr2 = 0;
+    a.store_mode = (int)opt.store_mode;
     a.fthr1 = a.fthr2 = 0; a.fold_env = a.fold_excess = 0.0; a.strict_counts = nullptr;
     plan->fold = false;
     plan->device = device;

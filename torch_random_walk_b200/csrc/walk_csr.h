@@ -11,6 +11,7 @@ struct WalkArgs {
     const int64_t* targets;
     int64_t n_walks, walk_id_offset;
     int walk_length;
+    int store_mode;  // experiment: L2 policy of the output stores (see output_policy)
     uint2 key;
     int64_t* out;
     int64_t out_row_stride;
