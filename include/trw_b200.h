@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TRW_ABI_VERSION 1
+#define TRW_ABI_VERSION 2
 
 enum {
     TRW_OK = 0,
@@ -70,6 +70,10 @@ int trw_device_check(int device);
  * reference's linear scan of adj(t).
  * ------------------------------------------------------------------------------------- */
 size_t trw_walk_csr_workspace_bytes(int64_t n_nodes, int64_t nnz, double p, double q);
+/* The exact size this call shape uses: shorter than the bound above when the walk is too short
+ * to pay for the per-call edge records (n_walks * walk_length < 3 * nnz). */
+size_t trw_walk_csr_workspace_bytes_for(int64_t n_nodes, int64_t nnz, double p, double q,
+                                        int64_t n_walks, int walk_length);
 
 int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                  const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
@@ -77,6 +81,29 @@ int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes
                  int64_t* out, int64_t out_row_stride,
                  void* workspace, size_t workspace_bytes,
                  int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Prepared graphs.  Everything trw_walk_csr derives from the graph alone (uint32 row index,
+ * hashed membership table, duplicate-edge check, 16-byte edge records) does not depend on p, q,
+ * the seed or the start nodes.  A caller that walks the same graph repeatedly (one rw.walk per
+ * epoch) prepares it once and passes the handle; the walk call is then the walk kernel alone.
+ * The reference has no counterpart (its walk_gpu is stateless, csrc/cuda/rw_cuda.cu:186-248);
+ * results are bit-identical to trw_walk_csr on the same arguments.
+ *
+ *   workspace: trw_csr_graph_workspace_bytes(n_nodes, nnz) bytes of 256-byte aligned device
+ *   memory.  It, row_ptr and col_idx belong to the caller and must stay alive and unchanged
+ *   until trw_csr_graph_destroy.  Preparation is enqueued on `stream`; walks on another stream
+ *   must be ordered after it by the caller.
+ * ------------------------------------------------------------------------------------- */
+typedef struct trw_csr_graph trw_csr_graph;
+size_t trw_csr_graph_workspace_bytes(int64_t n_nodes, int64_t nnz);
+int trw_csr_graph_prepare(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                          void* workspace, size_t workspace_bytes, int device, void* stream,
+                          trw_csr_graph** out_graph);
+int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* targets, int64_t n_walks,
+                          int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
+                          int64_t* out, int64_t out_row_stride, void* stream);
+void trw_csr_graph_destroy(trw_csr_graph* graph);
 
 /* Same computation with every buffer in HOST memory (pinned or pageable): stages the graph and
  * the start nodes to the device, walks in chunks and streams finished chunks back while the

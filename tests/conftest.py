@@ -25,3 +25,17 @@ def orc():
 
     _orc.build()
     return _orc
+
+
+@pytest.fixture(autouse=True)
+def _graph_cache_off_by_default(request):
+    """GPU tests compare library options on repeated calls with the same tensors; rw.walk's graph
+    cache would keep the first preparation.  Tests of the cache switch it on themselves."""
+    if "gpu" not in request.keywords:
+        yield
+        return
+    from torch_random_walk_b200 import native
+
+    native.set_graph_cache(False)
+    yield
+    native.set_graph_cache(False)

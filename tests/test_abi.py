@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 16
     for name in names:
         assert getattr(lib, name) is not None, name
-    assert lib.trw_abi_version() == 1
+    assert lib.trw_abi_version() == 2
 
 
 def test_library_has_no_torch_or_oracle_dependency():
@@ -105,6 +105,14 @@ def test_argument_validation_precedes_device_use():
     assert lib.trw_walk_csr(buf, buf, 1, 1, buf, 1, 0, 1.0, 1.0, 2, 1, buf, 2, None, 0, 0, None) == -1  # stride < L+1
     assert lib.trw_set_option(b"no_such_option", 1) == -1
     assert lib.trw_get_option(b"stage_output") in (0, 1)
-    uniform_ws = lib.trw_walk_csr_workspace_bytes(10, 100, 1.0, 1.0)  # only the uint32 row index
-    assert 11 * 4 <= uniform_ws <= 1024
-    assert lib.trw_walk_csr_workspace_bytes(10, 100, 0.5, 2.0) >= 100 * 8 + uniform_ws
+    short_ws = lib.trw_walk_csr_workspace_bytes_for(10, 100, 1.0, 1.0, 5, 10)  # short walk: only the uint32 row index
+    assert 11 * 4 <= short_ws <= 1024
+    # long walks add the 16-byte edge records; the unconditional bound covers them
+    assert lib.trw_walk_csr_workspace_bytes_for(10, 100, 1.0, 1.0, 50, 10) >= short_ws + 100 * 16
+    assert lib.trw_walk_csr_workspace_bytes(10, 100, 1.0, 1.0) >= short_ws + 100 * 16
+    assert lib.trw_walk_csr_workspace_bytes_for(10, 100, 0.5, 2.0, 5, 10) >= 100 * 8 + short_ws
+    assert lib.trw_csr_graph_workspace_bytes(10, 100) >= 100 * 24
+    handle = ctypes.c_void_p()
+    assert lib.trw_csr_graph_prepare(buf, buf, 1, 1, None, 0, 0, None, None) == -1  # null out_graph
+    assert lib.trw_walk_csr_prepared(None, buf, 1, 0, 1.0, 1.0, 2, 1, buf, 3, None) == -1  # null graph
+    lib.trw_csr_graph_destroy(None)

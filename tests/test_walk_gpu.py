@@ -89,7 +89,8 @@ def test_shards_are_bit_identical_to_one_call(native, p, q):
         assert torch.equal(torch.cat(parts), full), world
 
 
-DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": 4, "n2v_fold": 1}
+DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": 5, "n2v_fold": 1,
+            "records": -1}
 
 
 def test_kernel_variants_agree_bit_for_bit(native):
@@ -99,7 +100,8 @@ def test_kernel_variants_agree_bit_for_bit(native):
     rp, ci = random_csr(3, 4000, 60)  # mean degree 60: most rows use the table (>= 12 neighbours)
     rp, ci = cuda(rp, ci)
     nodes = torch.arange(4000, device="cuda")
-    variants = [{}, {"n2v_table": 0}, {"n2v_speculate": 0}, {"n2v_speculate": 1}, {"stage_output": 0}, {"row32": 0},
+    variants = [{}, {"records": 1}, {"records": 0}, {"records": 0, "n2v_table": 0}, {"records": 1, "n2v_table": 0},
+                {"records": 1, "n2v_min_ctas": 4}, {"n2v_min_ctas": 4}, {"smem_carveout_kb": 64}, {"n2v_table": 0}, {"n2v_speculate": 0}, {"n2v_speculate": 1}, {"stage_output": 0}, {"row32": 0},
                 {"build_mode": 0}, {"n2v_min_ctas": 5}, {"n2v_min_ctas": 6},
                 {"n2v_table": 0, "row32": 0, "stage_output": 0}, {"build_mode": 0, "row32": 0, "n2v_min_ctas": 6}]
     base = None
@@ -138,6 +140,75 @@ def test_table_build_on_skewed_graph_matches_scan(native):
         native.set_option("n2v_table", 1)
     assert torch.equal(a, b)
     assert torch.equal(a[:3000], c)
+
+
+def test_edge_records_match_row_index_path(native):
+    """Edge records (the proposal gather returns the neighbour's row span) vs row-index lookups, on a
+    graph with hubs, empty rows and neighbour ids outside [0, n): bit-identical walks, all three laws."""
+    from torch_random_walk_b200 import rmat
+
+    rp, ci = rmat.rmat_csr(16, 16, device="cuda", seed=11)
+    ci = ci.clone()
+    n = rp.numel() - 1
+    ci[::9973] = n + 5          # ids outside the graph: nodes without out-edges (the walk stays there)
+    ci[5::19997] = (1 << 40) + 3  # and one that needs the high word of the record
+    nodes = torch.arange(n, device="cuda")
+    res = {}
+    try:
+        for rec in (1, 0):
+            native.set_option("records", rec)
+            res[rec] = [native.walk(rp, ci, nodes, p_, q_, 20, 7) for p_, q_ in ((1.0, 1.0), (1.0, 0.5), (0.5, 2.0), (2.0, 1.0))]
+    finally:
+        native.set_option("records", -1)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
+    assert bool((res[1][1] == (1 << 40) + 3).any())
+
+
+def test_prepared_graph_and_graph_cache(native, rw):
+    """A graph prepared once (explicit handle, or rw.walk's cache from the second call on) must give
+    the walks of the stateless call, for every law, on any stream, and must notice in-place edits."""
+    from torch_random_walk_b200 import rmat
+
+    rp, ci = rmat.rmat_csr(15, 16, device="cuda", seed=3)
+    n = rp.numel() - 1
+    nodes = torch.arange(n, device="cuda")
+    laws = ((1.0, 1.0), (1.0, 0.5), (0.5, 2.0), (0.25, 4.0), (2.0, 1.0))
+    base = [native.walk(rp, ci, nodes, p_, q_, 30, 11, cache=False) for p_, q_ in laws]
+    g = native.prepare_csr(rp, ci)
+    for (p_, q_), b in zip(laws, base):
+        assert torch.equal(g.walk(nodes, p_, q_, 30, 11), b)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        w = g.walk(nodes, 1.0, 0.5, 30, 11)
+    side.synchronize()
+    assert torch.equal(w, base[1])
+    # sharded calls through the handle keep global walk ids
+    half = n // 2
+    parts = [g.walk(nodes[:half], 0.5, 2.0, 30, 11), g.walk(nodes[half:], 0.5, 2.0, 30, 11, walk_id_offset=half)]
+    assert torch.equal(torch.cat(parts), base[2])
+    del g
+
+    native.set_graph_cache(True)
+    try:
+        launches = []
+        for k in range(4):
+            native.reset_launch_count()
+            assert torch.equal(rw.walk(rp, ci, nodes, 1.0, 0.5, 30, 11), base[1])
+            launches.append(native.launch_count())
+        # call 1 one-shot (build + walk), call 2 prepares for keeps, calls 3+ are the walk kernel alone
+        assert launches[2] == 1 and launches[3] == 1 and launches[0] > 1 and launches[1] > launches[0]
+        assert torch.equal(rw.walk(rp, ci, nodes, 0.25, 4.0, 30, 11), base[3])  # same graph, other law: still cached
+        # an in-place edit bumps the version counter: the cached preparation must not be used
+        ci2 = ci.clone()
+        for _ in range(3):
+            ref = rw.walk(rp, ci2, nodes, 1.0, 0.5, 30, 11)
+        ci2[rp[5]:rp[6]] = ci2[rp[5]]  # all neighbours of node 5 become the same node
+        edited = rw.walk(rp, ci2, nodes, 1.0, 0.5, 30, 11)
+        assert torch.equal(edited, native.walk(rp, ci2, nodes, 1.0, 0.5, 30, 11, cache=False))
+        assert not torch.equal(edited, ref)
+    finally:
+        native.set_graph_cache(False)
 
 
 def test_unsorted_rows_and_duplicate_edges(native):

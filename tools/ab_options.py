@@ -30,6 +30,7 @@ def main():
     L = 80
     out = torch.empty((targets.numel(), L + 1), dtype=torch.int64, device="cuda")
     native.set_option("time_kernels", 1)
+    native.set_graph_cache(False)  # every variant must build with its own options
     res = {}
     for variant in ["default"] + args:
         opts = {} if variant == "default" else {kv.split("=")[0]: int(kv.split("=")[1]) for kv in variant.split(",")}

@@ -38,7 +38,7 @@ torch::Tensor walk(const torch::Tensor* row_ptr, const torch::Tensor* column_idx
   auto rp = row_ptr->contiguous(), ci = column_idx->contiguous(), tg = target_nodes->contiguous();
   auto walks = torch::empty({tg.size(0), walk_length + 1}, like(rp));
   const int64_t n_nodes = std::max<int64_t>(rp.size(0) - 1, 0), nnz = ci.size(0);
-  const size_t need = tg.size(0) ? trw_walk_csr_workspace_bytes(n_nodes, nnz, p, q) : 0;
+  const size_t need = tg.size(0) ? trw_walk_csr_workspace_bytes_for(n_nodes, nnz, p, q, tg.size(0), (int)walk_length) : 0;
   auto ws = torch::empty({(int64_t)need}, like(rp).dtype(torch::kUInt8));
   TRW_CHECK(trw_walk_csr(ptr(rp), ptr(ci), n_nodes, nnz, ptr(tg), tg.size(0), 0, p, q, walk_length, seed,
                          walks.data_ptr<int64_t>(), walk_length + 1, need ? ws.data_ptr() : nullptr, need,

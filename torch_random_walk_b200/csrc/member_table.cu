@@ -379,10 +379,38 @@ __global__ void __launch_bounds__(256) strict_boundaries_kernel(const int64_t* _
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(counts + 1, n);
 }
 
+// Edge records (member_table.cuh): one streaming pass over col_idx; the two row-index reads per
+// entry hit the L2-resident uint32 index (evict_last), the 16-byte records leave coalesced.
+__global__ void __launch_bounds__(256) edge_records_kernel(const int64_t* __restrict__ col_idx, int64_t nnz,
+                                                           const uint32_t* __restrict__ row32, int64_t n_nodes,
+                                                           uint4* __restrict__ records) {
+    constexpr int kBatch = 4;  // independent entries per thread and round
+    const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += kBatch * gsz) {
+        int64_t x[kBatch];
+        uint32_t b[kBatch], e[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) x[u] = i + u * gsz < nnz ? ldg64_stream(col_idx + i + u * gsz) : -1;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const bool inside = (uint64_t)x[u] < (uint64_t)n_nodes;
+            b[u] = inside ? (uint32_t)ldg32_keep(row32 + x[u], pol_keep) : 0u;
+            e[u] = inside ? (uint32_t)ldg32_keep(row32 + x[u] + 1, pol_keep) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            if (i + u * gsz >= nnz) continue;
+            const uint64_t id = (uint64_t)x[u];
+            stg_u32x4_hint(records + i + u * gsz, (uint32_t)id, e[u] - b[u], b[u], (uint32_t)(id >> 32), pol_stream);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform) {
+CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bool records) {
     CsrWorkspace w{};
     const bool ids_fit = (uint64_t)n_nodes < 0xFFFFFFFFull;   // neighbour ids must fit the uint32 table slots
     const bool offsets_fit = (uint64_t)nnz <= 0xFFFFFFFFull;   // row offsets must fit the uint32 row index
@@ -405,15 +433,19 @@ CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform) {
     if (nnz > 0) off += 256;
     w.row32 = off;
     if (w.has_row32) off += align256((size_t)(n_nodes + 1) * 4);
+    w.has_records = records && w.has_row32 && nnz > 0;  // spans are stored as uint32 (start, degree)
+    w.records = off;
+    if (w.has_records) off += align256((size_t)nnz * 16);
     w.total = off;
     return w;
 }
 
 int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
-                       const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, int build_mode,
-                       int device, cudaStream_t st, CsrPrepared* out) {
+                       const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, bool want_records,
+                       int build_mode, int device, cudaStream_t st, CsrPrepared* out) {
     want_table = want_table && w.has_table;
     want_row32 = want_row32 && w.has_row32;
+    want_records = want_records && w.has_records && want_row32;
     want_strict = want_strict && nnz > 0;
     *out = CsrPrepared{};
     if (!want_table && !want_row32 && !want_strict) return TRW_OK;
@@ -481,6 +513,14 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
         out->table_failed = b.failed;
     }
     out->row32 = b.row32;
+    if (want_records) {
+        uint4* records = (uint4*)(ws + w.records);
+        edge_records_kernel<<<sms * 16, 256, 0, st>>>(col_idx, nnz, b.row32, n_nodes, records);
+        count_launch(1);
+        rc = check_cuda(cudaGetLastError(), "edge records launch");
+        if (rc) return rc;
+        out->records = records;
+    }
     return TRW_OK;
 }
 

@@ -87,24 +87,31 @@ __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const
 // ---------------------------------------------------------------- host side (member_table.cu)
 // Offsets of the per-call scratch inside the caller's workspace (all 256-byte aligned).
 struct CsrWorkspace {
-    size_t table, tile_row0, hub_list, seg_work, cells, row32, total;
+    size_t table, tile_row0, hub_list, seg_work, cells, row32, records, total;
     int64_t n_tiles, n_buckets, max_hubs, max_segs;
-    bool has_table, has_row32;
+    bool has_table, has_row32, has_records;
 };
-CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform);
+CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bool records);
+
+// Edge record k of the CSR (option `records`): the neighbour id col_idx[k] together with that
+// neighbour's own row span, so that the gather which proposes the next node also returns where
+// its adjacency lives and the walk never touches the row index again (16 bytes, one LDG.128).
+//   .x = id, low 32 bits   .y = degree of id   .z = row start of id   .w = id, high 32 bits
+// An id outside [0, n_nodes) gets degree 0, i.e. a node without out-edges, as load_row() treats it.
 
 struct CsrPrepared {
     const uint32_t* table = nullptr;     // membership table, or nullptr
     const uint32_t* row32 = nullptr;     // uint32 copy of row_ptr, or nullptr
     const int* table_failed = nullptr;   // device flag: non-zero when a hub segment overflowed
     const unsigned long long* strict_counts = nullptr;  // [descents in col_idx, descents at row boundaries]
+    const uint4* records = nullptr;      // edge records, or nullptr
 };
 
 // Enqueues on `st` the per-call preparation of a CSR graph: the uint32 row index and (node2vec)
 // the membership table, and (want_strict) the two counters that tell whether every row is strictly
 // increasing, i.e. sorted without duplicate edges.  build_mode: 2 = shared memory (default), 0 = global CAS.
 int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
-                       const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, int build_mode,
-                       int device, cudaStream_t st, CsrPrepared* out);
+                       const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, bool want_records,
+                       int build_mode, int device, cudaStream_t st, CsrPrepared* out);
 
 }  // namespace trw

@@ -104,15 +104,20 @@ __device__ __forceinline__ uint64_t calib_load64(const int64_t* p, uint64_t pol)
 template <int BYTES, int MODE>
 __global__ void __launch_bounds__(256) calib_gather_kernel(const int64_t* __restrict__ table, uint64_t n_units,
                                                            int64_t n_threads, int loads, uint2 key,
-                                                           int64_t* __restrict__ sink) {
+                                                           int64_t* __restrict__ sink, int aux_mb) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_threads) return;
     const uint64_t pol = make_policy_evict_first();
+    const uint64_t pol_keep = make_policy_evict_last();
     uint64_t acc = 0;
     uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0, 0), key);
     uint64_t state = ((uint64_t)r.x << 32) | r.y;
     for (int k = 0; k < loads; ++k) {
         state = state * 6364136223846793005ull + 1442695040888963407ull;
+        if (aux_mb > 0) {  // experiment: one dependent L2-resident lookup per step, like the walk's row index
+            const uint64_t a_unit = __umul64hi(state ^ (state >> 31), (uint64_t)aux_mb << 18);
+            state += (uint64_t)ldg32_keep(reinterpret_cast<const uint32_t*>(table) + a_unit, pol_keep) & 0xFFu;
+        }
         uint64_t unit = __umul64hi(state ^ (state >> 29), n_units);
         if (BYTES == 8) {
             uint64_t v = calib_load64<MODE>(table + unit, pol);
@@ -169,7 +174,8 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
     uint2 key = philox_key(seed, 0x43414C49u);
     const int64_t units8 = table_elems;
     const int mode = (int)options().calib_mode;
-#define TRW_CALIB8(M) calib_gather_kernel<8, M><<<grid, 256, 0, st>>>(table, (uint64_t)units8, n_threads, loads_per_thread, key, sink)
+    const int aux_mb = (int)options().calib_aux_mb;
+#define TRW_CALIB8(M) calib_gather_kernel<8, M><<<grid, 256, 0, st>>>(table, (uint64_t)units8, n_threads, loads_per_thread, key, sink, aux_mb)
     if (bytes_per_load == 8) {
         switch (mode) {
             case 1: TRW_CALIB8(1); break;
@@ -181,11 +187,11 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
             default: TRW_CALIB8(0); break;
         }
     } else if (bytes_per_load == 32)
-        calib_gather_kernel<32, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 4), n_threads, loads_per_thread, key, sink);
+        calib_gather_kernel<32, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 4), n_threads, loads_per_thread, key, sink, aux_mb);
     else if (bytes_per_load == 64)
-        calib_gather_kernel<64, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 8), n_threads, loads_per_thread, key, sink);
+        calib_gather_kernel<64, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 8), n_threads, loads_per_thread, key, sink, aux_mb);
     else
-        calib_gather_kernel<128, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 16), n_threads, loads_per_thread, key, sink);
+        calib_gather_kernel<128, 0><<<grid, 256, 0, st>>>(table, (uint64_t)(table_elems / 16), n_threads, loads_per_thread, key, sink, aux_mb);
 #undef TRW_CALIB8
     count_launch(1);
     return check_cuda(cudaGetLastError(), "calib_gather launch");

@@ -151,6 +151,16 @@ __device__ __forceinline__ void stg_sector_hint(void* p, uint64_t a, uint64_t b,
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u64 [%0], {%1,%2,%3,%4}, %5;"
                  ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void stg_u32x4_hint(uint4* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_u32x4_hint(const uint4* p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ void stg64_hint(int64_t* p, int64_t v, uint64_t pol) {
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
@@ -204,6 +214,64 @@ struct RowStager {
                 for (int e = lo; e <= s; ++e) stg64_hint(row + e, ring[(phase + (uint32_t)e) & 3u][tid], policy);
             }
         }
+    }
+};
+
+
+// ---------------------------------------------------------------- staged row output, 128-byte lines
+// What bounds a random-gather kernel on B200 is the number of *requests* that leave L2 for memory
+// (about 48 G/s: profiles/), and a store request counts like a missed load whatever its size.  The
+// sector stager above issues one request per 32 bytes of output; this one parks 16 elements per
+// thread (one 128-byte line of its row) in shared memory and lets the warp write finished lines
+// cooperatively: 16 lanes x 8 bytes cover one whole line, so a store instruction carries two full
+// lines in two requests, a quarter of the requests per byte.  put() is a warp collective: all 32
+// lanes call it in convergence, `have` says whether this lane appends an element.
+template <int BLOCK, int SLOTS = 16>
+struct LineStager {
+    static_assert(SLOTS == 4 || SLOTS == 8 || SLOTS == 16, "a piece is 32, 64 or 128 bytes");
+    static constexpr int kPitch = SLOTS + 1;  // + 1: keeps the lanes' puts off a common bank for any row stride
+    static constexpr int kOwners = 32 / SLOTS;  // pieces written per store instruction
+    int64_t* ring;    // [BLOCK][kPitch] in shared memory
+    int64_t* row;     // this lane's output row
+    uint64_t policy;  // L2 policy of the stores
+    uint32_t phase;   // (address of row[0] / 8) & (SLOTS - 1)
+    int tid;
+
+    __device__ __forceinline__ void init(int64_t* smem, int64_t* row_, int tid_, uint64_t policy_) {
+        ring = smem; row = row_; tid = tid_; policy = policy_;
+        phase = (uint32_t)(((uintptr_t)row_ >> 3) & (SLOTS - 1));
+    }
+    // Element s of the row (calls with have == true come with strictly increasing s); `last` marks the final one.
+    __device__ __forceinline__ void put(bool have, int s, int64_t v, bool last) {
+        if (policy == 0) return;  // store_mode 3 (measurement only)
+        bool pending = false;
+        uint32_t slot = 0;
+        if (have) {
+            slot = (phase + (uint32_t)s) & (uint32_t)(SLOTS - 1);
+            ring[tid * kPitch + slot] = v;
+            pending = (slot == (uint32_t)(SLOTS - 1)) || last;
+        }
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, pending);
+        if (mask == 0) return;
+        __syncwarp();
+        // this lane's finished piece: slot 0 sits at row[first]; slots [lo, slot] hold elements of this row
+        const int first = s - (int)slot;
+        const unsigned long long piece_ptr = (unsigned long long)(uintptr_t)(row + first);
+        const uint32_t range = (uint32_t)(first < 0 ? -first : 0) | (slot << 8);
+        const int lane = tid & 31, sub = lane & (SLOTS - 1), group = lane / SLOTS;
+        while (mask) {
+            const int owner = (int)__fns(mask, 0, group + 1);  // the group-th pending lane, or -1 (0xFFFFFFFF)
+#pragma unroll
+            for (int k = 0; k < kOwners; ++k) mask &= mask - 1;  // no-op once zero
+            const int src = owner < 0 ? 0 : owner;
+            const unsigned long long pp = __shfl_sync(0xFFFFFFFFu, piece_ptr, src);
+            const uint32_t rg = __shfl_sync(0xFFFFFFFFu, range, src);
+            if (owner >= 0 && (uint32_t)sub >= (rg & 0xFFu) && (uint32_t)sub <= (rg >> 8)) {
+                const int64_t val = ring[((tid & ~31) + owner) * kPitch + sub];
+                stg64_hint(reinterpret_cast<int64_t*>((uintptr_t)pp) + sub, val, policy);
+            }
+        }
+        __syncwarp();
     }
 };
 

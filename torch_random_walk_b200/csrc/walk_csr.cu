@@ -21,6 +21,8 @@
 //     16 M nodes) and read with an L2 evict_last policy, while the never-reused gathers
 //     (proposals, table buckets) and the output stores carry evict_first, so the stream of
 //     random lines does not wash the row index out of L2: row lookups cost no HBM traffic.
+#include <new>
+
 #include "member_table.cuh"
 #include "trw_common.cuh"
 #include "trw_options.h"
@@ -43,55 +45,78 @@ __device__ __forceinline__ void load_row(const WalkArgs& a, int64_t v, int64_t& 
     }
 }
 
-// Neighbour of v at a uniformly random position, or v itself when it has none (rw_cuda.cu:8-31).
-__device__ __forceinline__ int64_t pick_neighbor(const WalkArgs& a, int64_t v, int64_t b, int64_t e, uint32_t r0,
-                                                 uint32_t r1, uint64_t pol_stream) {
+// Proposal: the neighbour of v at a uniformly random position, or v itself when it has none
+// (rw_cuda.cu:8-31).  REC: the gather is an edge record and also returns the neighbour's own row
+// span in (xb, xe); otherwise (xb, xe) are left for the caller to load.
+template <bool REC>
+__device__ __forceinline__ int64_t propose(const WalkArgs& a, int64_t v, int64_t b, int64_t e, uint32_t r0, uint32_t r1,
+                                           uint64_t pol_stream, int64_t& xb, int64_t& xe) {
     const int64_t deg = e - b;
-    if (deg <= 0) return v;
-    const int64_t idx = b + bounded(r0, r1, deg);
-    if ((uint64_t)idx >= (uint64_t)a.nnz) return v;
+    const int64_t idx = deg > 0 ? b + bounded(r0, r1, deg) : -1;
+    if ((uint64_t)idx >= (uint64_t)a.nnz) {  // no out-edge (or a span outside col_idx): the walk stays on v
+        xb = b; xe = e;
+        return v;
+    }
+    if (REC) {
+        const uint4 rec = ldg_u32x4_hint(a.records + idx, pol_stream);
+        xb = (int64_t)rec.z;
+        xe = xb + (int64_t)rec.y;
+        return (int64_t)(((uint64_t)rec.w << 32) | rec.x);
+    }
     return ldg64_hint(a.col_idx + idx, pol_stream);
 }
 
-template <int BLOCK, bool STAGE>
+// Output of one walk row: line-staged cooperative stores (STAGE) or plain 8-byte stores.  put() is a
+// warp collective (see LineStager): every lane of the warp calls it, `have` marks the lanes that append.
+template <int BLOCK, bool STAGE, int SLOTS = 16>
 struct RowOut {
-    RowStager<BLOCK> st;
+    LineStager<BLOCK, SLOTS> st;
     int64_t* row;
-    __device__ __forceinline__ void init(int64_t (*ring)[BLOCK], int64_t* r, int tid, uint64_t pol) {
+    __device__ __forceinline__ void init(int64_t* ring, int64_t* r, int tid, uint64_t pol) {
         row = r;
         if (STAGE) st.init(ring, r, tid, pol);
     }
-    __device__ __forceinline__ void put(int s, int64_t v, bool last) {
-        if (STAGE) st.put(s, v, last); else row[s] = v;
+    __device__ __forceinline__ void put(bool have, int s, int64_t v, bool last) {
+        if (STAGE) st.put(have, s, v, last);
+        else if (have) row[s] = v;
     }
+};
+template <int BLOCK, bool STAGE, int SLOTS = 16>
+struct RowOutSmem {
+    static constexpr int kWords = STAGE ? BLOCK * LineStager<BLOCK, SLOTS>::kPitch : 1;
 };
 
 // First-order walk: one thread per walk, two dependent gathers per step (row span from L2, then
 // the chosen col_idx entry from HBM), one Philox block per four steps.
-template <int BLOCK, bool STAGE, bool ROW32>
+template <int BLOCK, bool STAGE, bool ROW32, bool REC>
 __global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a) {
-    __shared__ int64_t ring[STAGE ? 4 : 1][BLOCK];
+    __shared__ int64_t ring[RowOutSmem<BLOCK, STAGE>::kWords];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= a.n_walks) return;
+    const bool live = i < a.n_walks;  // lanes past the end stay for the warp-collective stores
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowOut<BLOCK, STAGE> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
+    o.init(ring, a.out + (live ? i : 0) * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
 
-    int64_t v = __ldg(a.targets + i);
+    int64_t v = live ? __ldg(a.targets + i) : 0;
     const int L = a.walk_length;
-    o.put(0, v, L == 0);
+    o.put(live, 0, v, L == 0);
+    int64_t b = 0, e = 0;
+    if (REC && L > 0 && live) load_row<ROW32>(a, v, b, e, pol_keep);  // only the start node is looked up in the row index
     uint4 rnd = make_uint4(0, 0, 0, 0);
     for (int s = 1; s <= L; ++s) {
-        const int k = (s - 1) & 3;
-        if (k == 0)
-            rnd = philox4x32_10(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)((s - 1) >> 2), 0x80000000u), a.key);
-        const uint32_t r = rnd.x;
-        rnd.x = rnd.y; rnd.y = rnd.z; rnd.z = rnd.w;
-        int64_t b, e;
-        load_row<ROW32>(a, v, b, e, pol_keep);
-        v = pick_neighbor(a, v, b, e, r, r * 0x9E3779B1u + (uint32_t)s, pol_stream);
-        o.put(s, v, s == L);
+        if (live) {
+            const int k = (s - 1) & 3;
+            if (k == 0)
+                rnd = philox4x32_10(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)((s - 1) >> 2), 0x80000000u), a.key);
+            const uint32_t r = rnd.x;
+            rnd.x = rnd.y; rnd.y = rnd.z; rnd.z = rnd.w;
+            if (!REC) load_row<ROW32>(a, v, b, e, pol_keep);
+            int64_t xb, xe;
+            v = propose<REC>(a, v, b, e, r, r * 0x9E3779B1u + (uint32_t)s, pol_stream, xb, xe);
+            if (REC) { b = xb; e = xe; }
+        }
+        o.put(live, s, v, s == L);
     }
 }
 
@@ -107,147 +132,182 @@ __global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a
 // a point in bar x at height h is accepted iff h < min(w(x), M').  Every neighbour is therefore
 // still drawn with probability proportional to its node2vec weight (t: M' + e = 1/p).  This is
 // only exact when no edge is stored twice, which the prepare step verifies (strict_counts).
-template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32, bool FOLD>
+template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32, bool FOLD, bool REC>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const WalkArgs a) {
-    __shared__ int64_t ring[STAGE ? 4 : 1][BLOCK];
+    __shared__ int64_t ring[RowOutSmem<BLOCK, STAGE>::kWords];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= a.n_walks) return;
+    const bool live = i < a.n_walks;  // lanes past the end stay for the warp-collective stores
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     RowOut<BLOCK, STAGE> o;
-    o.init(ring, a.out + i * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
+    o.init(ring, a.out + (live ? i : 0) * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
     const int L = a.walk_length;
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
     // a table whose build reported an overflowing segment is not trusted: scan instead
     const uint32_t* table = (TABLE && a.table != nullptr && *a.table_failed == 0) ? a.table : nullptr;
 
-    int64_t t = __ldg(a.targets + i);
-    o.put(0, t, L == 0);
+    int64_t t = live ? __ldg(a.targets + i) : 0;
+    o.put(live, 0, t, L == 0);
     if (L == 0) return;
-    int64_t tb, te;
-    load_row<ROW32>(a, t, tb, te, pol_keep);
-    uint4 rnd = philox4x32_10(make_uint4(wlo, whi, 1u, 0u), a.key);
-    int64_t v = pick_neighbor(a, t, tb, te, rnd.x, rnd.z, pol_stream);  // first step is uniform (rw_cuda.cu:138)
-    o.put(1, v, L == 1);
+    int64_t tb = 0, te = 0, vb = 0, ve = 0, v = 0;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (live) {
+        load_row<ROW32>(a, t, tb, te, pol_keep);
+        rnd = philox4x32_10(make_uint4(wlo, whi, 1u, 0u), a.key);
+        v = propose<REC>(a, t, tb, te, rnd.x, rnd.z, pol_stream, vb, ve);  // first step is uniform (rw_cuda.cu:138)
+    }
+    o.put(live, 1, v, L == 1);
     if (L == 1) return;
-    int64_t vb, ve;
-    load_row<ROW32>(a, v, vb, ve, pol_keep);
+    if (!REC && live) load_row<ROW32>(a, v, vb, ve, pol_keep);
 
-    int s = 2;
+    // One loop iteration = one rejection trial of every lane that still walks, then the collective
+    // store of whatever the lanes accepted; the warp leaves the loop together.
+    int s = live ? 2 : L + 1;
     uint32_t trial = 0;
     if (FOLD && a.strict_counts[0] == a.strict_counts[1]) {
         // rows are strictly increasing (no duplicate edges): the folded envelope is exact
         const uint64_t fthr_any = min(a.fthr1, a.fthr2), fthr_top = max(a.fthr1, a.fthr2);
         uint32_t thr_extra = 0;  // P(point lands in the extra bar) for the current v, scaled by 2^32
         bool have_extra = false;
-        while (s <= L) {
-            if (!have_extra) {
-                const double area = (double)(ve - vb) * a.fold_env + a.fold_excess;
-                thr_extra = (uint32_t)fmin(a.fold_excess / area * 4294967296.0, 4294967295.0);
-                have_extra = true;
-            }
-            rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
-            int64_t x;
-            bool accept;
-            if (ve <= vb) {  // no out-edge: the walk stays on v (rw_cuda.cu:25-30), nothing to sample
-                x = v;
-                accept = true;
-            } else if (rnd.z < thr_extra) {
-                x = t;
-                accept = is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
-            } else {
-                x = pick_neighbor(a, v, vb, ve, rnd.x, rnd.w, pol_stream);
-                const uint32_t u = rnd.y;
-                if (x == t || u < fthr_any) accept = true;
-                else if (u >= fthr_top) accept = false;
-                else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream) ? a.fthr1 : a.fthr2);
-            }
-            if (accept) {
-                o.put(s, x, s == L);
+        while (__any_sync(0xFFFFFFFFu, s <= L)) {
+            bool accept = false;
+            int64_t x = 0;
+            const int s_now = s;
+            if (s <= L) {
+                if (!have_extra) {
+                    const double area = (double)(ve - vb) * a.fold_env + a.fold_excess;
+                    thr_extra = (uint32_t)fmin(a.fold_excess / area * 4294967296.0, 4294967295.0);
+                    have_extra = true;
+                }
+                rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
                 int64_t xb = 0, xe = 0;
-                if (s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
-                t = v; tb = vb; te = ve;
-                v = x; vb = xb; ve = xe;
-                ++s;
-                trial = 0;
-                have_extra = false;
-            } else {
-                ++trial;
+                if (ve <= vb) {  // no out-edge: the walk stays on v (rw_cuda.cu:25-30), nothing to sample
+                    x = v; xb = vb; xe = ve;
+                    accept = true;
+                } else if (rnd.z < thr_extra) {
+                    x = t; xb = tb; xe = te;
+                    accept = is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
+                } else {
+                    x = propose<REC>(a, v, vb, ve, rnd.x, rnd.w, pol_stream, xb, xe);
+                    const uint32_t u = rnd.y;
+                    if (x == t || u < fthr_any) accept = true;
+                    else if (u >= fthr_top) accept = false;
+                    else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream) ? a.fthr1 : a.fthr2);
+                }
+                if (accept) {
+                    if (!REC && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
+                    t = v; tb = vb; te = ve;
+                    v = x; vb = xb; ve = xe;
+                    ++s;
+                    trial = 0;
+                    have_extra = false;
+                } else {
+                    ++trial;
+                }
             }
+            o.put(accept, s_now, x, s_now == L);
         }
         return;
     }
     const uint64_t thr_any = min(a.thr0, min(a.thr1, a.thr2));  // below this every class accepts
     const uint64_t thr_far = max(a.thr1, a.thr2);               // at or above this only x == t can accept
-    while (s <= L) {
-        uint32_t r, u, r_hi;
-        if ((trial & 1u) == 0u) {
-            rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial >> 1), a.key);
-            r = rnd.x; u = rnd.y; r_hi = rnd.z;
-        } else {
-            r = rnd.z; u = rnd.w; r_hi = rnd.x;
+    while (__any_sync(0xFFFFFFFFu, s <= L)) {
+        bool accept = false;
+        int64_t x = 0;
+        const int s_now = s;
+        if (s <= L) {
+            uint32_t r, u, r_hi;
+            if ((trial & 1u) == 0u) {
+                rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial >> 1), a.key);
+                r = rnd.x; u = rnd.y; r_hi = rnd.z;
+            } else {
+                r = rnd.z; u = rnd.w; r_hi = rnd.x;
+            }
+            int64_t xb = 0, xe = 0;
+            x = propose<REC>(a, v, vb, ve, r, r_hi, pol_stream, xb, xe);
+            const bool back = (x == t);
+            const bool possible = back ? (u < a.thr0) : (u < thr_far);
+            if (!REC && SPECULATE && possible && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
+            if (u < thr_any) accept = true;
+            else if (back) accept = u < a.thr0;
+            else if (!possible) accept = false;
+            else if (a.thr1 == a.thr2) accept = true;  // q == 1: membership cannot change the answer
+            else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream) ? a.thr1 : a.thr2);
+            if (accept) {
+                if (!REC && !SPECULATE && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
+                t = v; tb = vb; te = ve;
+                v = x; vb = xb; ve = xe;
+                ++s;
+                trial = 0;
+            } else {
+                ++trial;
+            }
         }
-        const int64_t x = pick_neighbor(a, v, vb, ve, r, r_hi, pol_stream);
-        const bool back = (x == t);
-        const bool possible = back ? (u < a.thr0) : (u < thr_far);
-        int64_t xb = 0, xe = 0;
-        if (SPECULATE && possible && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
-        bool accept;
-        if (u < thr_any) accept = true;
-        else if (back) accept = u < a.thr0;
-        else if (!possible) accept = false;
-        else if (a.thr1 == a.thr2) accept = true;  // q == 1: membership cannot change the answer
-        else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream) ? a.thr1 : a.thr2);
-        if (accept) {
-            o.put(s, x, s == L);
-            if (!SPECULATE && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
-            t = v; tb = vb; te = ve;
-            v = x; vb = xb; ve = xe;
-            ++s;
-            trial = 0;
-        } else {
-            ++trial;
-        }
+        o.put(accept, s_now, x, s_now == L);
     }
 }
 
 // ------------------------------------------------------------------------------------------ launchers
-template <bool STAGE, bool ROW32>
+// Shared memory and L1 share one 256 KB array per SM, and the L1 side is where the in-flight
+// gathers land.  Measured on the benchmark graph (profiles/r01_summary.md): the first-order kernel
+// is fastest with 768 resident threads per SM and loses 40 % when its staging rings are allowed to
+// take 209 KB (six CTAs), so its carve-out is pinned to three CTAs' worth of rings.  The node2vec
+// kernel is flat between 768 and 1280 threads and keeps the driver's choice.
+constexpr int kUniformCarveoutKb = 132;
+
+template <typename K>
+static void set_carveout(K kernel, int64_t kb) {
+    int pct = kb <= 0 ? (int)cudaSharedmemCarveoutDefault : (int)((kb * 100 + 227) / 228);
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+#define TRW_LAUNCH(kernel, carveout_kb, grid, block, st, args)                                              \
+    do {                                                                                                    \
+        set_carveout(kernel, options().smem_carveout_kb > 0 ? options().smem_carveout_kb : (carveout_kb));  \
+        kernel<<<grid, block, 0, st>>>(args);                                                               \
+    } while (0)
+
+template <bool STAGE, bool ROW32, bool REC>
 static void launch_uniform(const WalkArgs& a, cudaStream_t st) {
     constexpr int BLOCK = 256;
     const unsigned grid = (unsigned)((a.n_walks + BLOCK - 1) / BLOCK);
-    uniform_walk_kernel<BLOCK, STAGE, ROW32><<<grid, BLOCK, 0, st>>>(a);
+    TRW_LAUNCH((uniform_walk_kernel<BLOCK, STAGE, ROW32, REC>), STAGE ? kUniformCarveoutKb : 0, grid, BLOCK, st, a);
 }
 
-template <int MIN_CTAS, bool STAGE, bool TABLE, bool ROW32>
+template <int MIN_CTAS, bool STAGE, bool TABLE, bool ROW32, bool REC>
 static void launch_n2v3(const WalkArgs& a, bool speculate, bool fold, cudaStream_t st) {
     constexpr int BLOCK = 256;
     const unsigned grid = (unsigned)((a.n_walks + BLOCK - 1) / BLOCK);
-    if (fold) node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, true><<<grid, BLOCK, 0, st>>>(a);
-    else if (speculate) node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, true, ROW32, false><<<grid, BLOCK, 0, st>>>(a);
-    else node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, false><<<grid, BLOCK, 0, st>>>(a);
+    if (fold) TRW_LAUNCH((node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, true, REC>), 0, grid, BLOCK, st, a);
+    else if (speculate && !REC) TRW_LAUNCH((node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, true, ROW32, false, false>), 0, grid, BLOCK, st, a);
+    else TRW_LAUNCH((node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, false, REC>), 0, grid, BLOCK, st, a);
 }
 
-template <bool STAGE, bool TABLE, bool ROW32>
+template <bool STAGE, bool TABLE, bool ROW32, bool REC>
 static void launch_n2v2(const WalkArgs& a, bool speculate, bool fold, int min_ctas, cudaStream_t st) {
-    if (min_ctas >= 6) launch_n2v3<6, STAGE, TABLE, ROW32>(a, speculate, fold, st);
-    else if (min_ctas == 5) launch_n2v3<5, STAGE, TABLE, ROW32>(a, speculate, fold, st);
-    else launch_n2v3<4, STAGE, TABLE, ROW32>(a, speculate, fold, st);
+    if (min_ctas >= 6) launch_n2v3<6, STAGE, TABLE, ROW32, REC>(a, speculate, fold, st);
+    else if (min_ctas == 5) launch_n2v3<5, STAGE, TABLE, ROW32, REC>(a, speculate, fold, st);
+    else launch_n2v3<4, STAGE, TABLE, ROW32, REC>(a, speculate, fold, st);
 }
 
-static void launch_n2v(const WalkArgs& a, bool stage, bool table, bool row32, bool speculate, bool fold, int min_ctas,
-                       cudaStream_t st) {
+static void launch_n2v(const WalkArgs& a, bool stage, bool table, bool row32, bool rec, bool speculate, bool fold,
+                       int min_ctas, cudaStream_t st) {
     if (!stage) {  // plain 8-byte stores: A/B path only, kept to one variant per table mode
-        if (table) launch_n2v3<4, false, true, false>(a, speculate, fold, st);
-        else launch_n2v3<4, false, false, false>(a, speculate, fold, st);
+        if (table) launch_n2v3<4, false, true, false, false>(a, speculate, fold, st);
+        else launch_n2v3<4, false, false, false, false>(a, speculate, fold, st);
+        return;
+    }
+    if (rec) {  // edge records imply the uint32 row index (used for the start nodes only)
+        if (table) launch_n2v2<true, true, true, true>(a, speculate, fold, min_ctas, st);
+        else launch_n2v2<true, false, true, true>(a, speculate, fold, min_ctas, st);
         return;
     }
     if (table) {
-        if (row32) launch_n2v2<true, true, true>(a, speculate, fold, min_ctas, st);
-        else launch_n2v2<true, true, false>(a, speculate, fold, min_ctas, st);
+        if (row32) launch_n2v2<true, true, true, false>(a, speculate, fold, min_ctas, st);
+        else launch_n2v2<true, true, false, false>(a, speculate, fold, min_ctas, st);
     } else {
-        if (row32) launch_n2v2<true, false, true>(a, speculate, fold, min_ctas, st);
-        else launch_n2v2<true, false, false>(a, speculate, fold, min_ctas, st);
+        if (row32) launch_n2v2<true, false, true, false>(a, speculate, fold, min_ctas, st);
+        else launch_n2v2<true, false, false, false>(a, speculate, fold, min_ctas, st);
     }
 }
 
@@ -284,73 +344,92 @@ static void set_row_window(cudaStream_t st, const void* base, size_t bytes, int 
     cudaGetLastError();
 }
 
-// Validates the graph-side arguments, derives the acceptance thresholds, re-encodes row_ptr and
-// (node2vec only) builds the membership table into `workspace`.  After this the plan can launch
-// any number of shards of start nodes (trw_walk_csr launches one; trw_walk_csr_host one per chunk).
-int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
-                     double p, double q, int walk_length, int64_t seed, void* workspace, size_t workspace_bytes,
-                     int device, cudaStream_t st) {
-    if (n_nodes < 0 || nnz < 0 || walk_length < 0) { set_error("trw_walk_csr: negative size"); return TRW_ERR_ARG; }
-    if (!(p > 0.0) || !(q > 0.0)) { set_error("trw_walk_csr: p and q must be positive"); return TRW_ERR_ARG; }
+// ------------------------------------------------------------------------------------------ graph side
+// Everything the walk derives from the graph alone: the uint32 row index, the membership table,
+// the strict-rows counters and the edge records, built into `workspace` (csr_workspace_layout with
+// the same `uniform` and `want_records`).  Independent of p, q, the seed and the start nodes, so one
+// prepared graph serves any number of walk calls (trw_csr_graph_* keeps it across calls;
+// trw_walk_csr builds it per call).
+int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                      bool uniform, bool want_table, bool want_strict, bool want_records, void* workspace,
+                      size_t workspace_bytes, int device, cudaStream_t st) {
+    if (n_nodes < 0 || nnz < 0) { set_error("trw_walk_csr: negative size"); return TRW_ERR_ARG; }
     if (!row_ptr || (nnz > 0 && !col_idx)) { set_error("trw_walk_csr: null pointer"); return TRW_ERR_ARG; }
     const Options& opt = options();
+    *g = CsrGraph{};
+    g->row_ptr = row_ptr; g->col_idx = col_idx; g->n_nodes = n_nodes; g->nnz = nnz; g->device = device;
+    if (workspace == nullptr) return TRW_OK;  // reference-style path: int64 row_ptr, linear-scan membership
+    const CsrWorkspace w = csr_workspace_layout(n_nodes, nnz, uniform, want_records);
+    if (w.total == 0) return TRW_OK;
+    if (workspace_bytes < w.total || ((uintptr_t)workspace & 255)) {
+        set_error("trw_walk_csr: workspace needs %zu bytes at 256-byte alignment (got %zu)", w.total, workspace_bytes);
+        return TRW_ERR_WORKSPACE;
+    }
+    timing_begin(0, st);
+    const int rc = csr_prepare_device(row_ptr, col_idx, n_nodes, nnz, workspace, w, want_table && opt.n2v_table != 0,
+                                      opt.row32 != 0, want_strict, want_records && opt.stage_output != 0,
+                                      (int)opt.build_mode, device, st, &g->prepared);
+    timing_end(0, st);
+    return rc;
+}
+
+// Walk-side parameters on top of a prepared graph: the acceptance thresholds of (p, q), the
+// Philox key, and which kernel variant what the graph holds allows.
+int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int walk_length, int64_t seed) {
+    if (walk_length < 0) { set_error("trw_walk_csr: negative walk_length"); return TRW_ERR_ARG; }
+    if (!(p > 0.0) || !(q > 0.0)) { set_error("trw_walk_csr: p and q must be positive"); return TRW_ERR_ARG; }
+    const Options& opt = options();
     WalkArgs& a = plan->a;
-    a.row_ptr = row_ptr; a.col_idx = col_idx; a.n_nodes = n_nodes; a.nnz = nnz;
-    a.targets = nullptr; a.n_walks = 0; a.walk_id_offset = 0;
+    a = WalkArgs{};
+    a.row_ptr = g.row_ptr; a.col_idx = g.col_idx; a.n_nodes = g.n_nodes; a.nnz = g.nnz;
     a.walk_length = walk_length; a.key = philox_key(seed, kTagWalkCsr);
-    a.out = nullptr; a.out_row_stride = 0; a.table = nullptr; a.table_failed = nullptr; a.row32 = nullptr;
-    a.thr0 = a.thr1 = a.thr2 = 0;
     a.store_mode = (int)opt.store_mode;
-    a.fthr1 = a.fthr2 = 0; a.fold_env = a.fold_excess = 0.0; a.strict_counts = nullptr;
-    plan->fold = false;
-    plan->device = device;
+    a.table = g.prepared.table;
+    a.table_failed = g.prepared.table_failed;
+    a.row32 = g.prepared.row32;
+    a.records = g.prepared.records;
+    a.strict_counts = g.prepared.strict_counts;
+    plan->device = g.device;
     plan->uniform = (p == 1.0 && q == 1.0);  // rw_cuda.cu:226
-    plan->table = false;
     plan->stage = opt.stage_output != 0;
     plan->persist = opt.persist_row_ptr != 0;
     plan->min_ctas = (int)opt.n2v_min_ctas;
     plan->speculate = false;
+    plan->fold = false;
+    plan->table = false;
     if (!plan->uniform) {
         const double mx = fmax(fmax(1.0 / p, 1.0), 1.0 / q);  // rw_cuda.cu:119-123
         const double p0 = 1.0 / p / mx, p1 = 1.0 / mx, p2 = 1.0 / q / mx;
         a.thr0 = threshold(p0); a.thr1 = threshold(p1); a.thr2 = threshold(p2);
         // Fetch row_ptr[x] before the verdict only when most proposals are accepted anyway.
         plan->speculate = opt.n2v_speculate < 0 ? (fmin(p1, p2) >= 0.5) : (opt.n2v_speculate != 0);
-        // Return-edge folding applies when 1/p is the strict maximum of the three weights.
+        // Return-edge folding applies when 1/p is the strict maximum of the three weights and the
+        // graph side has verified (strict_counts) that no edge is stored twice.
         const double env = fmax(1.0, 1.0 / q);
-        if (opt.n2v_fold != 0 && 1.0 / p > env) {
+        if (opt.n2v_fold != 0 && 1.0 / p > env && a.strict_counts != nullptr) {
             plan->fold = true;
             a.fold_env = env;
             a.fold_excess = 1.0 / p - env;
             a.fthr1 = threshold(1.0 / env);
             a.fthr2 = threshold(1.0 / q / env);
         }
+        plan->table = a.table != nullptr && a.thr1 != a.thr2;
+        if (!plan->table) a.table = nullptr;
     }
-    if (workspace == nullptr) {  // reference-style path: int64 row_ptr, linear-scan membership, plain rejection
-        plan->fold = false;
-        return TRW_OK;
-    }
-    const CsrWorkspace w = csr_workspace_layout(n_nodes, nnz, plan->uniform);
-    if (w.total == 0) return TRW_OK;
-    if (workspace_bytes < w.total || ((uintptr_t)workspace & 255)) {
-        set_error("trw_walk_csr: workspace needs %zu bytes at 256-byte alignment (got %zu)", w.total, workspace_bytes);
-        return TRW_ERR_WORKSPACE;
-    }
-    const bool want_table = !plan->uniform && opt.n2v_table != 0 && a.thr1 != a.thr2;
-    const bool want_row32 = opt.row32 != 0;
-    CsrPrepared prepared;
-    timing_begin(0, st);
-    const int rc = csr_prepare_device(row_ptr, col_idx, n_nodes, nnz, workspace, w, want_table, want_row32, plan->fold,
-                                      (int)opt.build_mode, device, st, &prepared);
-    timing_end(0, st);
-    if (rc) return rc;
-    a.table = prepared.table;
-    a.table_failed = prepared.table_failed;
-    a.row32 = prepared.row32;
-    a.strict_counts = prepared.strict_counts;
-    plan->table = prepared.table != nullptr;
-    plan->fold = plan->fold && prepared.strict_counts != nullptr;
     return TRW_OK;
+}
+
+// What a one-shot call builds for (p, q): the table only when membership can change a verdict,
+// the strict-rows check only when folding applies, the records only when the walk is long enough
+// to pay for them (one extra pass over col_idx per call; a kept graph always has them).
+void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int walk_length, bool* uniform,
+                        bool* want_table, bool* want_strict, bool* want_records) {
+    const Options& opt = options();
+    *uniform = (p == 1.0 && q == 1.0);
+    *want_table = !*uniform && q != 1.0;  // thr1 == thr2 iff q == 1
+    *want_strict = !*uniform && opt.n2v_fold != 0 && 1.0 / p > fmax(1.0, 1.0 / q);
+    const double steps = (double)n_walks * (double)walk_length;
+    *want_records = opt.records > 0 || (opt.records < 0 && steps >= 3.0 * (double)nnz);
 }
 
 int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
@@ -361,17 +440,19 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
     a.out = out; a.out_row_stride = out_row_stride;
     const bool stage = plan.stage && (((uintptr_t)out & 7) == 0);
     const bool row32 = a.row32 != nullptr;
+    const bool rec = a.records != nullptr && row32 && stage;
     if (plan.persist) {
         if (row32) set_row_window(st, a.row32, (size_t)(a.n_nodes + 1) * 4, plan.device, true);
         else set_row_window(st, a.row_ptr, (size_t)(a.n_nodes + 1) * 8, plan.device, true);
     }
     timing_begin(1, st);
     if (plan.uniform) {
-        if (!stage) launch_uniform<false, false>(a, st);
-        else if (row32) launch_uniform<true, true>(a, st);
-        else launch_uniform<true, false>(a, st);
+        if (!stage) launch_uniform<false, false, false>(a, st);
+        else if (rec) launch_uniform<true, true, true>(a, st);
+        else if (row32) launch_uniform<true, true, false>(a, st);
+        else launch_uniform<true, false, false>(a, st);
     } else {
-        launch_n2v(a, stage, plan.table, row32 && stage, plan.speculate, plan.fold, plan.min_ctas, st);
+        launch_n2v(a, stage, plan.table, row32 && stage, rec, plan.speculate, plan.fold, plan.min_ctas, st);
     }
     timing_end(1, st);
     count_launch(1);
@@ -384,28 +465,104 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
 
 using namespace trw;
 
+// Opaque handle of the C ABI: a prepared graph plus the flags it was built with.
+struct trw_csr_graph {
+    CsrGraph g;
+};
+
 extern "C" size_t trw_walk_csr_workspace_bytes(int64_t n_nodes, int64_t nnz, double p, double q) {
     if (n_nodes < 0 || nnz < 0) return 0;
-    return csr_workspace_layout(n_nodes, nnz, p == 1.0 && q == 1.0).total;
+    // sized for the larger of the two one-shot layouts (with records), so the auto rule never outgrows it
+    return csr_workspace_layout(n_nodes, nnz, p == 1.0 && q == 1.0, options().records != 0).total;
+}
+
+extern "C" size_t trw_walk_csr_workspace_bytes_for(int64_t n_nodes, int64_t nnz, double p, double q, int64_t n_walks,
+                                                   int walk_length) {
+    if (n_nodes < 0 || nnz < 0 || n_walks < 0 || walk_length < 0) return 0;
+    bool uniform, want_table, want_strict, want_records;
+    csr_one_shot_needs(p, q, nnz, n_walks, walk_length, &uniform, &want_table, &want_strict, &want_records);
+    return csr_workspace_layout(n_nodes, nnz, uniform, want_records).total;
+}
+
+static int walk_args_check(const char* fn, const int64_t* targets, int64_t n_walks, int walk_length, int64_t* out,
+                           int64_t out_row_stride) {
+    if (n_walks < 0 || walk_length < 0 || out_row_stride < (int64_t)walk_length + 1) {
+        set_error("%s: negative size or out_row_stride < walk_length+1", fn);
+        return TRW_ERR_ARG;
+    }
+    if (n_walks > 0 && (!targets || !out)) { set_error("%s: null pointer", fn); return TRW_ERR_ARG; }
+    return TRW_OK;
 }
 
 extern "C" int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                             const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, double p, double q,
                             int walk_length, int64_t seed, int64_t* out, int64_t out_row_stride, void* workspace,
                             size_t workspace_bytes, int device, void* stream) {
-    if (n_walks < 0 || walk_length < 0 || out_row_stride < (int64_t)walk_length + 1) {
-        set_error("trw_walk_csr: negative size or out_row_stride < walk_length+1");
-        return TRW_ERR_ARG;
-    }
-    if (n_walks > 0 && (!targets || !out)) { set_error("trw_walk_csr: null pointer"); return TRW_ERR_ARG; }
+    int rc = walk_args_check("trw_walk_csr", targets, n_walks, walk_length, out, out_row_stride);
+    if (rc) return rc;
     const int d = resolve_device(device);
     if (d < 0) return TRW_ERR_DEVICE;
     if (n_walks == 0) return TRW_OK;
     DeviceGuard guard(d);
     if (!guard.ok) { set_error("trw_walk_csr: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (!(p > 0.0) || !(q > 0.0)) { set_error("trw_walk_csr: p and q must be positive"); return TRW_ERR_ARG; }
+    bool uniform, want_table, want_strict, want_records;
+    csr_one_shot_needs(p, q, nnz, n_walks, walk_length, &uniform, &want_table, &want_strict, &want_records);
+    // the records are dropped rather than refused when the caller sized the workspace without them
+    if (want_records && workspace && workspace_bytes < csr_workspace_layout(n_nodes, nnz, uniform, true).total)
+        want_records = false;
+    CsrGraph g;
+    rc = csr_graph_prepare(&g, row_ptr, col_idx, n_nodes, nnz, uniform, want_table, want_strict, want_records, workspace,
+                           workspace_bytes, d, st);
+    if (rc) return rc;
     CsrWalkPlan plan;
-    int rc = csr_walk_prepare(&plan, row_ptr, col_idx, n_nodes, nnz, p, q, walk_length, seed, workspace, workspace_bytes, d, st);
+    rc = csr_walk_plan(&plan, g, p, q, walk_length, seed);
     if (rc) return rc;
     return csr_walk_launch(plan, targets, n_walks, walk_id_offset, out, out_row_stride, st);
 }
+
+extern "C" size_t trw_csr_graph_workspace_bytes(int64_t n_nodes, int64_t nnz) {
+    if (n_nodes < 0 || nnz < 0) return 0;
+    return csr_workspace_layout(n_nodes, nnz, false, options().records != 0).total;
+}
+
+extern "C" int trw_csr_graph_prepare(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                                     void* workspace, size_t workspace_bytes, int device, void* stream,
+                                     trw_csr_graph** out_graph) {
+    if (!out_graph) { set_error("trw_csr_graph_prepare: null out_graph"); return TRW_ERR_ARG; }
+    *out_graph = nullptr;
+    const int d = resolve_device(device);
+    if (d < 0) return TRW_ERR_DEVICE;
+    DeviceGuard guard(d);
+    if (!guard.ok) { set_error("trw_csr_graph_prepare: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }
+    if (n_nodes > 0 && nnz > 0 && workspace == nullptr) {
+        set_error("trw_csr_graph_prepare: a prepared graph needs its workspace (trw_csr_graph_workspace_bytes)");
+        return TRW_ERR_WORKSPACE;
+    }
+    trw_csr_graph* h = new (std::nothrow) trw_csr_graph();
+    if (!h) { set_error("trw_csr_graph_prepare: out of host memory"); return TRW_ERR_ARG; }
+    const int rc = csr_graph_prepare(&h->g, row_ptr, col_idx, n_nodes, nnz, /*uniform=*/false, /*want_table=*/true,
+                                     /*want_strict=*/true, /*want_records=*/options().records != 0, workspace,
+                                     workspace_bytes, d, (cudaStream_t)stream);
+    if (rc) { delete h; return rc; }
+    *out_graph = h;
+    return TRW_OK;
+}
+
+extern "C" int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* targets, int64_t n_walks,
+                                     int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
+                                     int64_t* out, int64_t out_row_stride, void* stream) {
+    if (!graph) { set_error("trw_walk_csr_prepared: null graph"); return TRW_ERR_ARG; }
+    int rc = walk_args_check("trw_walk_csr_prepared", targets, n_walks, walk_length, out, out_row_stride);
+    if (rc) return rc;
+    if (n_walks == 0) return TRW_OK;
+    DeviceGuard guard(graph->g.device);
+    if (!guard.ok) { set_error("trw_walk_csr_prepared: cudaSetDevice(%d) failed", graph->g.device); return TRW_ERR_DEVICE; }
+    CsrWalkPlan plan;
+    rc = csr_walk_plan(&plan, graph->g, p, q, walk_length, seed);
+    if (rc) return rc;
+    return csr_walk_launch(plan, targets, n_walks, walk_id_offset, out, out_row_stride, (cudaStream_t)stream);
+}
+
+extern "C" void trw_csr_graph_destroy(trw_csr_graph* graph) { delete graph; }

@@ -1,5 +1,6 @@
 // Internal interface of the CSR walk (shared by trw_walk_csr and trw_walk_csr_host).
 #pragma once
+#include "member_table.cuh"
 #include "trw_common.cuh"
 
 namespace trw {
@@ -18,6 +19,7 @@ struct WalkArgs {
     const uint32_t* table;
     const int* table_failed;  // device flag raised by the build when a hub segment overflowed
     const uint32_t* row32;  // uint32 copy of row_ptr (nullptr: read the int64 row_ptr)
+    const uint4* records;   // edge records (member_table.cuh), or nullptr
     uint64_t thr0, thr1, thr2;  // acceptance thresholds on a 32-bit uniform, scaled by 2^32
     // return-edge folding (see node2vec_walk_kernel): envelope M', excess 1/p - M', thresholds 1/M', (1/q)/M'
     uint64_t fthr1, fthr2;
@@ -25,16 +27,29 @@ struct WalkArgs {
     const unsigned long long* strict_counts;  // [descents in col_idx, descents at row boundaries]; equal = rows strictly increasing
 };
 
+// A CSR graph as the walk kernels see it: the caller's arrays plus what csr_graph_prepare derived
+// from them into the workspace (all optional: a null member selects the slower generic path).
+struct CsrGraph {
+    const int64_t* row_ptr = nullptr;
+    const int64_t* col_idx = nullptr;
+    int64_t n_nodes = 0, nnz = 0;
+    int device = 0;
+    CsrPrepared prepared;
+};
+
 struct CsrWalkPlan {
-    WalkArgs a;  // graph side filled by csr_walk_prepare; shard side by csr_walk_launch
+    WalkArgs a;  // graph side and (p, q, seed) filled by csr_walk_plan; shard side by csr_walk_launch
     int device;
     int min_ctas;
     bool uniform, table, speculate, stage, persist, fold;
 };
 
-int csr_walk_prepare(CsrWalkPlan* plan, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
-                     double p, double q, int walk_length, int64_t seed, void* workspace, size_t workspace_bytes,
-                     int device, cudaStream_t st);
+int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                      bool uniform, bool want_table, bool want_strict, bool want_records, void* workspace,
+                      size_t workspace_bytes, int device, cudaStream_t st);
+int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int walk_length, int64_t seed);
+void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int walk_length, bool* uniform,
+                        bool* want_table, bool* want_strict, bool* want_records);
 int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
                     int64_t* out, int64_t out_row_stride, cudaStream_t st);
 

@@ -88,7 +88,10 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
 
     const int64_t row_len = (int64_t)walk_length + 1;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(options().host_chunk_walks, n_walks));
-    const size_t ws_bytes = trw_walk_csr_workspace_bytes(n_nodes, nnz, p, q);
+    if (!(p > 0.0) || !(q > 0.0)) { set_error("trw_walk_csr_host: p and q must be positive"); return TRW_ERR_ARG; }
+    bool uniform, want_table, want_strict, want_records;
+    csr_one_shot_needs(p, q, nnz, n_walks, walk_length, &uniform, &want_table, &want_strict, &want_records);
+    const size_t ws_bytes = csr_workspace_layout(n_nodes, nnz, uniform, want_records).total;
 
     // TRW_HOST_TIMING=1 prints where an end-to-end call spends its time (adds one stream sync after the uploads).
     const bool timing = getenv("TRW_HOST_TIMING") != nullptr;
@@ -139,9 +142,12 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         ms_upload = ms_since(t_up);
     }
     const auto t_walk = now();
+    CsrGraph graph;
+    rc = csr_graph_prepare(&graph, (const int64_t*)d_row_ptr, (const int64_t*)d_col_idx, n_nodes, nnz, uniform, want_table,
+                           want_strict, want_records, d_workspace, ws_bytes, d, r.compute);
+    if (rc) return rc;
     CsrWalkPlan plan;
-    rc = csr_walk_prepare(&plan, (const int64_t*)d_row_ptr, (const int64_t*)d_col_idx, n_nodes, nnz, p, q,
-                              walk_length, seed, d_workspace, ws_bytes, d, r.compute);
+    rc = csr_walk_plan(&plan, graph, p, q, walk_length, seed);
     if (rc) return rc;
 
     int64_t done = 0;

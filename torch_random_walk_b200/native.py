@@ -10,6 +10,7 @@ import of this module.
 """
 import ctypes
 import os
+import weakref
 
 import torch
 
@@ -36,6 +37,16 @@ def _load():
     lib.trw_set_option.argtypes = [ctypes.c_char_p, _c_i64]
     lib.trw_walk_csr_workspace_bytes.restype = _c_size
     lib.trw_walk_csr_workspace_bytes.argtypes = [_c_i64, _c_i64, _c_dbl, _c_dbl]
+    lib.trw_walk_csr_workspace_bytes_for.restype = _c_size
+    lib.trw_walk_csr_workspace_bytes_for.argtypes = [_c_i64, _c_i64, _c_dbl, _c_dbl, _c_i64, _c_int]
+    lib.trw_csr_graph_workspace_bytes.restype = _c_size
+    lib.trw_csr_graph_workspace_bytes.argtypes = [_c_i64, _c_i64]
+    lib.trw_csr_graph_prepare.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr,
+                                          ctypes.POINTER(_c_ptr)]
+    lib.trw_walk_csr_prepared.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_i64,
+                                          _c_ptr]
+    lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
+    lib.trw_csr_graph_destroy.restype = None
     lib.trw_walk_csr.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
                                  _c_i64, _c_ptr, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr]
     lib.trw_walk_csr_host.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
@@ -52,7 +63,7 @@ def _load():
     lib.trw_windows_triples_cbow.argtypes = wint
     lib.trw_calib_gather.argtypes = [_c_ptr, _c_i64, _c_i64, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_ptr]
     lib.trw_device_check.argtypes = [_c_int]
-    if lib.trw_abi_version() != 1:
+    if lib.trw_abi_version() != 2:
         raise ImportError("libtrw_b200.so ABI version mismatch; rebuild with python -m torch_random_walk_b200._build")
     return lib
 
@@ -113,19 +124,126 @@ def reset_launch_count():
     _lib.trw_reset_launch_count()
 
 
-def walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None):
+class PreparedCsr:
+    """A CSR graph prepared once for any number of walks (trw_csr_graph_prepare): the uint32 row
+    index, the membership table, the duplicate-edge check and the edge records live in a workspace
+    tensor this object owns.  It keeps `row_ptr` / `column_idx` alive; they must not be modified
+    while it is in use.  Walks through it are bit-identical to the one-shot call."""
+
+    def __init__(self, row_ptr, column_idx):
+        _require_cuda(row_ptr, "row_ptr")
+        _require_cuda(column_idx, "column_idx")
+        self.row_ptr, self.column_idx = row_ptr.contiguous(), column_idx.contiguous()
+        self.device = row_ptr.device
+        self.n_nodes, self.nnz = max(self.row_ptr.numel() - 1, 0), self.column_idx.numel()
+        self._handle = _c_ptr()
+        with torch.cuda.device(self.device):
+            need = _lib.trw_csr_graph_workspace_bytes(self.n_nodes, self.nnz)
+            self.workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=self.device)
+            _check(_lib.trw_csr_graph_prepare(_ptr(self.row_ptr), _ptr(self.column_idx), self.n_nodes, self.nnz,
+                                              _ptr(self.workspace) if need else None, need, self.device.index,
+                                              _stream(self.device), ctypes.byref(self._handle)))
+            self._ready = torch.cuda.Event()
+            self._ready.record(torch.cuda.current_stream(self.device))
+            self._stream_id = torch.cuda.current_stream(self.device).cuda_stream
+
+    def walk(self, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None):
+        _require_cuda(target_nodes, "target_nodes")
+        dev = self.device
+        target_nodes = target_nodes.contiguous()
+        n, wl = target_nodes.size(0), int(walk_length) + 1
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            if stream.cuda_stream != self._stream_id:  # prepared on another stream: order after it, tell the allocator
+                stream.wait_event(self._ready)
+                self.workspace.record_stream(stream)
+            walks = torch.empty((n, wl), dtype=torch.int64, device=dev) if out is None else out
+            _check(_lib.trw_walk_csr_prepared(self._handle, _ptr(target_nodes), n, int(walk_id_offset), float(p), float(q),
+                                              int(walk_length), int(seed), _ptr(walks), walks.stride(0) if n else wl,
+                                              _stream(dev)))
+        return walks
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            _lib.trw_csr_graph_destroy(h)
+
+
+def prepare_csr(row_ptr, column_idx):
+    """Explicit form of what rw.walk's graph cache does: prepare once, then `.walk(...)` many times."""
+    return PreparedCsr(row_ptr, column_idx)
+
+
+# Graph cache of the drop-in `walk`: a user of the reference calls rw.walk(row_ptr, col_idx, ...) once
+# per epoch with the same tensors; the preparation of the graph is the same every time, so the last
+# graph per device is kept.  An entry is valid only for the very same tensor objects (held by weak
+# reference) at the same torch version counters, i.e. not modified in place since.  Writes that bypass
+# torch (raw pointers, other libraries) are not seen: call clear_graph_cache() after those, or switch
+# the cache off (set_graph_cache(False) or TRW_GRAPH_CACHE=0).  The cache holds
+# trw_csr_graph_workspace_bytes (24 bytes per CSR entry) of device memory per cached graph.
+_graph_cache = {}
+_seen_once = {}  # per device: signature of the last one-shot graph (a second call with it prepares the graph for keeps)
+_graph_cache_on = os.environ.get("TRW_GRAPH_CACHE", "1") != "0"
+
+
+def set_graph_cache(enabled):
+    global _graph_cache_on
+    _graph_cache_on = bool(enabled)
+    if not _graph_cache_on:
+        clear_graph_cache()
+
+
+def graph_cache_enabled():
+    return _graph_cache_on
+
+
+def clear_graph_cache():
+    _graph_cache.clear()
+    _seen_once.clear()
+
+
+def _cached_graph(row_ptr, column_idx, create):
+    key = row_ptr.device.index
+    sig = (row_ptr.data_ptr(), row_ptr._version, row_ptr.numel(), column_idx.data_ptr(), column_idx._version,
+           column_idx.numel())
+    hit = _graph_cache.get(key)
+    if hit is not None:
+        rp_ref, ci_ref, old_sig, graph = hit
+        if rp_ref() is row_ptr and ci_ref() is column_idx and old_sig == sig:
+            return graph
+        del _graph_cache[key]  # frees the old workspace before the new one is allocated
+    if not create:
+        return None
+    graph = PreparedCsr(row_ptr, column_idx)
+    _graph_cache[key] = (weakref.ref(row_ptr), weakref.ref(column_idx), sig, graph)
+    return graph
+
+
+def walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None, cache=None):
     """csrc/rw_init.cpp:11-25 -> csrc/cuda/rw_cuda.cu:186-248.  Returns walks[n, walk_length+1] on
-    row_ptr's device.  `walk_id_offset` / `out` are extensions for sharded callers."""
+    row_ptr's device.  `walk_id_offset` / `out` are extensions for sharded callers; `cache` overrides
+    the graph cache for this call (None: the module setting).  The first call on a graph is one-shot
+    (everything built per call, like the reference's stateless launcher); the second call with the
+    same tensors prepares the graph for keeps, and later calls are the walk kernel alone.  Cached and
+    one-shot calls return identical walks."""
     _require_cuda(row_ptr, "row_ptr")
     _require_cuda(column_idx, "column_idx")
     _require_cuda(target_nodes, "target_nodes")
     dev = row_ptr.device
+    use_cache = _graph_cache_on if cache is None else bool(cache)
+    n_nodes, nnz = max(row_ptr.numel() - 1, 0), column_idx.numel()
+    if use_cache and row_ptr.is_contiguous() and column_idx.is_contiguous() and nnz > 0 and target_nodes.size(0) > 0:
+        seen = _seen_once.get(dev.index)
+        sig = (row_ptr.data_ptr(), row_ptr._version, column_idx.data_ptr(), column_idx._version)
+        graph = _cached_graph(row_ptr, column_idx, create=(seen == sig))
+        if graph is not None:
+            return graph.walk(target_nodes, p, q, walk_length, seed, walk_id_offset=walk_id_offset, out=out)
+        _seen_once[dev.index] = sig
     row_ptr, column_idx, target_nodes = row_ptr.contiguous(), column_idx.contiguous(), target_nodes.contiguous()
     n, wl = target_nodes.size(0), int(walk_length) + 1
-    n_nodes, nnz = max(row_ptr.numel() - 1, 0), column_idx.numel()
     with torch.cuda.device(dev):
         walks = torch.empty((n, wl), dtype=torch.int64, device=dev) if out is None else out
-        need = _lib.trw_walk_csr_workspace_bytes(n_nodes, nnz, float(p), float(q)) if n else 0
+        need = _lib.trw_walk_csr_workspace_bytes_for(n_nodes, nnz, float(p), float(q), n, int(walk_length)) if n else 0
         ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
         _check(_lib.trw_walk_csr(_ptr(row_ptr), _ptr(column_idx), n_nodes, nnz, _ptr(target_nodes), n,
                                  int(walk_id_offset), float(p), float(q), int(walk_length), int(seed), _ptr(walks),
