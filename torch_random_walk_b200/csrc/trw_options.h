@@ -10,7 +10,7 @@ struct Options {
     int64_t n2v_table = 1;        // 1: hashed adjacency membership (needs workspace); 0: linear scan of adj(t)
     int64_t n2v_speculate = -1;   // fetch row_ptr[x] before the membership answer is known: 1 yes, 0 no, -1 by (p,q)
     int64_t n2v_fold = 1;         // 1: fold the return edge out of the rejection envelope when 1/p > max(1, 1/q)
-    int64_t n2v_min_ctas = 5;     // __launch_bounds__ min CTAs/SM of the node2vec kernel (4, 5 or 6)
+    int64_t n2v_min_ctas = -1;    // __launch_bounds__ min CTAs/SM of the node2vec kernel (4, 5 or 6; -1: 5 with edge records, else 4)
     int64_t row32 = 1;            // 1: re-encode row_ptr as uint32 offsets per call (needs workspace)
     int64_t records = -1;         // 16-byte edge records (neighbour id + its row span; the walk then needs no row-index loads): 1 always, 0 never,
                                   // -1 kept graphs always, one-shot calls when n_walks * walk_length >= 3 * nnz (they cost one pass over col_idx)

@@ -250,14 +250,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
 // ------------------------------------------------------------------------------------------ launchers
 // Shared memory and L1 share one 256 KB array per SM, and the L1 side is where the in-flight
 // gathers land.  Measured on the benchmark graph (profiles/r01_summary.md): the first-order kernel
-// is fastest with 768 resident threads per SM and loses 40 % when its staging rings are allowed to
-// take 209 KB (six CTAs), so its carve-out is pinned to three CTAs' worth of rings.  The node2vec
-// kernel is flat between 768 and 1280 threads and keeps the driver's choice.
-constexpr int kUniformCarveoutKb = 132;
+// is fastest with four resident CTAs (1024 threads, 164 KB configuration) and loses 40 % when its
+// staging rings are allowed to take 209 KB (six CTAs, 28 KB of L1 left), so its carve-out is pinned.
+// The node2vec kernel is flat between 768 and 1280 threads and keeps the driver's choice.
+constexpr int kUniformCarveoutKb = 164;
 
 template <typename K>
 static void set_carveout(K kernel, int64_t kb) {
-    int pct = kb <= 0 ? (int)cudaSharedmemCarveoutDefault : (int)((kb * 100 + 227) / 228);
+    int pct = kb <= 0 ? (int)cudaSharedmemCarveoutDefault : (int)(kb * 100 / 228);  // rounded down: the driver rounds up to a configuration
     if (pct > 100) pct = 100;
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
@@ -393,7 +393,8 @@ int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int 
     plan->uniform = (p == 1.0 && q == 1.0);  // rw_cuda.cu:226
     plan->stage = opt.stage_output != 0;
     plan->persist = opt.persist_row_ptr != 0;
-    plan->min_ctas = (int)opt.n2v_min_ctas;
+    // measured on the benchmark graphs: 5 CTAs/SM with edge records, 4 without (the row lookups like a larger L1)
+    plan->min_ctas = opt.n2v_min_ctas > 0 ? (int)opt.n2v_min_ctas : (a.records != nullptr ? 5 : 4);
     plan->speculate = false;
     plan->fold = false;
     plan->table = false;

@@ -137,6 +137,7 @@ class PreparedCsr:
         self.device = row_ptr.device
         self.n_nodes, self.nnz = max(self.row_ptr.numel() - 1, 0), self.column_idx.numel()
         self._handle = _c_ptr()
+        self._destroy = _lib.trw_csr_graph_destroy  # bound now: module globals may be gone at interpreter exit
         with torch.cuda.device(self.device):
             need = _lib.trw_csr_graph_workspace_bytes(self.n_nodes, self.nnz)
             self.workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=self.device)
@@ -165,8 +166,9 @@ class PreparedCsr:
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
-        if h:
-            _lib.trw_csr_graph_destroy(h)
+        destroy = getattr(self, "_destroy", None)
+        if h and destroy is not None:
+            destroy(h)
 
 
 def prepare_csr(row_ptr, column_idx):
