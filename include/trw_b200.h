@@ -71,7 +71,7 @@ int trw_device_check(int device);
  * ------------------------------------------------------------------------------------- */
 size_t trw_walk_csr_workspace_bytes(int64_t n_nodes, int64_t nnz, double p, double q);
 /* The exact size this call shape uses: shorter than the bound above when the walk is too short
- * to pay for the per-call edge records (n_walks * walk_length < 3 * nnz). */
+ * to pay for the per-call edge records (about 3 gathered lines per CSR entry). */
 size_t trw_walk_csr_workspace_bytes_for(int64_t n_nodes, int64_t nnz, double p, double q,
                                         int64_t n_walks, int walk_length);
 

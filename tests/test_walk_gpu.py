@@ -229,31 +229,38 @@ def test_unsorted_rows_and_duplicate_edges(native):
         native.set_option("n2v_table", 1)
     assert torch.equal(a, b)
     check_walks_follow_edges(a, rp, ci, nodes)
-    # return-edge folding needs duplicate-free rows: the prepare step must have switched it off here
+    # folding and the mixture need duplicate-free rows: the prepare step must have switched them off here
     native.set_option("n2v_fold", 0)
+    native.set_option("n2v_mix", 0)
     try:
         c = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
     finally:
         native.set_option("n2v_fold", 1)
+        native.set_option("n2v_mix", 1)
     assert torch.equal(a, c)
 
 
 def test_folding_changes_the_draws_not_the_law(native, golden):
-    """With strictly increasing rows and 1/p > max(1, 1/q) the folded envelope is used: other draws,
-    same distribution (the statistical tests below run with it); switching it off restores the
-    plain-rejection stream bit for bit."""
+    """With strictly increasing rows the kernel picks the tightest sampling scheme the law allows:
+    the two-sided mixture (q > 1, p <= q), else return-edge folding (1/p > max(1, 1/q)), else plain
+    rejection.  Other draws, same distribution (the statistical tests below run all three);
+    switching the faster schemes off restores the plain-rejection stream bit for bit."""
     rp, ci = cuda(*random_csr(6, 2000, 20))
     nodes = torch.arange(2000, device="cuda")
-    folded = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
-    native.set_option("n2v_fold", 0)
+    mixed = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+    native.set_option("n2v_mix", 0)
     try:
+        folded = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
+        native.set_option("n2v_fold", 0)
         plain = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
         plain2 = native.walk(rp, ci, nodes, 0.25, 4.0, 30, 5)
     finally:
         native.set_option("n2v_fold", 1)
-    assert torch.equal(plain, plain2) and not torch.equal(folded, plain)
-    check_walks_follow_edges(folded, rp, ci, nodes)
-    check_walks_follow_edges(plain, rp, ci, nodes)
+        native.set_option("n2v_mix", 1)
+    assert torch.equal(plain, plain2)
+    assert not torch.equal(folded, plain) and not torch.equal(mixed, plain) and not torch.equal(mixed, folded)
+    for w in (mixed, folded, plain):
+        check_walks_follow_edges(w, rp, ci, nodes)
     # p >= min(1, q): nothing to fold, the option is inert
     a = native.walk(rp, ci, nodes, 1.0, 0.5, 30, 5)
     native.set_option("n2v_fold", 0)
@@ -343,8 +350,15 @@ def test_first_order_transitions_are_uniform(rw, golden):
     assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
 
 
-@pytest.mark.parametrize("p,q,fold", [(0.5, 2.0, 1), (0.25, 4.0, 1), (1.0, 0.5, 1), (0.25, 4.0, 0), (0.5, 0.25, 1)])
-def test_second_order_statistics_match_analytic_and_oracle(rw, native, orc, golden, p, q, fold):
+# (p, q, options): every sampling scheme of the node2vec kernel -- two-sided mixture (q > 1, p <= q), return-edge
+# folding (1/p the strict maximum), plain rejection -- on the laws that select it, and the slower schemes forced
+# on the same laws by switching the faster ones off.
+SCHEMES = [(0.5, 2.0, {}), (0.25, 4.0, {}), (2.0, 4.0, {}), (0.5, 2.0, {"n2v_mix": 0}), (0.25, 4.0, {"n2v_mix": 0}),
+           (0.25, 4.0, {"n2v_mix": 0, "n2v_fold": 0}), (1.0, 0.5, {}), (0.25, 0.5, {}), (0.5, 0.25, {}), (4.0, 2.0, {})]
+
+
+@pytest.mark.parametrize("p,q,opts", SCHEMES)
+def test_second_order_statistics_match_analytic_and_oracle(rw, native, orc, golden, p, q, opts):
     """North-star criterion: chi-square p > 0.01 and pooled TV < 1e-2 at 1e7 samples, against the
     analytic node2vec probabilities and against the reference algorithm's own empirical counts."""
     rp, ci = T(golden["utils/karate/row_ptr"]), T(golden["utils/karate/col_idx"])
@@ -353,11 +367,13 @@ def test_second_order_statistics_match_analytic_and_oracle(rw, native, orc, gold
     L = 100
     reps = 3000  # 34 * 3000 walks * 99 second-order transitions = 1.0e7 samples
     nodes = torch.arange(n).repeat_interleave(reps)
-    native.set_option("n2v_fold", fold)
+    for k, v in opts.items():
+        native.set_option(k, v)
     try:
         walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, L, 2024)
     finally:
-        native.set_option("n2v_fold", 1)
+        for k in opts:
+            native.set_option(k, 1)
     check_walks_follow_edges(walks, rp, ci, nodes)
     got = second_order_counts(walks, n)
     assert sum(got.values()) >= 10_000_000
@@ -397,18 +413,26 @@ def _class_tv(counts, row_ptr, col_idx, p, q, n):
     return tv_sum / total
 
 
-def test_second_order_statistics_with_table_rows(rw, orc):
+@pytest.mark.parametrize("p,q,opts", [(0.5, 2.0, {}), (0.5, 2.0, {"records": 1}), (0.5, 2.0, {"n2v_mix": 0}), (2.0, 4.0, {}),
+                                      (1.0, 0.5, {"records": 1})])
+def test_second_order_statistics_with_table_rows(rw, native, orc, p, q, opts):
     """Same criterion on a graph whose rows are long enough (>= 12) to go through the hashed
-    membership table, with triangles so that all three acceptance classes occur.  With ~30
+    membership table, with triangles so that all three acceptance classes occur and with rows of
+    different lengths so that the mixture proposes common neighbours from both sides.  With ~30
     outcomes per context the per-neighbour TV at 1e7 samples is dominated by sampling noise
     (~0.02), so the TV bound is applied to the acceptance classes; chi-square stays per neighbour."""
     rp, ci = random_csr(11, 60, 40)
     n = 60
-    assert int((rp[1:] - rp[:-1]).min()) >= 16
-    p, q = 0.5, 2.0
+    assert int((rp[1:] - rp[:-1]).min()) >= 16 and int((rp[1:] - rp[:-1]).max()) > int((rp[1:] - rp[:-1]).min())
     table = node2vec_probs(rp, ci, p, q)
     nodes = torch.arange(n).repeat_interleave(3000)
-    walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, 100, 5)
+    for k, v in opts.items():
+        native.set_option(k, v)
+    try:
+        walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, 100, 5)
+    finally:
+        for k in opts:
+            native.set_option(k, {"records": -1}.get(k, 1))
     got = second_order_counts(walks, n)
     chi2, dof, tv = chi2_and_tv(got, table, n)
     assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)

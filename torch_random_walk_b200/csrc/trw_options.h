@@ -10,10 +10,11 @@ struct Options {
     int64_t n2v_table = 1;        // 1: hashed adjacency membership (needs workspace); 0: linear scan of adj(t)
     int64_t n2v_speculate = -1;   // fetch row_ptr[x] before the membership answer is known: 1 yes, 0 no, -1 by (p,q)
     int64_t n2v_fold = 1;         // 1: fold the return edge out of the rejection envelope when 1/p > max(1, 1/q)
+    int64_t n2v_mix = 1;          // 1: two-sided mixture sampling when q > 1 and p <= q (duplicate-free rows; see node2vec_walk_kernel)
     int64_t n2v_min_ctas = -1;    // __launch_bounds__ min CTAs/SM of the node2vec kernel (4, 5 or 6; -1: 5 with edge records, else 4)
     int64_t row32 = 1;            // 1: re-encode row_ptr as uint32 offsets per call (needs workspace)
     int64_t records = -1;         // 16-byte edge records (neighbour id + its row span; the walk then needs no row-index loads): 1 always, 0 never,
-                                  // -1 kept graphs always, one-shot calls when n_walks * walk_length >= 3 * nnz (they cost one pass over col_idx)
+                                  // -1 kept graphs always, one-shot calls when the walk is long enough to repay one pass over col_idx (csr_one_shot_needs)
     int64_t build_mode = 2;       // table build: 2 assembled in shared memory (tiles + hub segments); 0 global CAS (A/B baseline)
     int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
@@ -29,7 +30,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(n2v_mix) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb)
 
 Options& options();
 void count_launch(int n);

@@ -164,7 +164,74 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
     // store of whatever the lanes accepted; the warp leaves the loop together.
     int s = live ? 2 : L + 1;
     uint32_t trial = 0;
-    if (FOLD && a.strict_counts[0] == a.strict_counts[1]) {
+    if (FOLD && a.mix && a.strict_counts[0] == a.strict_counts[1]) {
+        // Two-sided mixture (q > 1, p <= q; rows without duplicate edges).  With weights scaled so that
+        // a common neighbour weighs 1, every neighbour of v weighs c = 1/q, a common neighbour 1 - c
+        // more and the return edge 1/p - c more:  w = c*[x in adj(v)] + (1-c)*[x in adj(v) & adj(t)] +
+        // (1/p-c)*[x == t].  A trial picks one of the three terms in proportion to an upper bound of
+        // its mass and samples it directly:
+        //   A  c*deg(v):                 a uniform neighbour of v, always accepted (one gather);
+        //   B  (1-c)*min(deg v, deg t):  a uniform entry of the SHORTER of the two rows, accepted iff it
+        //                                is in the other one (gather + probe) -- the common neighbours are
+        //                                proposed from the side where they are dense;
+        //   C  1/p - c:                  t itself, accepted iff t is a neighbour of v (one probe).
+        // Plain rejection spends q trials per step on the far neighbours' low weight; here the envelope
+        // exceeds the true mass only by the misses of B, so a step costs about one gather when deg(t)
+        // is much smaller than deg(v) and never more than plain rejection does.
+        const double c = a.fold_env, back = a.fold_excess;
+        uint32_t thr_a = 0, thr_ab = 0;
+        bool have_thr = false, t_side = false;
+        while (__any_sync(0xFFFFFFFFu, s <= L)) {
+            bool accept = false;
+            int64_t x = 0;
+            const int s_now = s;
+            if (s <= L) {
+                const int64_t dv = ve - vb, dt = te - tb;
+                if (!have_thr) {
+                    const double mass_a = c * (double)dv;
+                    const double mass_b = (1.0 - c) * (double)max((int64_t)0, min(dv, dt));
+                    const double total = mass_a + mass_b + back;
+                    thr_a = (uint32_t)fmin(mass_a / total * 4294967296.0, 4294967295.0);
+                    thr_ab = (uint32_t)fmin((mass_a + mass_b) / total * 4294967296.0, 4294967295.0);
+                    t_side = dt < dv;
+                    have_thr = true;
+                }
+                rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
+                int64_t xb = 0, xe = 0;
+                if (dv <= 0) {  // no out-edge: the walk stays on v (rw_cuda.cu:25-30)
+                    x = v; xb = vb; xe = ve;
+                    accept = true;
+                } else if (rnd.z < thr_a) {
+                    x = propose<REC>(a, v, vb, ve, rnd.x, rnd.w, pol_stream, xb, xe);
+                    accept = true;
+                } else if (rnd.z < thr_ab) {
+                    if (t_side) {
+                        x = propose<REC>(a, t, tb, te, rnd.x, rnd.w, pol_stream, xb, xe);
+                        accept = x != t && is_member<TABLE>(x, vb, ve, a.col_idx, table, pol_stream);
+                    } else {
+                        x = propose<REC>(a, v, vb, ve, rnd.x, rnd.w, pol_stream, xb, xe);
+                        accept = x != t && is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream);
+                    }
+                } else {
+                    x = t; xb = tb; xe = te;
+                    accept = is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
+                }
+                if (accept) {
+                    if (!REC && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
+                    t = v; tb = vb; te = ve;
+                    v = x; vb = xb; ve = xe;
+                    ++s;
+                    trial = 0;
+                    have_thr = false;
+                } else {
+                    ++trial;
+                }
+            }
+            o.put(accept, s_now, x, s_now == L);
+        }
+        return;
+    }
+    if (FOLD && !a.mix && a.strict_counts[0] == a.strict_counts[1]) {
         // rows are strictly increasing (no duplicate edges): the folded envelope is exact
         const uint64_t fthr_any = min(a.fthr1, a.fthr2), fthr_top = max(a.fthr1, a.fthr2);
         uint32_t thr_extra = 0;  // P(point lands in the extra bar) for the current v, scaled by 2^32
@@ -407,7 +474,13 @@ int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int 
         // Return-edge folding applies when 1/p is the strict maximum of the three weights and the
         // graph side has verified (strict_counts) that no edge is stored twice.
         const double env = fmax(1.0, 1.0 / q);
-        if (opt.n2v_fold != 0 && 1.0 / p > env && a.strict_counts != nullptr) {
+        if (opt.n2v_mix != 0 && q > 1.0 && p <= q && a.strict_counts != nullptr) {
+            // two-sided mixture (see node2vec_walk_kernel); it rides on the strict-rows kernel variant
+            plan->fold = true;
+            a.mix = 1;
+            a.fold_env = 1.0 / q;
+            a.fold_excess = 1.0 / p - 1.0 / q;
+        } else if (opt.n2v_fold != 0 && 1.0 / p > env && a.strict_counts != nullptr) {
             plan->fold = true;
             a.fold_env = env;
             a.fold_excess = 1.0 / p - env;
@@ -428,9 +501,13 @@ void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int wa
     const Options& opt = options();
     *uniform = (p == 1.0 && q == 1.0);
     *want_table = !*uniform && q != 1.0;  // thr1 == thr2 iff q == 1
-    *want_strict = !*uniform && opt.n2v_fold != 0 && 1.0 / p > fmax(1.0, 1.0 / q);
-    const double steps = (double)n_walks * (double)walk_length;
-    *want_records = opt.records > 0 || (opt.records < 0 && steps >= 3.0 * (double)nnz);
+    *want_strict = !*uniform && ((opt.n2v_fold != 0 && 1.0 / p > fmax(1.0, 1.0 / q)) || (opt.n2v_mix != 0 && q > 1.0 && p <= q));
+    // Records save about a tenth of the walk's gathers and cost one pass over col_idx: worth building
+    // per call when the walk fetches more than ~3 random lines per CSR entry (measured break-even on
+    // the benchmark graphs; lines per step: 1 first-order, ~1.5 for q <= 1, ~0.85 q + 0.8 for q > 1).
+    const double lines_per_step = *uniform ? 1.0 : (q <= 1.0 ? 1.5 : 0.85 * q + 0.8);
+    const double lines = (double)n_walks * (double)walk_length * lines_per_step;
+    *want_records = opt.records > 0 || (opt.records < 0 && lines >= 3.2 * (double)nnz);
 }
 
 int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
