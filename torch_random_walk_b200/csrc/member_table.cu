@@ -379,6 +379,27 @@ __global__ void __launch_bounds__(256) strict_boundaries_kernel(const int64_t* _
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(counts + 1, n);
 }
 
+// Packed uint32 copies of the rows too short for a hashed table (member_table.cuh).  Runs after the
+// table build, whose whole-bucket writes leave EMPTY over these rows' bytes; a short row's bytes are
+// its own, so nothing of a neighbouring row's table is touched.
+__global__ void __launch_bounds__(256) short_rows_kernel(const int64_t* __restrict__ row_ptr,
+                                                         const int64_t* __restrict__ col_idx, int64_t n_nodes,
+                                                         uint32_t* __restrict__ table) {
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_nodes; r += gsz) {
+        const int64_t b = __ldg(row_ptr + r), e = __ldg(row_ptr + r + 1);
+        const int64_t d = e - b;
+        if (d <= 0 || d >= kMinTableDeg) continue;
+        uint32_t ids[kMinTableDeg];
+#pragma unroll
+        for (int k = 0; k < kMinTableDeg - 1; ++k) ids[k] = k < d ? (uint32_t)ldg64_stream(col_idx + b + k) : kEmpty;
+        uint32_t* words = table + 2 * b;
+#pragma unroll
+        for (int k = 0; k < 2 * (kMinTableDeg - 1); ++k)
+            if (k < 2 * d) words[k] = k < kMinTableDeg - 1 ? ids[k] : kEmpty;
+    }
+}
+
 // Edge records (member_table.cuh): one streaming pass over col_idx; the two row-index reads per
 // entry hit the L2-resident uint32 index (evict_last), the 16-byte records leave coalesced.
 __global__ void __launch_bounds__(256) edge_records_kernel(const int64_t* __restrict__ col_idx, int64_t nnz,
@@ -507,6 +528,8 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
             build_hub_kernel<<<sms, kHubThreads, kHubSmemBytes, st>>>(b);
             count_launch(3);
         }
+        short_rows_kernel<<<sms * 8, 256, 0, st>>>(row_ptr, col_idx, n_nodes, b.table);
+        count_launch(1);
         rc = check_cuda(cudaGetLastError(), "membership table build launch");
         if (rc) return rc;
         out->table = b.table;

@@ -7,7 +7,10 @@
 // that span hold the row's neighbour ids as uint32 (8 slots per bucket, EMPTY = 0xFFFFFFFF), with
 // open addressing over buckets.  No per-row pointer is needed: the bucket range follows from the
 // row span the walk already holds.  A row of degree d >= kMinTableDeg owns nb >= (d-6)/4 buckets,
-// i.e. at least 2d-12 >= d slots; shorter rows are scanned directly (<= 11 ids).
+// i.e. at least 2d-12 >= d slots.  A shorter row keeps a packed uint32 copy of its d ids at the start
+// of its own bytes (words [2b, 2b+d), EMPTY up to 2e): at most six 8-byte loads instead of a scan of
+// the int64 adjacency, whose predicated 64-bit loads and compares were 8 % of the walk kernel's
+// instructions (the kernel is partly issue-bound: profiles/).
 //
 // Probing stays inside a *segment* of the row's buckets: rows with fewer than 2*kSegBuckets
 // buckets are one segment (so the capacity bound above is a guarantee); longer rows (hubs) are cut
@@ -53,7 +56,18 @@ __device__ __forceinline__ void probe_segment(int64_t nb, int64_t home, int64_t&
 template <bool TABLE>
 __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const int64_t* __restrict__ col_idx,
                                           const uint32_t* __restrict__ table, uint64_t pol_stream) {
-    if (TABLE && table != nullptr && e - b >= kMinTableDeg) {
+    if (TABLE && table != nullptr && e - b < kMinTableDeg) {
+        const uint32_t x32 = (uint32_t)x;
+        const uint32_t* words = table + 2 * b;
+        const int d = (int)(e - b);
+        bool found = false;
+        for (int k = 0; k < d; k += 2) {  // the word after an odd-length row's last id is EMPTY
+            const uint2 w = ldg_u32x2_hint(words + k, pol_stream);
+            found |= (w.x == x32) | (w.y == x32);
+        }
+        return found;
+    }
+    if (TABLE && table != nullptr) {
         int64_t first, nb, lo, hi;
         table_span(b, e, first, nb);
         const uint32_t x32 = (uint32_t)x;

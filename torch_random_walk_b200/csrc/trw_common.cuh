@@ -141,6 +141,11 @@ __device__ __forceinline__ int64_t ldg64_hint(const int64_t* p, uint64_t pol) {
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
     return v;
 }
+__device__ __forceinline__ uint2 ldg_u32x2_hint(const uint32_t* p, uint64_t pol) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ Sector64 ldg_sector_hint(const void* p, uint64_t pol) {
     Sector64 s;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
@@ -260,9 +265,13 @@ struct LineStager {
         const uint32_t range = (uint32_t)(first < 0 ? -first : 0) | (slot << 8);
         const int lane = tid & 31, sub = lane & (SLOTS - 1), group = lane / SLOTS;
         while (mask) {
-            const int owner = (int)__fns(mask, 0, group + 1);  // the group-th pending lane, or -1 (0xFFFFFFFF)
+            // the group-th pending lane serves as this lane's owner (-1: none left for this group)
+            int owner = -1;
 #pragma unroll
-            for (int k = 0; k < kOwners; ++k) mask &= mask - 1;  // no-op once zero
+            for (int k = 0; k < kOwners; ++k) {
+                if (k == group && mask) owner = __ffs(mask) - 1;
+                mask &= mask - 1;  // no-op once zero
+            }
             const int src = owner < 0 ? 0 : owner;
             const unsigned long long pp = __shfl_sync(0xFFFFFFFFu, piece_ptr, src);
             const uint32_t rg = __shfl_sync(0xFFFFFFFFu, range, src);
