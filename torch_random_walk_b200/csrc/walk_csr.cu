@@ -8,19 +8,22 @@
 //     prob_0 (x == t), prob_1 (x in adj(t)), prob_2 (otherwise), prob_k = {1/p,1,1/q}/max
 //     (rw_cuda.cu:119-123, 146-179).
 //
-// Design.  Both kernels are dependent random gathers; on B200 every gather
-// that misses L2 costs a full 128-byte line of HBM traffic, so what is optimised is the number of
-// random lines per step:
-//   * one thread owns one walk and the SMs are kept full of them;
-//   * the node2vec loop is flattened to one rejection *trial* per iteration, so lanes whose
-//     proposal was accepted move on instead of idling until the slowest lane is accepted;
-//   * "x in adj(t)" is one 32-byte sector of a hashed copy of the adjacency built per call into
-//     caller-provided workspace (member_table.cuh), not a scan or search of adj(t), and it is
-//     skipped whenever the uniform draw alone decides the trial;
-//   * row_ptr is re-encoded per call as uint32 offsets (half the bytes, fits the 126 MB L2 for
-//     16 M nodes) and read with an L2 evict_last policy, while the never-reused gathers
-//     (proposals, table buckets) and the output stores carry evict_first, so the stream of
-//     random lines does not wash the row index out of L2: row lookups cost no HBM traffic.
+// Design (DESIGN.md sections 3-4).  Both kernels are dependent random gathers.  On B200 a gather that
+// misses L2 moves a full 128-byte line of HBM, and what saturates first is the rate of requests
+// leaving L2 for memory (~48 G/s, loads and stores alike); L2 hits and shared-memory footprint
+// (which shrinks the L1 the in-flight gathers land in) cost too.  Hence:
+//   * one thread owns one walk; about 1024 resident threads per SM saturate the request rate;
+//   * the proposal gather reads a 16-byte edge record that carries the next node's row span, so a
+//     step never touches the row index (member_table.cuh; without records the uint32 row index is
+//     read with an L2 evict_last policy while everything streamed carries evict_first);
+//   * the node2vec loop is flattened to one *trial* per iteration and picks, per (p, q), the
+//     tightest exact sampling scheme: two-sided mixture, return-edge folding or plain rejection;
+//   * "x in adj(t)" is one 32-byte sector of a hashed copy of the adjacency (member_table.cuh),
+//     not a scan or search of adj(t), and is skipped whenever the uniform draw alone decides;
+//   * output leaves in whole 128-byte lines written cooperatively by the warp (LineStager), one
+//     request per line; the loops are therefore warp-converged, one trial per lane per iteration.
+// Everything derived from the graph alone (csr_graph_prepare) is separate from the per-call plan
+// (csr_walk_plan), so it is built per call by trw_walk_csr and once by trw_csr_graph_prepare.
 #include <new>
 
 #include "member_table.cuh"
