@@ -60,11 +60,14 @@ __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const
         const uint32_t x32 = (uint32_t)x;
         const uint32_t* words = table + 2 * b;
         const int d = (int)(e - b);
+        // all (at most six) loads are issued before the first compare: one memory latency, not one per pair
+        uint2 w[(kMinTableDeg) / 2];
+#pragma unroll
+        for (int k = 0; k < (int)kMinTableDeg / 2; ++k)  // the word after an odd-length row's last id is EMPTY
+            w[k] = 2 * k < d ? ldg_u32x2_hint(words + 2 * k, pol_stream) : make_uint2(kEmpty, kEmpty);
         bool found = false;
-        for (int k = 0; k < d; k += 2) {  // the word after an odd-length row's last id is EMPTY
-            const uint2 w = ldg_u32x2_hint(words + k, pol_stream);
-            found |= (w.x == x32) | (w.y == x32);
-        }
+#pragma unroll
+        for (int k = 0; k < (int)kMinTableDeg / 2; ++k) found |= (w[k].x == x32) | (w[k].y == x32);
         return found;
     }
     if (TABLE && table != nullptr) {
