@@ -461,6 +461,48 @@ def test_large_graph_structure_and_hubs(rw):
     assert torch.equal(w, iso[:, None].expand(-1, 6))
 
 
+@pytest.mark.parametrize("workload", ["c2", "c3"])
+def test_baseline_sizes_through_size_independent_properties(native, workload):
+    """BASELINE.json configs[1] (2.45 M nodes, 66 M CSR entries, p=0.5 q=2) and configs[2] (R-MAT scale 24,
+    521 M entries, p=1 q=0.5) at full size, L=80, one walk per degree>0 node.  The oracle cannot run these in
+    seconds, so the checks are the properties that hold at any size: column 0 = start nodes, every transition
+    an edge, reruns identical, any sharding of the start nodes concatenates to the single call, and the
+    prepared graph (edge records, kept table) gives the walks of the stateless call."""
+    from torch_random_walk_b200 import rmat
+
+    # the generator parameters bench.py uses for these configs
+    wl = {"c2": dict(scale=22, n_nodes=2449029, n_edges=34_000_000, p=0.5, q=2.0, L=80),
+          "c3": dict(scale=24, n_nodes=None, edge_factor=16, p=1.0, q=0.5, L=80)}[workload]
+    free, _ = torch.cuda.mem_get_info()
+    if workload == "c3" and free < 60 << 30:
+        pytest.skip("needs ~40 GB of free device memory")
+    rp, ci = rmat.rmat_csr(wl["scale"], wl.get("edge_factor", 16), n_nodes=wl.get("n_nodes"), device="cuda",
+                           n_edges=wl.get("n_edges"))
+    nodes = torch.nonzero(rp[1:] - rp[:-1] > 0).flatten().contiguous()
+    p, q, L = wl["p"], wl["q"], wl["L"]
+    n = nodes.numel()
+    one_shot = native.walk(rp, ci, nodes, p, q, L, 77, cache=False)
+    assert one_shot.shape == (n, L + 1) and torch.equal(one_shot[:, 0], nodes)
+    sample = one_shot[:: max(1, n // 200_000)]
+    assert rmat.transitions_are_edges(rp, ci, sample)
+    # checksums instead of a second full copy: a position-weighted sum that any changed entry changes
+    weights = torch.arange(1, L + 2, device="cuda", dtype=torch.int64)
+
+    def digest(w):
+        return (w * weights).sum(1)
+
+    want = digest(one_shot)
+    del one_shot, sample
+    graph = native.prepare_csr(rp, ci)
+    assert torch.equal(digest(graph.walk(nodes, p, q, L, 77)), want)
+    cuts = [0, n // 3, n // 3 + 12345, n]
+    parts = [digest(graph.walk(nodes[a:b].contiguous(), p, q, L, 77, walk_id_offset=a)) for a, b in zip(cuts, cuts[1:])]
+    assert torch.equal(torch.cat(parts), want)
+    uni = graph.walk(nodes, 1.0, 1.0, L, 5)
+    assert rmat.transitions_are_edges(rp, ci, uni[:: max(1, n // 200_000)])
+    assert not torch.equal(digest(graph.walk(nodes, p, q, L, 78)), want)  # another seed, another set of walks
+
+
 def test_walk_host_matches_device_path(native):
     rp, ci = random_csr(8, 3000, 20)
     nodes = torch.randint(0, 3000, (10000,))
