@@ -124,6 +124,34 @@ def test_deterministic_and_seeded(rw):
     assert float(hist.min()) > 0.8 * float(hist.mean()) and float(hist.max()) < 1.2 * float(hist.mean())
 
 
+def test_row_fast_paths_equal_the_element_path(rw):
+    """W=5 rows and skip-gram negatives are written as whole 32-byte rows when the output is 32-byte
+    aligned; an output shifted by one element takes the per-element path.  Same values either way."""
+    import ctypes
+
+    from torch_random_walk_b200 import native
+
+    lib = native.lib()
+    n, wl, W, nodes = 1234, 81, 5, 1 << 20
+    walks = torch.randint(0, nodes, (n, wl), device="cuda")
+    k = n * (wl - W + 1)
+    fast = rw.to_windows(walks, W, nodes, 9)
+    fast_cbow = rw.to_windows_cbow(walks, W, nodes, 9)
+    # pure-torch restatement of the positives (windows_cuda.cu:40-55): the window without its middle element
+    idx = torch.arange(wl - W + 1, device="cuda")[:, None] + torch.tensor([0, 1, 3, 4], device="cuda")[None, :]
+    assert torch.equal(fast[1], walks[:, idx].reshape(k, W - 1)) and torch.equal(fast_cbow[2], fast[1])
+    assert torch.equal(fast[0], walks[:, 2:wl - 2].reshape(k))
+    bufs = [torch.empty(k * (W - 1) + 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    tgt = torch.empty(k, dtype=torch.int64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.trw_windows(ctypes.c_void_p(walks.data_ptr()), n, wl, W, nodes, 9, ctypes.c_void_p(tgt.data_ptr()),
+                         ctypes.c_void_p(bufs[0].data_ptr() + 8), ctypes.c_void_p(bufs[1].data_ptr() + 8), 0, st)
+    assert rc == 0
+    assert torch.equal(bufs[0][1:1 + k * (W - 1)].view(k, W - 1), fast[1])
+    assert torch.equal(bufs[1][1:1 + k * (W - 1)].view(k, W - 1), fast[2])
+    assert int(fast[2].min()) >= 0 and int(fast[2].max()) < nodes
+
+
 def test_cbow_single_node_and_degenerate_triples(rw):
     walks = torch.zeros((4, 9), dtype=torch.int64, device="cuda")
     pos, neg, win = rw.to_windows_cbow(walks, 3, 1, 5)  # only node 0 exists: 101 redraws, then the same node

@@ -272,6 +272,31 @@ __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
         const uint64_t gbase = (uint64_t)i0 * a.epw[which];
         int64_t* dst = a.out[which] + gbase;
         const uint32_t n = (uint32_t)tw * a.epw[which];
+        // Fast paths of the node windows: whole 32-byte rows per thread.  The generic loop below pays two
+        // divisions per 8-byte element and, for the negatives, one Philox block per element although a
+        // block yields the four draws of an aligned quad -- that redundancy alone kept the kernel
+        // issue-bound at 4.0 TB/s.
+        if (MODE == kSkipGram && which == 2 && (uint64_t)a.num_nodes <= 0xFFFFFFFFull && (gbase & 3u) == 0 &&
+            (((uintptr_t)dst) & 31) == 0) {
+            const uint32_t nq = n >> 2, nn = (uint32_t)a.num_nodes;
+            for (uint32_t q = threadIdx.x; q < nq; q += BLOCK) {
+                const uint64_t gq = (gbase >> 2) + q;  // same block and word order as window_element()
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), 1u, 0x51554144u), a.key);
+                stg_sector(dst + 4u * q, __umulhi(r.x, nn), __umulhi(r.y, nn), __umulhi(r.z, nn), __umulhi(r.w, nn));
+            }
+            for (uint32_t k = (nq << 2) + threadIdx.x; k < n; k += BLOCK) dst[k] = window_element<MODE>(a, tile, which, k, gbase + k);
+            continue;
+        }
+        if ((MODE == kSkipGram ? which == 1 : (MODE == kCbow && which == 2)) && a.W == 5 && (((uintptr_t)dst) & 31) == 0) {
+            const uint32_t nw = (uint32_t)tw * (uint32_t)a.per_walk;  // one window = one 32-byte row (w0, w1, w3, w4)
+            for (uint32_t k = threadIdx.x; k < nw; k += BLOCK) {
+                uint32_t i, sidx;
+                a.by_per_walk.divmod(k, i, sidx);
+                const int64_t* w = tile + (size_t)i * a.wl + sidx;
+                stg_sector(dst + 4u * k, (uint64_t)w[0], (uint64_t)w[1], (uint64_t)w[3], (uint64_t)w[4]);
+            }
+            continue;
+        }
         if ((((uintptr_t)dst) & 15) == 0) {
             const uint32_t n2 = n >> 1;
             for (uint32_t k = threadIdx.x; k < n2; k += BLOCK) {
@@ -334,13 +359,13 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     a.by_per_walk.set((uint32_t)per_walk);
     a.by_row.set(kTripleMode ? (uint32_t)(2 * W) : (uint32_t)(W - 1));
     a.by_3.set(3);
-    // Tile: an even number of walk rows, about 32 KiB of them, and < 2^31 elements per output segment.
+    // Tile: a multiple of four walk rows, about 32 KiB of them, and < 2^31 elements per output segment.
     constexpr int BLOCK = 256;
     int64_t tw = (32 * 1024) / (walk_cols * 8);
     const int64_t cap = (1ll << 30) / (max_epw > 0 ? max_epw : 1);
     if (tw > cap) tw = cap;
-    tw &= ~1ll;
-    if (tw < 2) tw = 2;
+    tw &= ~3ll;  // a multiple of four: every tile's output segments start on a 32-byte boundary of their tensor
+    if (tw < 4) tw = 4;
     size_t smem = (size_t)tw * walk_cols * 8;
     a.use_smem = 1;
     if (smem > 200 * 1024) { a.use_smem = 0; smem = 0; }
