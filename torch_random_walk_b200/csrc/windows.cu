@@ -140,61 +140,83 @@ __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_
 }
 
 // ------------------------------------------------------------------------------------------
-// Triple modes: 24-byte rows make the per-element index arithmetic (three divisions) and the
-// per-element Philox call the bound, not HBM.  So (a) every thread walks its elements with an
-// odometer -- (component, window row, target, walk) advanced by constant strides with single
-// carries, no division in the loop -- and (b) the negative rows of a chunk are drawn first, four
-// per Philox block, into shared memory, then streamed out.  Stores stay coalesced and 8 bytes wide
-// per lane (a warp writes 256 contiguous bytes per instruction).
+// Triple modes.  Every output row is a triple (24 bytes); producing the outputs element by element
+// pays the index arithmetic and, for the negatives, the random draw three times per row, and kept
+// the kernel issue-bound at 3-4 TB/s (59 % of the issue slots, ncu).  So rows are produced whole --
+// one thread decodes (walk, target, window row) once and computes the three values -- into a
+// per-warp shared-memory stage, and the stage leaves with coalesced 16-byte stores: per-lane 24-byte pieces
+// written directly would touch every 128-byte line of the warp's span three times, and requests,
+// not bytes, are what the memory system charges for.
 // ------------------------------------------------------------------------------------------
-struct Odometer {  // element e = ((i * K + ti) * R + h) * 3 + c, advanced by a fixed stride
-    uint32_t c, h, ti, i;
-    uint32_t dc, dh, dti, di, R, K;
-    __device__ __forceinline__ void init(uint32_t e, uint32_t stride, uint32_t R_, uint32_t K_) {
-        R = R_; K = K_;
-        c = e % 3u; uint32_t row = e / 3u;
-        h = row % R; uint32_t k = row / R;
-        ti = k % K; i = k / K;
-        dc = stride % 3u; uint32_t drow = stride / 3u;
-        dh = drow % R; uint32_t dk = drow / R;
-        dti = dk % K; di = dk / K;
-    }
-    __device__ __forceinline__ void advance() {
-        c += dc; uint32_t carry = c >= 3u; c -= 3u * carry;
-        h += dh + carry; carry = h >= R; h -= R * carry;
-        ti += dti + carry; carry = ti >= K; ti -= K * carry;
-        i += di + carry;
-    }
-};
+constexpr int kNegChunkRows = 2048;  // negative rows drawn per round (8 KiB of row indices)
+constexpr int kWarpRows = 64;  // rows a warp stages per round: 1536 bytes, three 16-byte pieces per lane
 
-constexpr int kNegChunkRows = 4096;  // negative rows drawn per round (16 KiB of row indices)
+// Every warp takes blocks of kWarpRows consecutive rows of the segment: row_fn(row, stage_slot) writes one row's three
+// values, two rows per lane; then the warp streams its 1.5 KB to dst.  Only warp-level synchronisation.
+template <int BLOCK, class RowFn>
+__device__ __forceinline__ void emit_rows(int64_t* __restrict__ dst, uint32_t n_rows, int64_t* __restrict__ stage, RowFn row_fn) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t* wstage = stage + warp * (kWarpRows * 3);
+    const bool vec = (((uintptr_t)dst) & 15) == 0;
+    for (uint32_t first = warp * kWarpRows; first < n_rows; first += (BLOCK / 32) * kWarpRows) {
+        const uint32_t cnt = min((uint32_t)kWarpRows, n_rows - first);
+        for (uint32_t g = lane; g < cnt; g += 32) row_fn(first + g, wstage + 3u * g);
+        __syncwarp();
+        const uint32_t n_el = cnt * 3u;
+        int64_t* out = dst + (uint64_t)first * 3u;  // first is even: 16-byte alignment carries over from dst
+        if (vec) {
+            for (uint32_t k = lane; k < (n_el >> 1); k += 32)
+                reinterpret_cast<longlong2*>(out)[k] = reinterpret_cast<const longlong2*>(wstage)[k];
+            if ((n_el & 1u) && lane == 0) out[n_el - 1] = wstage[n_el - 1];
+        } else {
+            for (uint32_t k = lane; k < n_el; k += 32) out[k] = wstage[k];
+        }
+        __syncwarp();
+    }
+}
 
 template <int MODE, int BLOCK>
 __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* tile, int64_t i0, int tw) {
-    __shared__ uint32_t neg_rows[MODE == kTriples ? kNegChunkRows : 1];
+    __shared__ __align__(16) int64_t stage[(BLOCK / 32) * kWarpRows * 3];
     const uint32_t K = (uint32_t)a.per_walk, R = (uint32_t)(2 * a.W);
     const int pos_out = (MODE == kTriples) ? 1 : 2, neg_out = (MODE == kTriples) ? 2 : 1;
-    const int tid = threadIdx.x;
-    // targets / pos_triples: element = (i*K + ti)*3 + c  ->  walk[i][2*ti + c]
-    {
-        int64_t* dst = a.out[0] + (uint64_t)i0 * K * 3u;
-        const uint32_t n = (uint32_t)tw * K * 3u;
-        Odometer o;
-        o.init((uint32_t)tid, BLOCK, 1u, K);
-        for (uint32_t e = tid; e < n; e += BLOCK, o.advance()) dst[e] = tile[(size_t)o.i * a.wl + 2u * o.ti + o.c];
-    }
-    // positive windows: element = ((i*K + ti)*2W + h)*3 + c
+    // targets / pos_triples: row (i, ti) = walk[i][2*ti .. 2*ti+2]
+    emit_rows<BLOCK>(a.out[0] + (uint64_t)i0 * K * 3u, (uint32_t)tw * K, stage, [&](uint32_t row, int64_t* o) {
+        uint32_t i, ti;
+        a.by_per_walk.divmod(row, i, ti);
+        const int64_t* w = tile + (size_t)i * a.wl + 2u * ti;
+        o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+    });
+    // positive windows: row (i, ti, h), the three slots of triple_window_value() at once
     if (R > 0) {
-        int64_t* dst = a.out[pos_out] + (uint64_t)i0 * K * R * 3u;
-        const uint32_t n = (uint32_t)tw * K * R * 3u;
-        Odometer o;
-        o.init((uint32_t)tid, BLOCK, R, K);
-        for (uint32_t e = tid; e < n; e += BLOCK, o.advance())
-            dst[e] = triple_window_value(tile + (size_t)o.i * a.wl, a.wl, a.W, a.pad, (int)o.ti, (int)o.h, (int)o.c);
+        emit_rows<BLOCK>(a.out[pos_out] + (uint64_t)i0 * K * R * 3u, (uint32_t)tw * K * R, stage, [&](uint32_t row, int64_t* o) {
+            uint32_t k, h, i, ti;
+            a.by_row.divmod(row, k, h);
+            a.by_per_walk.divmod(k, i, ti);
+            const int64_t* w = tile + (size_t)i * a.wl;
+            const int r = 2 * (int)ti + 1;
+            if ((int)h < a.W) {  // left rows: (walk[ri], walk[ri], walk[ri+1]) -- windows_cuda.cu:284-313, head slot as the reference has it
+                const int ri = r - 2 * ((int)h + 1);
+                const int64_t rel = ri >= 1 ? w[ri] : a.pad;
+                o[0] = rel; o[1] = rel;
+                o[2] = ri >= -1 ? w[ri + 1] : a.pad;
+            } else {             // right rows: walk[idx .. idx+2] where it exists (:315-345)
+                const int idx = r + 2 * ((int)h - a.W + 1) - 1;
+                o[0] = idx < a.wl ? w[idx] : a.pad;
+                o[1] = idx + 1 < a.wl ? w[idx + 1] : a.pad;
+                o[2] = idx + 2 < a.wl ? w[idx + 2] : a.pad;
+            }
+        });
     }
     if (MODE == kTriples) {
-        // neg_windows: every row a uniformly drawn row of `triples` (windows_cuda.cu:353-365)
-        const uint64_t row0 = (uint64_t)i0 * K * R;  // first global negative row of this tile (a multiple of 4)
+        // neg_windows: every row a uniformly drawn row of `triples` (windows_cuda.cu:353-365).  The row
+        // indices of a chunk are drawn first, four per Philox block (the tile's first row is a multiple
+        // of four), then the rows are gathered element by element straight into the coalesced stores
+        // (measured: gathering whole rows per lane through the stage is slower, 3.3 vs 4.3 TB/s -- the
+        // gathers hit the L2-resident table and want one sector request per ~3 lanes, not three per lane).
+        __shared__ uint32_t neg_rows[kNegChunkRows];
+        const int tid = threadIdx.x;
+        const uint64_t row0 = (uint64_t)i0 * K * R;
         const uint32_t n_rows = (uint32_t)tw * K * R;
         int64_t* dst = a.out[neg_out] + row0 * 3u;
         const bool small = (uint64_t)a.n_triples <= 0xFFFFFFFFull;
@@ -214,8 +236,7 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
                 const uint32_t row = e / 3u, c = e - row * 3u;
                 int64_t idx = neg_rows[row];
                 if (!small) {  // more than 2^32 triples: widen the draw with a second block (never in practice)
-                    const uint64_t g = row0 + base + row;
-                    const uint2 r = draw64(a.key, g, 3u, 1u);
+                    const uint2 r = draw64(a.key, row0 + base + row, 3u, 1u);
                     idx = bounded((uint32_t)idx, r.x, a.n_triples);
                 }
                 dst[(uint64_t)base * 3u + e] = __ldg(a.triples + idx * 3 + c);
@@ -224,22 +245,21 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
         }
     } else {
         // neg_triples: one row per target, redrawn while identical to the positive triple (windows_cuda.cu:485-505)
-        int64_t* dst = a.out[neg_out] + (uint64_t)i0 * K * 3u;
-        const uint32_t n = (uint32_t)tw * K * 3u;
-        Odometer o;
-        o.init((uint32_t)tid, BLOCK, 1u, K);
-        for (uint32_t e = tid; e < n; e += BLOCK, o.advance()) {
-            const uint64_t grow = ((uint64_t)i0 + o.i) * K + o.ti;
-            const int64_t* w = tile + (size_t)o.i * a.wl + 2u * o.ti;
+        emit_rows<BLOCK>(a.out[neg_out] + (uint64_t)i0 * K * 3u, (uint32_t)tw * K, stage, [&](uint32_t row, int64_t* o) {
+            uint32_t i, ti;
+            a.by_per_walk.divmod(row, i, ti);
+            const uint64_t grow = ((uint64_t)i0 + i) * K + ti;
+            const int64_t* w = tile + (size_t)i * a.wl + 2u * ti;
             const int64_t ph = w[0], pr = w[1], pt = w[2];
-            int64_t idx = 0;
+            int64_t nh = 0, nr = 0, nt = 0;
             for (uint32_t attempt = 0; attempt <= 101u; ++attempt) {
                 const uint2 r = draw64(a.key, grow, 4u, attempt);
-                idx = bounded(r.x, r.y, a.n_triples);
-                if (__ldg(a.triples + idx * 3) != ph || __ldg(a.triples + idx * 3 + 1) != pr || __ldg(a.triples + idx * 3 + 2) != pt) break;
+                const int64_t* t = a.triples + bounded(r.x, r.y, a.n_triples) * 3;
+                nh = __ldg(t); nr = __ldg(t + 1); nt = __ldg(t + 2);
+                if (nh != ph || nr != pr || nt != pt) break;
             }
-            dst[e] = __ldg(a.triples + idx * 3 + o.c);
-        }
+            o[0] = nh; o[1] = nr; o[2] = nt;
+        });
     }
 }
 
@@ -361,7 +381,8 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     a.by_3.set(3);
     // Tile: a multiple of four walk rows, about 32 KiB of them, and < 2^31 elements per output segment.
     constexpr int BLOCK = 256;
-    int64_t tw = (32 * 1024) / (walk_cols * 8);
+    // (triple modes add a 12 KiB output stage and 8 KiB of drawn row indices: a 16 KiB tile keeps six CTAs per SM)
+    int64_t tw = ((kTripleMode ? 16 : 32) * 1024) / (walk_cols * 8);
     const int64_t cap = (1ll << 30) / (max_epw > 0 ? max_epw : 1);
     if (tw > cap) tw = cap;
     tw &= ~3ll;  // a multiple of four: every tile's output segments start on a 32-byte boundary of their tensor
