@@ -8,9 +8,11 @@
 // stores scattered over three tensors.  Here the problem is turned around: every output tensor
 // is a dense array whose element e is a pure function of e (which walk, which window, which
 // slot), so a CTA stages a tile of walk rows in shared memory once and then streams the three
-// contiguous output segments that belong to that tile with fully coalesced 16-byte stores.
-// Positives and targets are bit-exact with the reference; negatives are Philox draws indexed
-// by the output element, so they do not depend on the launch shape.
+// contiguous output segments that belong to that tile, coalesced: node windows as whole 32-byte
+// rows per thread where the shape allows (else 16-byte pairs through window_element()), triple
+// rows produced whole into per-warp stages (triple_tile()).  Positives and targets are bit-exact
+// with the reference; negatives are Philox draws indexed by the output element (one block per
+// aligned quad of draws), so they do not depend on the launch shape or on which path wrote them.
 #include "trw_common.cuh"
 #include "trw_options.h"
 
@@ -44,7 +46,6 @@ struct WinArgs {
     uint32_t epw[3];       // elements of out[k] per walk
     FastDiv by_per_walk;   // / per_walk
     FastDiv by_row;        // / (W-1)   (node windows)  or  / (2W) (triple windows)
-    FastDiv by_3;
 };
 
 // Draw #draw of stream `stream` for item g: 64 random bits as two words.
@@ -53,23 +54,10 @@ __device__ __forceinline__ uint2 draw64(const uint2 key, uint64_t g, uint32_t st
     return (draw & 1u) ? make_uint2(r.z, r.w) : make_uint2(r.x, r.y);
 }
 
-// Positive window slot (row h of 2W, component c) of target triple ti in walk row w
-// (windows_cuda.cu:284-345; note the head slot of a LEFT row holds walk[rel_idx], :294-295).
-__device__ __forceinline__ int64_t triple_window_value(const int64_t* w, int wl, int W, int64_t pad, int ti, int h, int c) {
-    const int r = 2 * ti + 1;
-    if (h < W) {
-        const int ri = r - 2 * (h + 1);
-        if (c == 2) return ri >= -1 ? w[ri + 1] : pad;
-        return ri >= 1 ? w[ri] : pad;
-    }
-    const int idx = r + 2 * (h - W + 1) - 1 + c;
-    return idx < wl ? w[idx] : pad;
-}
-
 template <int MODE>
 __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_t* tile, int which, uint32_t e, uint64_t g) {
     // e: element index inside this tile's segment of out[which]; g: the same index in the whole tensor.
-    if (MODE == kSkipGram || MODE == kCbow) {
+    if (MODE == kSkipGram || MODE == kCbow) {  // element path of the node windows (fast row paths: windows_kernel)
         const int pos_out = (MODE == kSkipGram) ? 1 : 2, neg_out = (MODE == kSkipGram) ? 2 : 1;
         if (which == 0) {  // target_nodes / pos_nodes
             uint32_t i, s;
@@ -104,39 +92,7 @@ __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_
         }
         return neg;
     }
-    // Triple modes.
-    const int pos_out = (MODE == kTriples) ? 1 : 2;
-    uint32_t row, c;
-    a.by_3.divmod(e, row, c);
-    if (which == 0) {  // target_triples / pos_triples
-        uint32_t i, ti;
-        a.by_per_walk.divmod(row, i, ti);
-        return tile[(size_t)i * a.wl + 2 * ti + c];
-    }
-    if (which == pos_out) {
-        uint32_t k, h, i, ti;
-        a.by_row.divmod(row, k, h);
-        a.by_per_walk.divmod(k, i, ti);
-        return triple_window_value(tile + (size_t)i * a.wl, a.wl, a.W, a.pad, (int)ti, (int)h, (int)c);
-    }
-    const uint64_t grow = g / 3;  // row of the negative tensor
-    if (MODE == kTriples) {  // neg_windows: a uniformly drawn row of `triples` (:353-365)
-        uint2 r = draw64(a.key, grow, 3u, 0u);
-        const int64_t idx = bounded(r.x, r.y, a.n_triples);
-        return __ldg(a.triples + idx * 3 + c);
-    }
-    // Triple CBOW neg_triples: redraw while identical to the positive triple (:485-505)
-    uint32_t i, ti;
-    a.by_per_walk.divmod(row, i, ti);
-    const int64_t* w = tile + (size_t)i * a.wl + 2 * ti;
-    const int64_t ph = w[0], pr = w[1], pt = w[2];
-    int64_t idx = 0;
-    for (uint32_t attempt = 0; attempt <= 101u; ++attempt) {
-        uint2 r = draw64(a.key, grow, 4u, attempt);
-        idx = bounded(r.x, r.y, a.n_triples);
-        if (__ldg(a.triples + idx * 3) != ph || __ldg(a.triples + idx * 3 + 1) != pr || __ldg(a.triples + idx * 3 + 2) != pt) break;
-    }
-    return __ldg(a.triples + idx * 3 + c);
+    return 0;  // triple modes never come here: triple_tile() produces their rows whole
 }
 
 // ------------------------------------------------------------------------------------------
@@ -378,7 +334,6 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     for (int k = 0; k < 3; ++k) a.epw[k] = epw[k];
     a.by_per_walk.set((uint32_t)per_walk);
     a.by_row.set(kTripleMode ? (uint32_t)(2 * W) : (uint32_t)(W - 1));
-    a.by_3.set(3);
     // Tile: a multiple of four walk rows, about 32 KiB of them, and < 2^31 elements per output segment.
     constexpr int BLOCK = 256;
     // (triple modes add a 12 KiB output stage and 8 KiB of drawn row indices: a 16 KiB tile keeps six CTAs per SM)
