@@ -503,6 +503,45 @@ def test_baseline_sizes_through_size_independent_properties(native, workload):
     assert not torch.equal(digest(graph.walk(nodes, p, q, L, 78)), want)  # another seed, another set of walks
 
 
+def test_guard_bands_around_outputs_and_workspace(native):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are looked for directly: the
+    workspace (row index, table, records, work lists) and the walk output get sentinel-filled guard
+    bands on both sides, the library is called through the C ABI with pointers into the middle, and
+    the bands must come back untouched.  Shapes: hubs, empty rows, a walk count that is no multiple
+    of the warp size, a row length that is no multiple of the 16-element staging pieces."""
+    import ctypes
+
+    from torch_random_walk_b200 import rmat
+
+    lib = native.lib()
+    rp, ci = rmat.rmat_csr(14, 16, device="cuda", seed=9)
+    n, nnz = rp.numel() - 1, ci.numel()
+    nodes = torch.arange(n - 7, device="cuda")
+    nw, L, guard = nodes.numel(), 37, 4096
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sentinel = -0x0123456789ABCDEF
+    for p_, q_, rec in ((1.0, 1.0, 1), (1.0, 0.5, 1), (0.5, 2.0, 1), (0.25, 4.0, 0), (1.0, 0.5, 0)):
+        native.set_option("records", rec)
+        try:
+            need = lib.trw_walk_csr_workspace_bytes(n, nnz, p_, q_)
+            ws_words = (need + 7) // 8
+            ws = torch.full((guard + ws_words + guard,), sentinel, dtype=torch.int64, device="cuda")
+            out = torch.full((guard + nw * (L + 1) + guard,), sentinel, dtype=torch.int64, device="cuda")
+            base = ws.data_ptr() + guard * 8
+            assert base % 256 == 0
+            rc = lib.trw_walk_csr(ctypes.c_void_p(rp.data_ptr()), ctypes.c_void_p(ci.data_ptr()), n, nnz,
+                                  ctypes.c_void_p(nodes.data_ptr()), nw, 0, p_, q_, L, 5,
+                                  ctypes.c_void_p(out.data_ptr() + guard * 8), L + 1, ctypes.c_void_p(base), need, 0, st)
+            assert rc == 0, lib.trw_last_error()
+            torch.cuda.synchronize()
+            for t in (ws, out):
+                assert bool((t[:guard] == sentinel).all()) and bool((t[-guard:] == sentinel).all()), (p_, q_, rec)
+            walks = out[guard:guard + nw * (L + 1)].view(nw, L + 1)
+            assert torch.equal(walks, native.walk(rp, ci, nodes, p_, q_, L, 5, cache=False))
+        finally:
+            native.set_option("records", -1)
+
+
 def test_walk_host_matches_device_path(native):
     rp, ci = random_csr(8, 3000, 20)
     nodes = torch.randint(0, 3000, (10000,))

@@ -152,6 +152,53 @@ def test_row_fast_paths_equal_the_element_path(rw):
     assert int(fast[2].min()) >= 0 and int(fast[2].max()) < nodes
 
 
+def test_window_outputs_stay_inside_their_tensors(rw):
+    """Guard bands around every output of the four window kernels (see the walk test of the same name)."""
+    import ctypes
+
+    from torch_random_walk_b200 import native
+
+    lib = native.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    guard, sentinel = 1024, -0x0123456789ABCDEF
+    walks = torch.randint(0, 300, (131, 41), device="cuda")
+    triples = torch.randint(0, 300, (500, 3), device="cuda")
+
+    def padded(numel):
+        return torch.full((guard + numel + guard,), sentinel, dtype=torch.int64, device="cuda")
+
+    def ptr(t):
+        return ctypes.c_void_p(t.data_ptr() + guard * 8)
+
+    def intact(*ts):
+        torch.cuda.synchronize()
+        return all(bool((t[:guard] == sentinel).all()) and bool((t[-guard:] == sentinel).all()) for t in ts)
+
+    for W in (1, 4, 5, 7):
+        k = 131 * (41 - W + 1)
+        a, b, c = padded(k), padded(k * (W - 1)), padded(k * (W - 1))
+        assert lib.trw_windows(ctypes.c_void_p(walks.data_ptr()), 131, 41, W, 300, 3, ptr(a), ptr(b), ptr(c), 0, st) == 0
+        assert intact(a, b, c)
+        ref = rw.to_windows(walks, W, 300, 3)
+        assert torch.equal(b[guard:guard + k * (W - 1)].view(k, W - 1), ref[1])
+        a, b, c = padded(k), padded(k), padded(k * (W - 1))
+        assert lib.trw_windows_cbow(ctypes.c_void_p(walks.data_ptr()), 131, 41, W, 300, 3, ptr(a), ptr(b), ptr(c), 0, st) == 0
+        assert intact(a, b, c)
+    for W in (1, 3, 5):
+        k = 131 * 20
+        a, b, c = padded(k * 3), padded(k * 2 * W * 3), padded(k * 2 * W * 3)
+        assert lib.trw_windows_triples(ctypes.c_void_p(walks.data_ptr()), 131, 41, W, 300, 999, ctypes.c_void_p(triples.data_ptr()),
+                                       500, 3, ptr(a), ptr(b), ptr(c), 0, st) == 0
+        assert intact(a, b, c)
+        ref = rw.to_windows_triples(walks, W, 300, 999, triples, 3)
+        assert torch.equal(b[guard:guard + k * 2 * W * 3].view(k, 2 * W, 3), ref[1])
+        assert torch.equal(c[guard:guard + k * 2 * W * 3].view(k, 2 * W, 3), ref[2])
+        a, b, c = padded(k * 3), padded(k * 3), padded(k * 2 * W * 3)
+        assert lib.trw_windows_triples_cbow(ctypes.c_void_p(walks.data_ptr()), 131, 41, W, 300, 999,
+                                            ctypes.c_void_p(triples.data_ptr()), 500, 3, ptr(a), ptr(b), ptr(c), 0, st) == 0
+        assert intact(a, b, c)
+
+
 def test_cbow_single_node_and_degenerate_triples(rw):
     walks = torch.zeros((4, 9), dtype=torch.int64, device="cuda")
     pos, neg, win = rw.to_windows_cbow(walks, 3, 1, 5)  # only node 0 exists: 101 redraws, then the same node
