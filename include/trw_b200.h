@@ -135,6 +135,20 @@ int trw_walk_edge_list(const int64_t* edge_list, int64_t n_edges,
                        int64_t padding_idx, int restart,
                        int64_t* out, int64_t out_row_stride, int device, void* stream);
 
+/* The same walk with a workspace: the second-order path then answers "x is a neighbour of t" from
+ * the hashed membership table of the CSR walk (built per call over a CSR view of the edge list)
+ * instead of the reference's O(deg) scan (rw_cuda_edge_list.cu:98-123), with identical results.
+ * workspace: trw_walk_edge_list_workspace_bytes() bytes of 256-byte aligned device memory (0 for
+ * p == q == 1, which needs none); NULL selects the scan. */
+size_t trw_walk_edge_list_workspace_bytes(int64_t n_edges, int64_t n_index_rows, double p, double q);
+int trw_walk_edge_list_ws(const int64_t* edge_list, int64_t n_edges,
+                          const int64_t* node_edge_index, int64_t n_index_rows,
+                          const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
+                          double p, double q, int walk_length, int64_t seed,
+                          int64_t padding_idx, int restart,
+                          int64_t* out, int64_t out_row_stride,
+                          void* workspace, size_t workspace_bytes, int device, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Knowledge-graph triple walks.   Replaces walk_triples() -> triples::walk_triples_gpu():
  * csrc/rw_init.cpp:47-75, csrc/cuda/rw_cuda_triples.cu:103-169 (kernel :49-96).

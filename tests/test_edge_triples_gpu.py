@@ -106,6 +106,47 @@ def test_biased_edge_list_statistics_match_oracle(rw, orc, p, q, restart):
     assert set(fa) == set(fb)
 
 
+@pytest.mark.parametrize("duplicates,sort_tails", [(False, True), (False, False), (True, False)])
+def test_edge_list_table_path_equals_the_reference_scan(rw, duplicates, sort_tails):
+    """The second-order edge-list walk answers "x in adj(t)" from the hashed table when it has a
+    workspace; the reference scans [first, last) -- the last out-edge excluded.  Same draws, so the
+    walks must be bit-identical, on long rows (hashed), short rows (packed), unsorted tails and
+    tails stored twice (where "x is the last tail" has to count the earlier copy)."""
+    from helpers import random_csr
+    from torch_random_walk_b200 import native
+
+    rp, ci = random_csr(31, 1500, 30, sort_rows=sort_tails)
+    rp_np, ci_np = rp.numpy(), ci.numpy().copy()
+    if duplicates:  # the last tail of every other row also appears in the row's first slot, or not at all elsewhere
+        for v in range(0, 1500, 2):
+            if rp_np[v + 1] - rp_np[v] >= 3:
+                ci_np[rp_np[v]] = ci_np[rp_np[v + 1] - 1]
+    n = 1500
+    heads = np.repeat(np.arange(n), np.diff(rp_np))
+    el = T(np.stack((heads, ci_np), 1)).cuda()
+    nei, el = utils.build_node_edge_index(el, torch.arange(n))
+    nodes = torch.arange(n, device="cuda")
+    for p, q, restart in ((0.5, 2.0, True), (1.0, 0.5, False), (0.25, 4.0, True), (2.0, 0.5, True)):
+        a = rw.walk_edge_list(el, nei, nodes, p, q, 30, 4, n, restart=restart)
+        native.set_option("el_table", 0)
+        try:
+            b = rw.walk_edge_list(el, nei, nodes, p, q, 30, 4, n, restart=restart)
+        finally:
+            native.set_option("el_table", 1)
+        assert torch.equal(a, b), (p, q, restart)
+    # an index that does not describe the edge list must not be trusted: the walk falls back to the scan
+    bad = nei.clone()
+    rows_with_edges = torch.nonzero(bad[:, 0] >= 0).flatten()
+    bad[rows_with_edges[5], 1] -= 1  # node loses its last edge in the index only
+    a = rw.walk_edge_list(el, bad, nodes, 0.5, 2.0, 20, 4, n)
+    native.set_option("el_table", 0)
+    try:
+        b = rw.walk_edge_list(el, bad, nodes, 0.5, 2.0, 20, 4, n)
+    finally:
+        native.set_option("el_table", 1)
+    assert torch.equal(a, b)
+
+
 def test_edge_list_matches_reference_golden_dead_ends(rw, golden):
     # rows that never branch are RNG-free: compare them with the reference's own output
     for case in range(2):

@@ -55,9 +55,11 @@ torch::Tensor walk_edge_list(const torch::Tensor* edge_list_indexed, const torch
   c10::cuda::CUDAGuard guard(node_edges_idx->device());
   auto el = edge_list_indexed->contiguous(), nei = node_edges_idx->contiguous(), tg = target_nodes->contiguous();
   auto walks = torch::empty({tg.size(0), walk_length + 1}, like(nei));
-  TRW_CHECK(trw_walk_edge_list(ptr(el), el.size(0), ptr(nei), nei.size(0), ptr(tg), tg.size(0), 0, p, q, walk_length, seed,
-                               padding_idx, restart ? 1 : 0, walks.data_ptr<int64_t>(), walk_length + 1,
-                               nei.device().index(), stream()));
+  const size_t need = tg.size(0) ? trw_walk_edge_list_workspace_bytes(el.size(0), nei.size(0), p, q) : 0;
+  auto ws = torch::empty({(int64_t)need}, like(nei).dtype(torch::kUInt8));
+  TRW_CHECK(trw_walk_edge_list_ws(ptr(el), el.size(0), ptr(nei), nei.size(0), ptr(tg), tg.size(0), 0, p, q, walk_length, seed,
+                                  padding_idx, restart ? 1 : 0, walks.data_ptr<int64_t>(), walk_length + 1,
+                                  need ? ws.data_ptr() : nullptr, need, nei.device().index(), stream()));
   return walks;
 }
 

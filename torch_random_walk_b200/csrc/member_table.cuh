@@ -101,6 +101,41 @@ __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const
     return false;
 }
 
+// Does x occur at least TWICE in the row?  Only meaningful for tables assembled in shared memory
+// (build_mode 2), which store every entry of a row, duplicates included.  Used by the edge-list walk,
+// whose reference semantics ignore the last out-edge of a row (walk_other.cu).
+__device__ __forceinline__ bool member_twice(int64_t x, int64_t b, int64_t e, const uint32_t* __restrict__ table,
+                                             uint64_t pol_stream) {
+    const uint32_t x32 = (uint32_t)x;
+    int count = 0;
+    if (e - b < kMinTableDeg) {
+        const uint32_t* words = table + 2 * b;
+        const int d = (int)(e - b);
+#pragma unroll
+        for (int k = 0; k < (int)kMinTableDeg / 2; ++k) {
+            const uint2 w = 2 * k < d ? ldg_u32x2_hint(words + 2 * k, pol_stream) : make_uint2(kEmpty, kEmpty);
+            count += (w.x == x32) + (w.y == x32);
+        }
+        return count >= 2;
+    }
+    int64_t first, nb, lo, hi;
+    table_span(b, e, first, nb);
+    int64_t bkt = home_bucket(x32, nb);
+    probe_segment(nb, bkt, lo, hi);
+    for (int64_t probes = lo; probes < hi; ++probes) {
+        const Sector64 s = ldg_sector_hint(table + (first + bkt) * 8, pol_stream);
+        const uint32_t w[8] = {(uint32_t)s.a, (uint32_t)(s.a >> 32), (uint32_t)s.b, (uint32_t)(s.b >> 32),
+                               (uint32_t)s.c, (uint32_t)(s.c >> 32), (uint32_t)s.d, (uint32_t)(s.d >> 32)};
+        bool open = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { count += (w[j] == x32); open |= (w[j] == kEmpty); }
+        if (count >= 2) return true;
+        if (open) return false;
+        if (++bkt == hi) bkt = lo;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------- host side (member_table.cu)
 // Offsets of the per-call scratch inside the caller's workspace (all 256-byte aligned).
 struct CsrWorkspace {

@@ -13,6 +13,7 @@ struct Options {
     int64_t n2v_mix = 1;          // 1: two-sided mixture sampling when q > 1 and p <= q (duplicate-free rows; see node2vec_walk_kernel)
     int64_t n2v_min_ctas = -1;    // __launch_bounds__ min CTAs/SM of the node2vec kernel (4, 5 or 6; -1: 5 with edge records, else 4)
     int64_t row32 = 1;            // 1: re-encode row_ptr as uint32 offsets per call (needs workspace)
+    int64_t el_table = 1;         // 1: edge-list node2vec walks test membership through the hashed table (needs workspace); 0: the reference's scan
     int64_t records = -1;         // 16-byte edge records (neighbour id + its row span; the walk then needs no row-index loads): 1 always, 0 never,
                                   // -1 kept graphs always, one-shot calls when the walk is long enough to repay one pass over col_idx (csr_one_shot_needs)
     int64_t build_mode = 2;       // table build: 2 assembled in shared memory (tiles + hub segments); 0 global CAS (A/B baseline)
@@ -30,7 +31,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(n2v_mix) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb)
 
 Options& options();
 void count_launch(int n);

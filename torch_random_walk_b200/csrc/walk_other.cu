@@ -6,6 +6,14 @@
 // edge-list walk, the acceptance chain of rw_cuda_edge_list.cu:203-230 whose empirical
 // distribution differs from textbook node2vec: parity for that path is
 // defined against the reference, so its rule is reproduced rather than "fixed".
+//
+// The reference tests "x is a neighbour of t" by scanning t's out-edges (rw_cuda_edge_list.cu:98-123),
+// O(deg(t)) per rejection trial: 1-4 M steps/s on a power-law graph.  With a workspace
+// (trw_walk_edge_list_ws) the edge list is viewed as a CSR -- tails copied contiguously, row starts
+// found by bisection of the sorted heads -- and the CSR walk's hashed membership table
+// (member_table.cuh) answers the test with one sector, reference quirk included (see
+// el_is_neighbor_table).  Same draws, same decisions: the walks are bit-identical to the scan path.
+#include "member_table.cuh"
 #include "trw_common.cuh"
 #include "trw_options.h"
 
@@ -25,6 +33,11 @@ struct IndexedWalkArgs {
     int64_t* out;
     int64_t out_row_stride;
     uint64_t thr0, thr1, thr2;
+    // membership table over the CSR view of the edge list (all null: scan, as the reference does)
+    const int64_t* col;            // tails, contiguous: col[k] = rows[2k+1]
+    const uint32_t* table;
+    const int* table_failed;       // a hub segment overflowed during the build
+    const int* view_mismatch;      // node_edge_index disagrees with the bisection of the heads (or heads unsorted)
 };
 
 // Inclusive row range of node v; false when v has no rows (or lies outside the index, which the
@@ -60,6 +73,49 @@ __device__ __forceinline__ bool el_is_neighbor(const IndexedWalkArgs& a, int64_t
     return false;
 }
 
+// The same answer from the hashed table.  The reference's scan stops BEFORE the last out-edge of t
+// (half-open [first, last) over an inclusive range: rw_cuda_edge_list.cu:112).  The table holds the
+// whole row, every entry of it, so when x is that last tail it counts only if it is stored twice.
+__device__ __forceinline__ bool el_is_neighbor_table(const IndexedWalkArgs& a, int64_t x, int64_t t, uint64_t pol_stream) {
+    int64_t first, last;
+    if (!row_range(a, t, first, last)) return false;
+    if (last <= first) return false;  // one out-edge: the scanned range is empty
+    if (!is_member<true>(x, first, last + 1, a.col, a.table, pol_stream)) return false;
+    if (ldg64_hint(a.col + last, pol_stream) != x) return true;
+    return member_twice(x, first, last + 1, a.table, pol_stream);
+}
+
+// CSR view of an edge list sorted by head: contiguous tails, row starts by bisection of the heads,
+// and a check that node_edge_index says the same (it is what the walk samples from).
+__global__ void __launch_bounds__(256) edge_list_view_kernel(const int64_t* __restrict__ rows, int64_t n_rows,
+                                                             const int64_t* __restrict__ index, int64_t n_index_rows,
+                                                             int64_t* __restrict__ col, int64_t* __restrict__ row_ptr,
+                                                             int* __restrict__ mismatch) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = gtid; k < n_rows; k += gsz) {
+        col[k] = ldg64_stream(rows + 2 * k + 1);
+        if (k + 1 < n_rows && __ldg(rows + 2 * k) > __ldg(rows + 2 * k + 2)) *mismatch = 1;  // heads not sorted
+    }
+    auto lower_bound = [&](int64_t v) {  // first edge whose head is >= v
+        int64_t lo = 0, hi = n_rows;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(rows + 2 * mid) < v) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    for (int64_t v = gtid; v <= n_index_rows; v += gsz) {
+        const int64_t b = lower_bound(v);
+        row_ptr[v] = v == n_index_rows ? n_rows : b;  // edges whose head lies outside the index belong to no row
+        if (v == n_index_rows) break;
+        const int64_t e = lower_bound(v + 1);
+        const int64_t first = __ldg(index + 2 * v), last = __ldg(index + 2 * v + 1);
+        const bool has = !(first == -1 || last == -1);
+        if (has ? (first != b || last + 1 != e) : (b != e)) *mismatch = 1;
+    }
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) edge_list_uniform_kernel(const IndexedWalkArgs a) {
     __shared__ int64_t ring[4][BLOCK];
@@ -88,6 +144,10 @@ __global__ void __launch_bounds__(BLOCK) edge_list_biased_kernel(const IndexedWa
     __shared__ int64_t ring[4][BLOCK];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= a.n_walks) return;
+    // the table is used only when its build succeeded and the CSR view agrees with node_edge_index;
+    // any doubt selects the reference's scan (same results, slower)
+    const bool use_table = a.table != nullptr && *a.table_failed == 0 && *a.view_mismatch == 0;
+    const uint64_t pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
     RowStager<BLOCK> o;
@@ -118,7 +178,7 @@ __global__ void __launch_bounds__(BLOCK) edge_list_biased_kernel(const IndexedWa
             accept = true;                      // return edge (rw_cuda_edge_list.cu:203-208)
         } else if (x == a.pad) {                // separate `if` in the source: reached after a rejected return too
             if (u < a.thr0) { accept = true; sel = jump; }
-        } else if (el_is_neighbor(a, x, t)) {
+        } else if (use_table ? el_is_neighbor_table(a, x, t, pol_stream) : el_is_neighbor(a, x, t)) {
             accept = u < a.thr1;
         } else {
             accept = u < a.thr2;
@@ -177,11 +237,35 @@ static uint64_t threshold(double prob) {
 
 using namespace trw;
 
-extern "C" int trw_walk_edge_list(const int64_t* edge_list, int64_t n_edges, const int64_t* node_edge_index,
-                                  int64_t n_index_rows, const int64_t* targets, int64_t n_walks,
-                                  int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
-                                  int64_t padding_idx, int restart, int64_t* out, int64_t out_row_stride, int device,
-                                  void* stream) {
+namespace trw {
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct EdgeListWorkspace {
+    size_t col, row_ptr, flags, csr, total;
+    CsrWorkspace w;
+};
+static EdgeListWorkspace edge_list_workspace_layout(int64_t n_edges, int64_t n_index_rows) {
+    EdgeListWorkspace l{};
+    l.w = csr_workspace_layout(n_index_rows, n_edges, /*uniform=*/false, /*records=*/false);
+    size_t off = 0;
+    l.col = off; off += align256((size_t)n_edges * 8);
+    l.row_ptr = off; off += align256((size_t)(n_index_rows + 1) * 8);
+    l.flags = off; off += 256;
+    l.csr = off; off += l.w.total;
+    l.total = (l.w.has_table && n_edges > 0 && n_index_rows > 0) ? off : 0;
+    return l;
+}
+}  // namespace trw
+
+extern "C" size_t trw_walk_edge_list_workspace_bytes(int64_t n_edges, int64_t n_index_rows, double p, double q) {
+    if (n_edges < 0 || n_index_rows < 0 || (p == 1.0 && q == 1.0) || options().el_table == 0) return 0;
+    return edge_list_workspace_layout(n_edges, n_index_rows).total;
+}
+
+extern "C" int trw_walk_edge_list_ws(const int64_t* edge_list, int64_t n_edges, const int64_t* node_edge_index,
+                                     int64_t n_index_rows, const int64_t* targets, int64_t n_walks,
+                                     int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
+                                     int64_t padding_idx, int restart, int64_t* out, int64_t out_row_stride,
+                                     void* workspace, size_t workspace_bytes, int device, void* stream) {
     if (n_walks < 0 || n_edges < 0 || n_index_rows < 0 || walk_length < 0 || out_row_stride < (int64_t)walk_length + 1) {
         set_error("trw_walk_edge_list: negative size or out_row_stride < walk_length+1");
         return TRW_ERR_ARG;
@@ -196,7 +280,7 @@ extern "C" int trw_walk_edge_list(const int64_t* edge_list, int64_t n_edges, con
     if (n_walks == 0) return TRW_OK;
     DeviceGuard guard(d);
     if (!guard.ok) { set_error("trw_walk_edge_list: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }
-    IndexedWalkArgs a;
+    IndexedWalkArgs a{};
     a.rows = edge_list; a.n_rows = n_edges; a.index = node_edge_index; a.n_index_rows = n_index_rows;
     a.targets = targets; a.n_walks = n_walks; a.walk_id_offset = walk_id_offset; a.walk_length = walk_length;
     a.key = philox_key(seed, kTagWalkEdgeList); a.pad = padding_idx; a.restart = restart ? 1 : 0;
@@ -206,10 +290,48 @@ extern "C" int trw_walk_edge_list(const int64_t* edge_list, int64_t n_edges, con
     constexpr int BLOCK = 256;
     const unsigned grid = (unsigned)((n_walks + BLOCK - 1) / BLOCK);
     cudaStream_t st = (cudaStream_t)stream;
-    if (p == 1.0 && q == 1.0) edge_list_uniform_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a);  // rw_cuda_edge_list.cu:281
+    const bool uniform = (p == 1.0 && q == 1.0);  // rw_cuda_edge_list.cu:281
+    // (the table must hold every entry of a row, duplicates included: only the shared-memory build does)
+    if (!uniform && workspace != nullptr && options().el_table != 0 && options().build_mode != 0) {
+        const EdgeListWorkspace l = edge_list_workspace_layout(n_edges, n_index_rows);
+        if (l.total > 0) {
+            if (workspace_bytes < l.total || ((uintptr_t)workspace & 255)) {
+                set_error("trw_walk_edge_list_ws: workspace needs %zu bytes at 256-byte alignment (got %zu)", l.total, workspace_bytes);
+                return TRW_ERR_WORKSPACE;
+            }
+            char* ws = (char*)workspace;
+            int64_t* col = (int64_t*)(ws + l.col);
+            int64_t* row_ptr = (int64_t*)(ws + l.row_ptr);
+            int* mismatch = (int*)(ws + l.flags);
+            int rc = check_cuda(cudaMemsetAsync(mismatch, 0, 256, st), "edge-list flags memset");
+            if (rc) return rc;
+            edge_list_view_kernel<<<sm_count(d) * 8, 256, 0, st>>>(edge_list, n_edges, node_edge_index, n_index_rows, col, row_ptr, mismatch);
+            count_launch(1);
+            rc = check_cuda(cudaGetLastError(), "edge-list view launch");
+            if (rc) return rc;
+            CsrPrepared prepared;
+            rc = csr_prepare_device(row_ptr, col, n_index_rows, n_edges, ws + l.csr, l.w, /*want_table=*/true, /*want_row32=*/false,
+                                    /*want_strict=*/false, /*want_records=*/false, (int)options().build_mode, d, st, &prepared);
+            if (rc) return rc;
+            if (prepared.table) {
+                a.col = col; a.table = prepared.table; a.table_failed = prepared.table_failed;
+                a.view_mismatch = mismatch;
+            }
+        }
+    }
+    if (uniform) edge_list_uniform_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a);
     else edge_list_biased_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "edge-list walk launch");
+}
+
+extern "C" int trw_walk_edge_list(const int64_t* edge_list, int64_t n_edges, const int64_t* node_edge_index,
+                                  int64_t n_index_rows, const int64_t* targets, int64_t n_walks,
+                                  int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
+                                  int64_t padding_idx, int restart, int64_t* out, int64_t out_row_stride, int device,
+                                  void* stream) {
+    return trw_walk_edge_list_ws(edge_list, n_edges, node_edge_index, n_index_rows, targets, n_walks, walk_id_offset, p, q,
+                                 walk_length, seed, padding_idx, restart, out, out_row_stride, nullptr, 0, device, stream);
 }
 
 extern "C" int trw_walk_triples(const int64_t* triples, int64_t n_triples, const int64_t* relation_tail_index,
@@ -231,7 +353,7 @@ extern "C" int trw_walk_triples(const int64_t* triples, int64_t n_triples, const
     if (n_walks == 0) return TRW_OK;
     DeviceGuard guard(d);
     if (!guard.ok) { set_error("trw_walk_triples: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }
-    IndexedWalkArgs a;
+    IndexedWalkArgs a{};
     a.rows = triples; a.n_rows = n_triples; a.index = relation_tail_index; a.n_index_rows = n_index_rows;
     a.targets = targets; a.n_walks = n_walks; a.walk_id_offset = walk_id_offset; a.walk_length = walk_length;
     a.key = philox_key(seed, kTagWalkTriples); a.pad = padding_idx; a.restart = 0;

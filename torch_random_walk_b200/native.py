@@ -53,6 +53,10 @@ def _load():
                                       _c_i64, _c_ptr, _c_int]
     lib.trw_walk_edge_list.argtypes = [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
                                        _c_i64, _c_i64, _c_int, _c_ptr, _c_i64, _c_int, _c_ptr]
+    lib.trw_walk_edge_list_workspace_bytes.restype = _c_size
+    lib.trw_walk_edge_list_workspace_bytes.argtypes = [_c_i64, _c_i64, _c_dbl, _c_dbl]
+    lib.trw_walk_edge_list_ws.argtypes = [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
+                                          _c_i64, _c_i64, _c_int, _c_ptr, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr]
     lib.trw_walk_triples.argtypes = [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_int,
                                      _c_i64, _c_ptr, _c_i64, _c_int, _c_ptr]
     win = [_c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
@@ -266,9 +270,12 @@ def walk_edge_list(edge_list_indexed, node_edges_idx, target_nodes, p, q, walk_l
     n, wl = tg.size(0), int(walk_length) + 1
     with torch.cuda.device(dev):
         walks = torch.empty((n, wl), dtype=torch.int64, device=dev)
-        _check(_lib.trw_walk_edge_list(_ptr(el), el.size(0), _ptr(nei), nei.size(0), _ptr(tg), n, int(walk_id_offset),
-                                       float(p), float(q), int(walk_length), int(seed), int(padding_idx),
-                                       1 if restart else 0, _ptr(walks), wl, dev.index, _stream(dev)))
+        need = _lib.trw_walk_edge_list_workspace_bytes(el.size(0), nei.size(0), float(p), float(q)) if n else 0
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
+        _check(_lib.trw_walk_edge_list_ws(_ptr(el), el.size(0), _ptr(nei), nei.size(0), _ptr(tg), n, int(walk_id_offset),
+                                          float(p), float(q), int(walk_length), int(seed), int(padding_idx),
+                                          1 if restart else 0, _ptr(walks), wl, _ptr(ws) if ws is not None else None, need,
+                                          dev.index, _stream(dev)))
     return walks
 
 
