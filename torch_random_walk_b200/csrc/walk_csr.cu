@@ -123,6 +123,13 @@ __global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a
     }
 }
 
+// Elements per cooperative output store piece of the node2vec kernel.  Measured in one run on the benchmark
+// graph (boxes differ by +-2 %): the plain-rejection variant is 1 % faster with 64-byte pieces and the L1 they
+// leave free (26.14 vs 26.43 ms on C3; option n2v_slots for the A/B), the mixture/folding variants with whole
+// lines (40.0 vs 40.8 ms at p=0.5 q=2).
+template <bool FOLD>
+constexpr int kN2vSlots = FOLD ? 16 : 8;
+
 // Second-order walk.  One iteration of the loop = one rejection trial of this thread's walk.
 //
 // FOLD (used when the return edge carries the largest weight, 1/p > max(1, 1/q)): plain rejection
@@ -135,14 +142,14 @@ __global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a
 // a point in bar x at height h is accepted iff h < min(w(x), M').  Every neighbour is therefore
 // still drawn with probability proportional to its node2vec weight (t: M' + e = 1/p).  This is
 // only exact when no edge is stored twice, which the prepare step verifies (strict_counts).
-template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32, bool FOLD, bool REC>
+template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32, bool FOLD, bool REC, int SLOTS = kN2vSlots<FOLD>>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const WalkArgs a) {
-    __shared__ int64_t ring[RowOutSmem<BLOCK, STAGE>::kWords];
+    __shared__ int64_t ring[RowOutSmem<BLOCK, STAGE, SLOTS>::kWords];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = i < a.n_walks;  // lanes past the end stay for the warp-collective stores
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
-    RowOut<BLOCK, STAGE> o;
+    RowOut<BLOCK, STAGE, SLOTS> o;
     o.init(ring, a.out + (live ? i : 0) * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
     const int L = a.walk_length;
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
@@ -350,6 +357,7 @@ static void launch_n2v3(const WalkArgs& a, bool speculate, bool fold, cudaStream
     const unsigned grid = (unsigned)((a.n_walks + BLOCK - 1) / BLOCK);
     if (fold) TRW_LAUNCH((node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, true, REC>), 0, grid, BLOCK, st, a);
     else if (speculate && !REC) TRW_LAUNCH((node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, true, ROW32, false, false>), 0, grid, BLOCK, st, a);
+    else if (REC && STAGE && options().n2v_slots == 16) TRW_LAUNCH((node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, false, REC, 16>), 0, grid, BLOCK, st, a);
     else TRW_LAUNCH((node2vec_walk_kernel<BLOCK, MIN_CTAS, STAGE, TABLE, false, ROW32, false, REC>), 0, grid, BLOCK, st, a);
 }
 
