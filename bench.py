@@ -589,7 +589,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "walk_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": wl["desc"], "p": p, "q": q, "walk_length": L, "n_nodes": n_nodes, "nnz": nnz,
                        "walks_per_gpu": n_walks, "start_nodes": "all nodes with degree>0, one walk each per GPU",

@@ -90,7 +90,7 @@ def test_shards_are_bit_identical_to_one_call(native, p, q):
 
 
 DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": -1, "n2v_fold": 1,
-            "records": -1}
+            "records": -1, "n2v_slots": 8}
 
 
 def test_kernel_variants_agree_bit_for_bit(native):
@@ -101,7 +101,7 @@ def test_kernel_variants_agree_bit_for_bit(native):
     rp, ci = cuda(rp, ci)
     nodes = torch.arange(4000, device="cuda")
     variants = [{}, {"records": 1}, {"records": 0}, {"records": 0, "n2v_table": 0}, {"records": 1, "n2v_table": 0},
-                {"records": 1, "n2v_min_ctas": 4}, {"n2v_min_ctas": 5}, {"smem_carveout_kb": 64}, {"n2v_table": 0}, {"n2v_speculate": 0}, {"n2v_speculate": 1}, {"stage_output": 0}, {"row32": 0},
+                {"records": 1, "n2v_min_ctas": 4}, {"records": 1, "n2v_slots": 16}, {"n2v_min_ctas": 5}, {"smem_carveout_kb": 64}, {"n2v_table": 0}, {"n2v_speculate": 0}, {"n2v_speculate": 1}, {"stage_output": 0}, {"row32": 0},
                 {"build_mode": 0}, {"n2v_min_ctas": 5}, {"n2v_min_ctas": 6},
                 {"n2v_table": 0, "row32": 0, "stage_output": 0}, {"build_mode": 0, "row32": 0, "n2v_min_ctas": 6}]
     base = None
