@@ -24,7 +24,9 @@
 //     request per line; the loops are therefore warp-converged, one trial per lane per iteration.
 // Everything derived from the graph alone (csr_graph_prepare) is separate from the per-call plan
 // (csr_walk_plan), so it is built per call by trw_walk_csr and once by trw_csr_graph_prepare.
+#include <mutex>
 #include <new>
+#include <unordered_map>
 
 #include "member_table.cuh"
 #include "trw_common.cuh"
@@ -336,7 +338,17 @@ template <typename K>
 static void set_carveout(K kernel, int64_t kb) {
     int pct = kb <= 0 ? (int)cudaSharedmemCarveoutDefault : (int)(kb * 100 / 228);  // rounded down: the driver rounds up to a configuration
     if (pct > 100) pct = 100;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    // one attribute call per kernel, device and value, not one per launch (K is the same pointer type for every
+    // instantiation, so the cache is keyed by the function's address)
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, int> last;
+    int d = 0;
+    cudaGetDevice(&d);
+    const uint64_t key = (uint64_t)(uintptr_t)reinterpret_cast<const void*>(kernel) ^ ((uint64_t)(uint32_t)d << 56);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = last.find(key);
+    if (it != last.end() && it->second == pct) return;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) == cudaSuccess) last[key] = pct;
 }
 #define TRW_LAUNCH(kernel, carveout_kb, grid, block, st, args)                                              \
     do {                                                                                                    \
