@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import torch

@@ -10,7 +10,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from torch_random_walk_b200 import native, rmat, rw, utils  # noqa: E402
+from torch_random_walk_b200 import rmat, rw, utils  # noqa: E402
 
 
 def main():
