@@ -443,6 +443,34 @@ def test_second_order_statistics_with_table_rows(rw, native, orc, p, q, opts):
     assert chi2_pvalue(chi2_2, dof_2) > 0.01, (chi2_2, dof_2)
 
 
+@pytest.mark.parametrize("p,q,opts", [(0.5, 2.0, {}), (0.5, 2.0, {"records": 1}), (0.25, 0.5, {}), (1.0, 0.5, {"records": 1})])
+def test_second_order_statistics_on_a_directed_graph(rw, native, orc, p, q, opts):
+    """A directed graph: t -> v does not imply v -> t, so the return edge and the common-neighbour
+    class are decided by adj(v) and adj(t) separately -- the mixture's third term (t accepted iff t is
+    a neighbour of v) and its t-side proposals (accepted iff in adj(v)) have to get this right."""
+    rp, ci = random_csr(17, 50, 24, symmetric=False)
+    n = 50
+    deg = (rp[1:] - rp[:-1])
+    assert int(deg.min()) >= 12  # no dead ends, every row through the hashed table
+    table = node2vec_probs(rp, ci, p, q)
+    nodes = torch.arange(n).repeat_interleave(3000)
+    for k, v in opts.items():
+        native.set_option(k, v)
+    try:
+        walks = rw.walk(rp.cuda(), ci.cuda(), nodes.cuda(), p, q, 80, 23)
+    finally:
+        for k in opts:
+            native.set_option(k, {"records": -1}.get(k, 1))
+    check_walks_follow_edges(walks, rp, ci, nodes)
+    got = second_order_counts(walks, n)
+    chi2, dof, tv = chi2_and_tv(got, table, n)
+    assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
+    assert _class_tv(got, rp, ci, p, q, n) < 1e-2
+    ref_counts = second_order_counts(orc.walk(rp, ci, torch.arange(n).repeat_interleave(300), p, q, 80, 3), n)
+    chi2_2, dof_2 = two_sample_chi2(got, ref_counts, n)
+    assert chi2_pvalue(chi2_2, dof_2) > 0.01, (chi2_2, dof_2)
+
+
 def test_large_graph_structure_and_hubs(rw):
     """A skewed graph (R-MAT scale 16) at a size where hubs, the table build's tile logic and many
     CTAs are all exercised; size-independent property: every transition is an edge."""
