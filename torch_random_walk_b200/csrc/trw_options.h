@@ -6,14 +6,14 @@
 namespace trw {
 
 struct Options {
-    int64_t stage_output = 1;     // 1: 256-bit sector stores via the shared-memory ring; 0: plain 8-byte stores
+    int64_t stage_output = 1;     // 1: CSR walk output staged in shared memory and written as whole lines by the warp (LineStager); 0: plain 8-byte stores
     int64_t n2v_table = 1;        // 1: hashed adjacency membership (needs workspace); 0: linear scan of adj(t)
     int64_t n2v_speculate = -1;   // fetch row_ptr[x] before the membership answer is known: 1 yes, 0 no, -1 by (p,q)
     int64_t n2v_fold = 1;         // 1: fold the return edge out of the rejection envelope when 1/p > max(1, 1/q)
     int64_t n2v_slots = 8;        // A/B: 16 selects whole-line store pieces for the plain-rejection kernel with records (default 64-byte pieces)
     int64_t n2v_mix = 1;          // 1: two-sided mixture sampling when q > 1 and p <= q (duplicate-free rows; see node2vec_walk_kernel)
     int64_t n2v_min_ctas = -1;    // __launch_bounds__ min CTAs/SM of the node2vec kernel (4, 5 or 6; -1: 5 with edge records, else 4)
-    int64_t row32 = 1;            // 1: re-encode row_ptr as uint32 offsets per call (needs workspace)
+    int64_t row32 = 1;            // 1: re-encode row_ptr as uint32 offsets (needs workspace; the edge records depend on it)
     int64_t el_table = 1;         // 1: edge-list node2vec walks test membership through the hashed table (needs workspace); 0: the reference's scan
     int64_t records = -1;         // 16-byte edge records (neighbour id + its row span; the walk then needs no row-index loads): 1 always, 0 never,
                                   // -1 kept graphs always, one-shot calls when the walk is long enough to repay one pass over col_idx (csr_one_shot_needs)
