@@ -305,6 +305,11 @@ def test_edge_cases(rw, native):
     assert (big[:, 0] == -7).all() and (big[:, 10:] == -7).all()
     with pytest.raises(RuntimeError, match="Long"):
         rw.walk(rp.int(), ci, nodes, 1.0, 1.0, 3, 1)
+    for bad in (torch.empty((100, 8), dtype=torch.int64, device="cuda"), torch.empty((99, 9), dtype=torch.int64, device="cuda"),
+                torch.empty((100, 9), dtype=torch.int32, device="cuda"), torch.empty((100, 9), dtype=torch.int64),
+                torch.empty((100, 18), dtype=torch.int64, device="cuda")[:, ::2]):
+        with pytest.raises(RuntimeError, match="out must"):
+            native.walk(rp, ci, nodes, 0.5, 2.0, 8, 11, out=bad)
     # non-contiguous inputs are accepted (the reference reads through strided accessors)
     w = rw.walk(rp, ci, torch.arange(100, device="cuda")[::2], 1.0, 1.0, 4, 1)
     check_walks_follow_edges(w, rp, ci, torch.arange(100, device="cuda")[::2])

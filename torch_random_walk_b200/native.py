@@ -128,6 +128,18 @@ def reset_launch_count():
     _lib.trw_reset_launch_count()
 
 
+def _check_out(out, n, wl, dev):
+    """`out=` is an extension of this binding (the reference always allocates): refuse anything the kernels would
+    write outside of."""
+    if out is None:
+        return
+    if not (isinstance(out, torch.Tensor) and out.is_cuda and out.device == dev and out.dtype == torch.int64):
+        raise RuntimeError("out must be an int64 CUDA tensor on the graph's device")
+    if out.dim() != 2 or out.size(0) != n or out.size(1) != wl or (n and wl > 1 and out.stride(1) != 1) or \
+            (n > 1 and out.stride(0) < wl):
+        raise RuntimeError(f"out must have shape ({n}, {wl}) with unit column stride and non-overlapping rows")
+
+
 class PreparedCsr:
     """A CSR graph prepared once for any number of walks (trw_csr_graph_prepare): the uint32 row
     index, the membership table, the duplicate-edge check and the edge records live in a workspace
@@ -157,6 +169,7 @@ class PreparedCsr:
         dev = self.device
         target_nodes = target_nodes.contiguous()
         n, wl = target_nodes.size(0), int(walk_length) + 1
+        _check_out(out, n, wl, dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             if stream.cuda_stream != self._stream_id:  # prepared on another stream: order after it, tell the allocator
@@ -247,6 +260,7 @@ def walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_off
         _seen_once[dev.index] = sig
     row_ptr, column_idx, target_nodes = row_ptr.contiguous(), column_idx.contiguous(), target_nodes.contiguous()
     n, wl = target_nodes.size(0), int(walk_length) + 1
+    _check_out(out, n, wl, dev)
     with torch.cuda.device(dev):
         walks = torch.empty((n, wl), dtype=torch.int64, device=dev) if out is None else out
         need = _lib.trw_walk_csr_workspace_bytes_for(n_nodes, nnz, float(p), float(q), n, int(walk_length)) if n else 0
