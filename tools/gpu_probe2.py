@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from torch_random_walk_b200 import native, rmat  # noqa: E402
 
 DEFAULTS = {"stage_output": 1, "n2v_table": 1, "n2v_speculate": -1, "persist_row_ptr": 0, "row32": 1, "build_mode": 2,
-            "n2v_min_ctas": 4, "persist_l2_mb": 64}
+            "n2v_min_ctas": -1, "persist_l2_mb": 64}
 
 
 def timed(fn, reps=3, warm=1):
@@ -79,6 +79,7 @@ def main():
     print(res["graph"], flush=True)
     out = torch.empty((n_walks, L + 1), dtype=torch.int64, device="cuda")
     native.set_option("time_kernels", 1)
+    native.set_graph_cache(False)  # every variant builds with its own options
     variants = {}
 
     def run(name, p, q, opts):
