@@ -190,6 +190,8 @@ def run_reference_arm(args, wl):
     fn, kind = cpu_walk_fn()
     cores = os.cpu_count() or 1
     per_step_budget = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    if os.environ.get("TRW_BENCH_CPU_BUDGET_S"):  # tests shrink the CPU sample
+        per_step_budget = float(os.environ["TRW_BENCH_CPU_BUDGET_S"])
     results = {}
     for threads in sorted({1, cores}):
         best = 0.0
