@@ -586,3 +586,40 @@ def test_walk_host_matches_device_path(native):
             assert host.device.type == "cpu" and torch.equal(host, dev.cpu())
     finally:
         native.set_option("host_chunk_walks", 1 << 20)
+
+
+def test_walk_host_wire_formats_agree(native):
+    """The host path sends col_idx and fetches the walks as uint32 when it has the threads for it; the
+    int64 copies, the compressed path over several upload and download chunks, pageable and pinned
+    buffers, and the fallback for an id that needs more than 32 bits must all give the device path's walks."""
+    rp, ci = random_csr(9, 20000, 16)  # ~320 k CSR entries: five upload chunks of 65,536
+    nodes = torch.randint(0, 20000, (25000,))
+    dev = native.walk(rp.cuda(), ci.cuda(), nodes.cuda(), 1.0, 0.5, 21, 7, cache=False).cpu()
+    saved = {k: native.get_option(k) for k in ("host_chunk_walks", "host_up_chunk", "host_threads", "host_compress")}
+    try:
+        native.set_option("host_chunk_walks", 4000)
+        native.set_option("host_up_chunk", 1 << 16)
+        native.set_option("host_threads", 8)  # enough to switch the compression on whatever the machine has
+        for compress in (1, 0):
+            native.set_option("host_compress", compress)
+            assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 21, 7, device=0), dev), compress
+        native.set_option("host_compress", 1)
+        pinned_out = torch.empty((25000, 22), dtype=torch.int64, pin_memory=True)
+        pageable_out = torch.empty((25000, 22), dtype=torch.int64)
+        for out in (pinned_out, pageable_out):
+            native.walk_host(rp.pin_memory(), ci.pin_memory(), nodes, 1.0, 0.5, 21, 7, device=0, out=out)
+            assert torch.equal(out, dev)
+        # one neighbour id beyond 32 bits in the last upload chunk: the call must notice and use plain copies
+        wide = ci.clone()
+        wide[-3] = (1 << 33) + 5
+        ref = native.walk(rp.cuda(), wide.cuda(), nodes.cuda(), 1.0, 0.5, 21, 7, cache=False).cpu()
+        assert torch.equal(native.walk_host(rp, wide, nodes, 1.0, 0.5, 21, 7, device=0), ref)
+        # and a start node beyond 32 bits (outside the graph: the walk stays there)
+        far = nodes.clone()
+        far[17] = (1 << 35) + 1
+        ref = native.walk(rp.cuda(), ci.cuda(), far.cuda(), 1.0, 1.0, 21, 7, cache=False).cpu()
+        got = native.walk_host(rp, ci, far, 1.0, 1.0, 21, 7, device=0)
+        assert torch.equal(got, ref) and bool((got[17] == (1 << 35) + 1).all())
+    finally:
+        for k, v in saved.items():
+            native.set_option(k, v)
