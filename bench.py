@@ -515,7 +515,7 @@ def main():
                    "d2h_bytes_per_step": int(out_h.numel() * 8), "steps": args.e2e_steps,
                    "api": "native.walk_host -> trw_walk_csr_host (pinned host tensors in, pinned host walks out); h2d/d2h bytes are "
                           "the caller's int64 tensors -- the library sends col_idx and fetches the walks as uint32 when every id fits "
-                          "and it has >= 8 host threads to convert with (option host_compress)"}
+                          "and it has >= 12 host threads to convert with (option host_compress)"}
             # the device path and the host path must agree on the result
             check = native.walk(row_ptr, col_idx, targets[:4096].contiguous(), p, q, L, 3000 + args.e2e_steps - 1,
                                 walk_id_offset=offset)

@@ -599,7 +599,7 @@ def test_walk_host_wire_formats_agree(native):
     try:
         native.set_option("host_chunk_walks", 4000)
         native.set_option("host_up_chunk", 1 << 16)
-        native.set_option("host_threads", 8)  # enough to switch the compression on whatever the machine has
+        native.set_option("host_threads", 12)  # enough to switch the compression on whatever the machine has
         for compress in (1, 0):
             native.set_option("host_compress", compress)
             assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 21, 7, device=0), dev), compress

@@ -21,7 +21,7 @@ struct Options {
     int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
     int64_t host_chunk_walks = 1 << 20;  // walks per pipelined chunk in trw_walk_csr_host
-    int64_t host_compress = 1;    // 1: trw_walk_csr_host sends col_idx and fetches the walks as uint32 when ids fit and >= 8 host threads are free
+    int64_t host_compress = 1;    // 1: trw_walk_csr_host sends col_idx and fetches the walks as uint32 when ids fit and >= 12 host threads are free
     int64_t host_threads = 0;     // host threads of the wire compression (0: the machine's, divided by LOCAL_WORLD_SIZE)
     int64_t host_up_chunk = 1 << 25;  // col_idx entries per compressed upload chunk
     int64_t host_cache_buffers = 1;  // 1: trw_walk_csr_host keeps its device buffers between calls
