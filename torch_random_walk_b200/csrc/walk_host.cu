@@ -97,8 +97,14 @@ template <class F>
 static void parallel_for(int n_threads, F f) {
     std::vector<std::thread> workers;
     workers.reserve(n_threads > 1 ? n_threads - 1 : 0);
-    for (int t = 1; t < n_threads; ++t) workers.emplace_back(f, t, n_threads);
+    int started = 1;  // slice 0 is the caller's
+    try {
+        for (; started < n_threads; ++started) workers.emplace_back(f, started, n_threads);
+    } catch (...) {
+        // the system refused a thread: the caller works through the slices that got none
+    }
     f(0, n_threads);
+    for (int t = started; t < n_threads; ++t) f(t, n_threads);
     for (auto& w : workers) w.join();
 }
 
