@@ -21,7 +21,18 @@ def main():
     n = rp.numel() - 1
     deg = rp[1:] - rp[:-1]
     el = torch.stack((torch.repeat_interleave(torch.arange(n, device="cuda"), deg), ci), 1).contiguous()
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     nei, el = utils.build_node_edge_index(el, torch.arange(n))
+    torch.cuda.synchronize()
+    print(f"utils.build_node_edge_index on the device: {el.size(0)} edges, {n} nodes in {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
+    t0 = time.perf_counter()
+    rp2, ci2 = utils.csr_from_edge_index(el, n)
+    torch.cuda.synchronize()
+    print(f"utils.csr_from_edge_index on the device: {(time.perf_counter() - t0) * 1e3:.1f} ms "
+          f"(same CSR as the generator's: {bool(torch.equal(rp2, rp) and torch.equal(ci2, ci))})", flush=True)
+    del rp2, ci2
     starts = torch.nonzero(deg > 0).flatten()
     for name, p, q, count in (("first-order", 1.0, 1.0, starts.numel()), ("node2vec p=0.5 q=2", 0.5, 2.0, args.walks),
                               ("node2vec p=1 q=0.5", 1.0, 0.5, args.walks)):
