@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TRW_ABI_VERSION 2
+#define TRW_ABI_VERSION 3
 
 enum {
     TRW_OK = 0,
@@ -104,6 +104,11 @@ int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* targets, in
                           int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
                           int64_t* out, int64_t out_row_stride, void* stream);
 void trw_csr_graph_destroy(trw_csr_graph* graph);
+/* What a prepared graph holds, after waiting for `stream` (the stream it was prepared on):
+ * out[0] membership table, out[1] edge records, out[2] bits of the L2-resident edge filter (0: none),
+ * out[3] triangle Blooms computed, out[4] graph symmetric (1 yes, 0 no, -1 not checked),
+ * out[5] table build overflowed (the walk then scans).  n_out >= 6. */
+int trw_csr_graph_info(const trw_csr_graph* graph, void* stream, int64_t* out, int n_out);
 
 /* Same computation with every buffer in HOST memory (pinned or pageable): stages the graph and
  * the start nodes to the device, walks in chunks and streams finished chunks back while the

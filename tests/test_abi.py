@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 16
     for name in names:
         assert getattr(lib, name) is not None, name
-    assert lib.trw_abi_version() == 2
+    assert lib.trw_abi_version() == 3
 
 
 def test_library_has_no_torch_or_oracle_dependency():

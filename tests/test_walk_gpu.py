@@ -90,7 +90,7 @@ def test_shards_are_bit_identical_to_one_call(native, p, q):
 
 
 DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": -1, "n2v_fold": 1,
-            "records": -1, "n2v_slots": 8}
+            "records": -1, "n2v_slots": 8, "edge_filter_mb": 64}
 
 
 def test_kernel_variants_agree_bit_for_bit(native):
@@ -102,7 +102,8 @@ def test_kernel_variants_agree_bit_for_bit(native):
     nodes = torch.arange(4000, device="cuda")
     variants = [{}, {"records": 1}, {"records": 0}, {"records": 0, "n2v_table": 0}, {"records": 1, "n2v_table": 0},
                 {"records": 1, "n2v_min_ctas": 4}, {"records": 1, "n2v_slots": 16}, {"n2v_min_ctas": 5}, {"smem_carveout_kb": 64}, {"n2v_table": 0}, {"n2v_speculate": 0}, {"n2v_speculate": 1}, {"stage_output": 0}, {"row32": 0},
-                {"build_mode": 0}, {"n2v_min_ctas": 5}, {"n2v_min_ctas": 6},
+                {"build_mode": 0}, {"n2v_min_ctas": 5}, {"n2v_min_ctas": 6}, {"edge_filter_mb": 0}, {"edge_filter_mb": 1},
+                {"edge_filter_mb": 0, "records": 1}, {"edge_filter_mb": 1, "records": 0},
                 {"n2v_table": 0, "row32": 0, "stage_output": 0}, {"build_mode": 0, "row32": 0, "n2v_min_ctas": 6}]
     base = None
     try:
@@ -131,6 +132,12 @@ def test_table_build_on_skewed_graph_matches_scan(native):
     assert int(deg.max()) >= 2048  # hub rows take the global-CAS path of the tiled build
     a = native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1)
     try:
+        # a filter so small that it is saturated ("maybe" for nearly every pair), and none at all
+        native.set_option("edge_filter_mb", 1)
+        assert torch.equal(a, native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1))
+        native.set_option("edge_filter_mb", 0)
+        assert torch.equal(a, native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1))
+        native.set_option("edge_filter_mb", 64)
         native.set_option("build_mode", 0)
         b = native.walk(rp, ci, nodes, 0.5, 2.0, 12, 1)
         native.set_option("n2v_table", 0)
@@ -138,6 +145,7 @@ def test_table_build_on_skewed_graph_matches_scan(native):
     finally:
         native.set_option("build_mode", 2)
         native.set_option("n2v_table", 1)
+        native.set_option("edge_filter_mb", 64)
     assert torch.equal(a, b)
     assert torch.equal(a[:3000], c)
 
@@ -153,15 +161,27 @@ def test_edge_records_match_row_index_path(native):
     ci[::9973] = n + 5          # ids outside the graph: nodes without out-edges (the walk stays there)
     ci[5::19997] = (1 << 40) + 3  # and one that needs the high word of the record
     nodes = torch.arange(n, device="cuda")
+    ci[7::15013] = (1 << 32) + 17  # aliases node 17 in a 32-bit slot: the uint32 table must not answer for it
+    d17 = min(3, int(rp[18] - rp[17]))  # and a row that holds such ids next to real ones
+    ci[int(rp[17]):int(rp[17]) + d17] = torch.tensor([(1 << 32) + 17, n + 5, (1 << 40) + 3], device="cuda")[:d17]
+    nodes = torch.arange(n, device="cuda")
+    laws = ((1.0, 1.0), (1.0, 0.5), (0.5, 2.0), (2.0, 1.0))
     res = {}
     try:
         for rec in (1, 0):
             native.set_option("records", rec)
-            res[rec] = [native.walk(rp, ci, nodes, p_, q_, 20, 7) for p_, q_ in ((1.0, 1.0), (1.0, 0.5), (0.5, 2.0), (2.0, 1.0))]
+            res[rec] = [native.walk(rp, ci, nodes, p_, q_, 20, 7) for p_, q_ in laws]
+        # the reference's answer: a linear scan of the int64 adjacency (csrc/cuda/rw_cuda.cu:33-57), no table, no filter
+        native.set_option("n2v_table", 0)
+        sub = nodes[:6000].contiguous()
+        scan = [native.walk(rp, ci, sub, p_, q_, 20, 7) for p_, q_ in laws]
     finally:
         native.set_option("records", -1)
+        native.set_option("n2v_table", 1)
     for a, b in zip(res[1], res[0]):
         assert torch.equal(a, b)
+    for a, b in zip(res[1], scan):
+        assert torch.equal(a[:6000], b)
     assert bool((res[1][1] == (1 << 40) + 3).any())
 
 
@@ -209,6 +229,69 @@ def test_prepared_graph_and_graph_cache(native, rw):
         assert not torch.equal(edited, ref)
     finally:
         native.set_graph_cache(False)
+
+
+def _clustered_csr(seed, n, communities, avg_deg):
+    """A graph with many triangles: nodes fall into communities and mostly link inside them."""
+    rng = np.random.default_rng(seed)
+    m = n * avg_deg // 2
+    src = rng.integers(0, n, m)
+    inside = rng.random(m) < 0.8
+    size = n // communities
+    dst = np.where(inside, (src // size) * size + rng.integers(0, size, m), rng.integers(0, n, m)) % n
+    keep = src != dst
+    src, dst = np.r_[src[keep], dst[keep]], np.r_[dst[keep], src[keep]]
+    key = np.unique(src.astype(np.int64) * n + dst)
+    src, dst = key // n, key % n
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(row_ptr, src + 1, 1)
+    return torch.from_numpy(np.cumsum(row_ptr)), torch.from_numpy(dst.astype(np.int64))
+
+
+@pytest.mark.parametrize("kind", ["rmat", "clustered", "directed", "duplicates", "out_of_graph_ids"])
+def test_triangle_blooms_and_edge_filter_do_not_change_a_walk(native, kind):
+    """A kept graph carries triangle Blooms in its edge records and an L2-resident edge filter
+    (member_table.cuh).  Both are one-sided short cuts in front of the membership table: whatever the
+    graph (symmetric or not, with or without triangles, duplicate or out-of-graph entries), every walk
+    must equal the stateless call's, which has neither, for every law and every cap."""
+    from torch_random_walk_b200 import rmat
+
+    if kind == "rmat":
+        rp, ci = rmat.rmat_csr(15, 16, device="cuda", seed=21)
+    elif kind == "clustered":
+        rp, ci = cuda(*_clustered_csr(5, 6000, 60, 40))
+    elif kind == "directed":
+        rp, ci = cuda(*random_csr(6, 4000, 30, symmetric=False))
+    elif kind == "duplicates":
+        rp, ci = random_csr(7, 3000, 40, sort_rows=False)
+        rp_np, ci_np = rp.numpy(), ci.numpy().copy()
+        for v in range(0, 3000, 2):
+            if rp_np[v + 1] - rp_np[v] >= 2:
+                ci_np[rp_np[v] + 1] = ci_np[rp_np[v]]
+        rp, ci = cuda(rp, T(ci_np))
+    else:
+        rp, ci = rmat.rmat_csr(14, 16, device="cuda", seed=4)
+        ci = ci.clone()
+        ci[::577] = (1 << 32) + 9
+        ci[3::1013] = rp.numel() + 7
+    n = rp.numel() - 1
+    nodes = torch.arange(n, device="cuda")
+    laws = ((1.0, 0.5), (0.5, 2.0), (0.25, 4.0), (0.4, 0.8), (2.0, 3.0))
+    try:
+        native.set_option("edge_filter_mb", 0)
+        base = [native.walk(rp, ci, nodes, p_, q_, 40, 3, cache=False) for p_, q_ in laws]
+        for cap, filter_mb in ((256, 64), (8, 64), (1 << 20, 0), (0, 64), (256, 1)):
+            native.set_option("edge_bloom_cap", cap)
+            native.set_option("edge_filter_mb", filter_mb)
+            g = native.prepare_csr(rp, ci)
+            for (p_, q_), b in zip(laws, base):
+                assert torch.equal(g.walk(nodes, p_, q_, 40, 3), b), (kind, cap, filter_mb, p_, q_)
+            if cap == 256 and filter_mb == 64:
+                assert g.symmetric == (kind in ("rmat", "clustered"))
+            del g
+    finally:
+        native.set_option("edge_bloom_cap", 256)
+        native.set_option("edge_filter_mb", 64)
 
 
 def test_unsorted_rows_and_duplicate_edges(native):

@@ -12,6 +12,8 @@
 //     segment, from L2.
 // A pre-pass finds the first row of every tile (edge-balanced tiling of a power-law graph), lists
 // the hub rows and their segments, and writes the uint32 row index.
+#include <algorithm>
+
 #include "member_table.cuh"
 #include "trw_options.h"
 
@@ -52,8 +54,30 @@ struct BuildArgs {
     unsigned long long* next_segment; // work counter of build_hub_kernel
     int* failed;                     // set when a segment had no room (see member_table.cuh)
     uint32_t* row32;                 // optional uint32 copy of row_ptr
+    uint32_t* filter;                // optional edge filter (member_table.cuh), cleared before the build
+    uint32_t filter_bits;
     int64_t n_tiles, n_buckets, max_hubs, max_segs;
 };
+
+// A neighbour id as the uint32 structures store it; kEmpty for one that does not fit (never stored:
+// is_member scans for such ids).
+__device__ __forceinline__ uint32_t slot_id(int64_t x) { return (uint64_t)x < (uint64_t)kEmpty ? (uint32_t)x : kEmpty; }
+
+// Edge filter: set the bit of the unordered pair {row, x}.  On a symmetric graph the mirror entry
+// (x, row) sets the same bit, so the larger-row half looks first and usually finds it set: half the
+// atomics.  A stale look only costs a redundant RED.
+__device__ __forceinline__ void filter_insert(uint32_t* __restrict__ filter, uint32_t n_bits, uint32_t row, uint32_t x,
+                                              uint64_t pol_keep) {
+    const uint32_t slot = pair_slot(row, x, n_bits);
+    uint32_t* word = filter + (slot >> 5);
+    const uint32_t bit = 1u << (slot & 31);
+    if (row > x) {
+        uint32_t seen;
+        asm volatile("ld.relaxed.gpu.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(seen) : "l"(word), "l"(pol_keep) : "memory");
+        if (seen & bit) return;
+    }
+    red_or32_hint(word, bit, pol_keep);
+}
 
 // Largest r with row_ptr[r] <= e (the non-empty row that holds CSR entry e).
 __device__ __forceinline__ int64_t row_of_entry(const int64_t* __restrict__ row_ptr, int64_t n_nodes, int64_t e) {
@@ -198,14 +222,16 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
         const int idx = k * kBuildThreads + tid;
         const uint32_t code = head[head_at(idx)];
         const bool ours = code != 0 && code != kNotOurs && e0 + idx < own_end;
-        xs[k] = ours ? (uint32_t)ldg64_stream(a.col_idx + e0 + idx) : kEmpty;
+        xs[k] = ours ? slot_id(ldg64_stream(a.col_idx + e0 + idx)) : kEmpty;
     }
     int64_t cur_row = -1, first = 0, nb = 0;
     bool ok = true;
+    const uint64_t pol_keep = make_policy_evict_last();
 #pragma unroll
     for (int k = 0; k < kRangePerThread; ++k) {
-        if (xs[k] == kEmpty) continue;  // not ours (ids never equal the EMPTY marker in table mode)
+        if (xs[k] == kEmpty) continue;  // not ours, or an id the uint32 slots cannot hold
         const int64_t r = r0 + head[head_at(k * kBuildThreads + tid)] - 1;
+        if (a.filter) filter_insert(a.filter, a.filter_bits, (uint32_t)r, xs[k], pol_keep);
         if (r != cur_row) {
             cur_row = r;
             const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
@@ -251,19 +277,23 @@ __global__ void __launch_bounds__(kHubThreads, 1) build_hub_kernel(const BuildAr
         for (int64_t i = tid; i < size; i += kHubThreads) hub_count[i] = 0;
         __syncthreads();
         bool ok = true;
+        const uint64_t pol_keep = make_policy_evict_last();
         // eight independent loads in flight per thread; the row comes from L2 after its first reader
         for (int64_t i = b + tid; i < e; i += 8 * kHubThreads) {
             uint32_t x[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int64_t idx = i + (int64_t)u * kHubThreads;
-                x[u] = idx < e ? (uint32_t)__ldg(a.col_idx + idx) : kEmpty;
+                x[u] = idx < e ? slot_id(__ldg(a.col_idx + idx)) : kEmpty;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 if (x[u] == kEmpty) continue;
                 const int64_t home = home_bucket(x[u], nb);
-                if (home >= lo && home < hi) ok &= smem_insert(hub_image, hub_count, size, home - lo, x[u]);
+                if (home >= lo && home < hi) {  // every entry of the row has its home in exactly one segment
+                    ok &= smem_insert(hub_image, hub_count, size, home - lo, x[u]);
+                    if (a.filter) filter_insert(a.filter, a.filter_bits, (uint32_t)work.row, x[u], pol_keep);
+                }
             }
         }
         if (!ok) *a.failed = 1;
@@ -346,7 +376,8 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_flat_kernel(const Buil
             const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
             if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
         }
-        if (nb > 0) ok &= global_insert(a.table, first, nb, (uint32_t)ldg64_stream(a.col_idx + mine + k));
+        const uint32_t x = slot_id(ldg64_stream(a.col_idx + mine + k));
+        if (nb > 0 && x != kEmpty) ok &= global_insert(a.table, first, nb, x);
     }
     if (!ok) *a.failed = 1;
 }
@@ -392,7 +423,7 @@ __global__ void __launch_bounds__(256) short_rows_kernel(const int64_t* __restri
         if (d <= 0 || d >= kMinTableDeg) continue;
         uint32_t ids[kMinTableDeg];
 #pragma unroll
-        for (int k = 0; k < kMinTableDeg - 1; ++k) ids[k] = k < d ? (uint32_t)ldg64_stream(col_idx + b + k) : kEmpty;
+        for (int k = 0; k < kMinTableDeg - 1; ++k) ids[k] = k < d ? slot_id(ldg64_stream(col_idx + b + k)) : kEmpty;
         uint32_t* words = table + 2 * b;
 #pragma unroll
         for (int k = 0; k < 2 * (kMinTableDeg - 1); ++k)
@@ -423,15 +454,125 @@ __global__ void __launch_bounds__(256) edge_records_kernel(const int64_t* __rest
         for (int u = 0; u < kBatch; ++u) {
             if (i + u * gsz >= nnz) continue;
             const uint64_t id = (uint64_t)x[u];
-            stg_u32x4_hint(records + i + u * gsz, (uint32_t)id, e[u] - b[u], b[u], (uint32_t)(id >> 32), pol_stream);
+            const uint32_t deg = e[u] - b[u];
+            stg_u32x4_hint(records + i + u * gsz, (uint32_t)id, deg, b[u], record_last_word(id, deg, kBloomAll), pol_stream);
         }
+    }
+}
+
+// Triangle Blooms of a kept graph (member_table.cuh): word .w of record (t -> v) becomes the 32-bit Bloom
+// of adj(t) & adj(v).  The set is the same from either end, so each unordered pair is worked out once, by
+// the entry that sits in the LONGER row (ties: the larger id): it walks the shorter row adj(v), asks row
+// t's table about every w (edge filter first) and, on the way, meets t itself -- at the position of the
+// mirror entry (v -> t), which receives the same word.  A warp owns 32 consecutive CSR entries; the
+// (entry, neighbour) pairs of the tile are flattened over the lanes, two per lane and round, so short
+// rows do not idle the warp and two gathers are in flight per lane.  Pairs whose shorter row exceeds
+// `cap` keep the saturated word: their Bloom would be full anyway and the work is quadratic in hub size.
+// The same pass proves or refutes that the graph is symmetric (every (t -> v) has its (v -> t)), which
+// the walk needs before it may look at a triangle from its far side.
+constexpr int kBloomWarps = 8;
+constexpr int kBloomUnroll = 2;
+__global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(const int64_t* __restrict__ col_idx, int64_t nnz,
+                                                                      const uint32_t* __restrict__ row32, int64_t n_nodes,
+                                                                      uint4* __restrict__ records,
+                                                                      const uint32_t* __restrict__ table, EdgeFilter filter,
+                                                                      uint32_t cap, const int* __restrict__ table_failed,
+                                                                      int* __restrict__ asymmetric) {
+    __shared__ uint32_t s_bloom[kBloomWarps][32];
+    __shared__ uint32_t s_mirror[kBloomWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
+    const int64_t n_tiles = (nnz + 31) >> 5;
+    constexpr uint32_t kNoMirror = 0xFFFFFFFFu;
+    if (*table_failed != 0) {  // a table that overflowed cannot be asked: the words stay saturated, symmetry unproven
+        if (threadIdx.x == 0) *asymmetric = 1;
+        return;
+    }
+    for (int64_t tile = (int64_t)blockIdx.x * kBloomWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kBloomWarps) {
+        const int64_t k = tile * 32 + lane;
+        const bool valid = k < nnz;
+        // this lane's entry: row t (bisection of the L2-resident row index), neighbour v with its span from the record
+        uint32_t t = 0, tb = 0, dt = 0, v = 0, vb = 0, dv = 0;
+        if (valid) {
+            int64_t lo = 0, hi = n_nodes;  // row32[lo] <= k < row32[hi]
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if ((int64_t)ldg32_keep(row32 + mid, pol_keep) <= k) lo = mid; else hi = mid;
+            }
+            t = (uint32_t)lo;
+            tb = (uint32_t)ldg32_keep(row32 + lo, pol_keep);
+            dt = (uint32_t)ldg32_keep(row32 + lo + 1, pol_keep) - tb;
+            const uint4 rec = records[k];
+            v = rec.x; dv = rec.y; vb = rec.z;
+        }
+        const bool live = valid && dv > 0;  // a neighbour without out-edges (or outside the graph) keeps its word
+        const bool owner = live && (dt > dv || (dt == dv && t >= v));
+        const bool exact = owner && dv <= cap;
+        // every other live entry only has to know that its mirror exists
+        if (live && !exact && !is_member<true>((int64_t)t, (int64_t)vb, (int64_t)vb + dv, col_idx, table, pol_stream)) *asymmetric = 1;
+        s_bloom[warp][lane] = 0;
+        s_mirror[warp][lane] = kNoMirror;
+        const uint32_t items = exact ? dv : 0u;
+        uint32_t incl = items;  // inclusive prefix of the work items over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        __syncwarp();
+        for (uint32_t i0 = 0; i0 < total; i0 += 32 * kBloomUnroll) {
+            int j[kBloomUnroll];
+            uint32_t pos[kBloomUnroll], row[kBloomUnroll], bb[kBloomUnroll], bd[kBloomUnroll];
+            int64_t w[kBloomUnroll];
+            bool act[kBloomUnroll];
+#pragma unroll
+            for (int u = 0; u < kBloomUnroll; ++u) {
+                const uint32_t i = i0 + u * 32 + lane;
+                // entry j that owns item i: the first lane whose inclusive prefix exceeds i
+                int jj = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t probe = __shfl_sync(0xFFFFFFFFu, incl, jj + step - 1);
+                    if (probe <= i) jj += step;
+                }
+                j[u] = jj;
+                const uint32_t j_incl = __shfl_sync(0xFFFFFFFFu, incl, jj);
+                const uint32_t j_items = __shfl_sync(0xFFFFFFFFu, items, jj);
+                const uint32_t j_vb = __shfl_sync(0xFFFFFFFFu, vb, jj);
+                row[u] = __shfl_sync(0xFFFFFFFFu, t, jj);
+                bb[u] = __shfl_sync(0xFFFFFFFFu, tb, jj);
+                bd[u] = __shfl_sync(0xFFFFFFFFu, dt, jj);
+                act[u] = i < total;
+                pos[u] = j_vb + (i - (j_incl - j_items));
+                w[u] = act[u] ? ldg64_hint(col_idx + pos[u], pol_stream) : -1;
+            }
+            bool maybe[kBloomUnroll];
+#pragma unroll
+            for (int u = 0; u < kBloomUnroll; ++u) {
+                if (act[u] && w[u] == (int64_t)row[u]) s_mirror[warp][j[u]] = pos[u];
+                maybe[u] = act[u] && filter_maybe(filter, (int64_t)row[u], w[u], pol_keep);
+            }
+#pragma unroll
+            for (int u = 0; u < kBloomUnroll; ++u)
+                if (maybe[u] && is_member<true>(w[u], (int64_t)bb[u], (int64_t)bb[u] + bd[u], col_idx, table, pol_stream))
+                    atomicOr(&s_bloom[warp][j[u]], bloom_bit(w[u]));
+        }
+        __syncwarp();
+        if (exact) {
+            const uint32_t word = s_bloom[warp][lane], mirror = s_mirror[warp][lane];
+            reinterpret_cast<uint32_t*>(records + k)[3] = word;
+            if (mirror != kNoMirror) reinterpret_cast<uint32_t*>(records + mirror)[3] = word;
+            else *asymmetric = 1;
+        }
+        __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------ host
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bool records) {
+CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bool records, bool filter) {
     CsrWorkspace w{};
     const bool ids_fit = (uint64_t)n_nodes < 0xFFFFFFFFull;   // neighbour ids must fit the uint32 table slots
     const bool offsets_fit = (uint64_t)nnz <= 0xFFFFFFFFull;   // row offsets must fit the uint32 row index
@@ -457,13 +598,22 @@ CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bo
     w.has_records = records && w.has_row32 && nnz > 0;  // spans are stored as uint32 (start, degree)
     w.records = off;
     if (w.has_records) off += align256((size_t)nnz * 16);
+    // edge filter: 32 bits per CSR entry for small graphs, capped at edge_filter_mb (it has to stay L2-resident)
+    w.filter = off;
+    w.filter_bits = 0;
+    const int64_t filter_mb = options().edge_filter_mb > 511 ? 511 : options().edge_filter_mb;
+    if (w.has_table && filter && filter_mb > 0) {
+        const size_t bytes = std::min((size_t)filter_mb << 20, align256((size_t)nnz * 4));
+        w.filter_bits = (uint32_t)(bytes * 8);
+        off += bytes;
+    }
     w.total = off;
     return w;
 }
 
 int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
                        const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, bool want_records,
-                       int build_mode, int device, cudaStream_t st, CsrPrepared* out) {
+                       int build_mode, int device, cudaStream_t st, CsrPrepared* out, int64_t bloom_cap) {
     want_table = want_table && w.has_table;
     want_row32 = want_row32 && w.has_row32;
     want_records = want_records && w.has_records && want_row32;
@@ -475,7 +625,14 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
     b.row_ptr = row_ptr; b.col_idx = col_idx; b.n_nodes = n_nodes; b.nnz = nnz;
     b.n_tiles = w.n_tiles; b.n_buckets = w.n_buckets; b.max_hubs = w.max_hubs; b.max_segs = w.max_segs;
     b.row32 = want_row32 ? (uint32_t*)(ws + w.row32) : nullptr;
+    const bool want_filter = want_table && build_mode != 0 && w.filter_bits != 0;
     int rc;
+    if (want_filter) {
+        b.filter = (uint32_t*)(ws + w.filter);
+        b.filter_bits = w.filter_bits;
+        rc = check_cuda(cudaMemsetAsync(b.filter, 0, (size_t)w.filter_bits / 8, st), "edge filter memset");
+        if (rc) return rc;
+    }
     if (want_table) {
         b.table = (uint32_t*)(ws + w.table);
         b.tile_row0 = (int64_t*)(ws + w.tile_row0);
@@ -534,6 +691,7 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
         if (rc) return rc;
         out->table = b.table;
         out->table_failed = b.failed;
+        if (want_filter) { out->filter.bits = b.filter; out->filter.n_bits = b.filter_bits; }
     }
     out->row32 = b.row32;
     if (want_records) {
@@ -543,6 +701,15 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
         rc = check_cuda(cudaGetLastError(), "edge records launch");
         if (rc) return rc;
         out->records = records;
+        if (bloom_cap > 0 && out->table != nullptr && build_mode != 0) {
+            int* asymmetric = (int*)(ws + w.cells + 192);
+            edge_bloom_kernel<<<sms * 8, kBloomWarps * 32, 0, st>>>(col_idx, nnz, b.row32, n_nodes, records, out->table, out->filter,
+                                                                     (uint32_t)std::min<int64_t>(bloom_cap, 1 << 20), b.failed, asymmetric);
+            count_launch(1);
+            rc = check_cuda(cudaGetLastError(), "edge bloom launch");
+            if (rc) return rc;
+            out->asymmetric = asymmetric;
+        }
     }
     return TRW_OK;
 }

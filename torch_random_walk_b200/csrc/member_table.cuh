@@ -56,7 +56,10 @@ __device__ __forceinline__ void probe_segment(int64_t nb, int64_t home, int64_t&
 template <bool TABLE>
 __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const int64_t* __restrict__ col_idx,
                                           const uint32_t* __restrict__ table, uint64_t pol_stream) {
-    if (TABLE && table != nullptr && e - b < kMinTableDeg) {
+    // Table slots hold uint32 ids below kEmpty; an id that does not fit (out-of-graph, possible only in a
+    // hand-built col_idx) is never stored there, so the table cannot speak for it: such an x is scanned.
+    const bool fits = (uint64_t)x < (uint64_t)kEmpty;
+    if (TABLE && table != nullptr && fits && e - b < kMinTableDeg) {
         const uint32_t x32 = (uint32_t)x;
         const uint32_t* words = table + 2 * b;
         const int d = (int)(e - b);
@@ -70,7 +73,7 @@ __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const
         for (int k = 0; k < (int)kMinTableDeg / 2; ++k) found |= (w[k].x == x32) | (w[k].y == x32);
         return found;
     }
-    if (TABLE && table != nullptr) {
+    if (TABLE && table != nullptr && fits) {
         int64_t first, nb, lo, hi;
         table_span(b, e, first, nb);
         const uint32_t x32 = (uint32_t)x;
@@ -99,6 +102,33 @@ __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const
         if (found) return true;
     }
     return false;
+}
+
+// ---------------------------------------------------------------- edge filter (L2-resident)
+// Most membership questions of a walk on a sparse graph are answered "no" (R-MAT: 96 %), and each
+// of them costs a random 128-byte line of HBM for the table sector.  The edge filter answers most of
+// the "no"s from L2: one bit per hashed unordered pair {row, id}, set for every CSR entry, in a
+// bitmap small enough to stay L2-resident (evict_last; default 64 MB, option edge_filter_mb).  A
+// clear bit proves that neither (row, id) nor (id, row) is stored, so "not a member" is exact; a set
+// bit says "maybe" and the caller asks the table as before.  Same answers, fewer lines: with n/2
+// distinct pairs of a symmetric graph in M bits a fraction exp(-n/2M) of the "no"s stops here
+// (c3: 0.62 at 64 MB).  Ids that do not fit 32 bits are never inserted and never asked.
+struct EdgeFilter {
+    const uint32_t* bits = nullptr;
+    uint32_t n_bits = 0;
+};
+__host__ __device__ __forceinline__ uint32_t pair_slot(uint32_t a, uint32_t b, uint32_t n_bits) {
+    const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+    uint64_t z = (((uint64_t)hi << 32) | lo) * 0x9E3779B97F4A7C15ull;
+    z ^= z >> 32;
+    z *= 0xD6E8FEB86659FD93ull;
+    return mulhi32((uint32_t)(z >> 32), n_bits);
+}
+// false: `x` is certainly not stored in the row of node `row`; true: ask the table.
+__device__ __forceinline__ bool filter_maybe(const EdgeFilter& f, int64_t row, int64_t x, uint64_t pol_keep) {
+    if (f.bits == nullptr || ((uint64_t)row | (uint64_t)x) >= (uint64_t)kEmpty) return true;
+    const uint32_t slot = pair_slot((uint32_t)row, (uint32_t)x, f.n_bits);
+    return (ldg32_l2keep(f.bits + (slot >> 5), pol_keep) >> (slot & 31)) & 1u;
 }
 
 // Does x occur at least TWICE in the row?  Only meaningful for tables assembled in shared memory
@@ -139,17 +169,33 @@ __device__ __forceinline__ bool member_twice(int64_t x, int64_t b, int64_t e, co
 // ---------------------------------------------------------------- host side (member_table.cu)
 // Offsets of the per-call scratch inside the caller's workspace (all 256-byte aligned).
 struct CsrWorkspace {
-    size_t table, tile_row0, hub_list, seg_work, cells, row32, records, total;
+    size_t table, tile_row0, hub_list, seg_work, cells, row32, records, filter, total;
     int64_t n_tiles, n_buckets, max_hubs, max_segs;
+    uint32_t filter_bits;
     bool has_table, has_row32, has_records;
 };
-CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bool records);
+CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bool records, bool filter = true);
 
 // Edge record k of the CSR (option `records`): the neighbour id col_idx[k] together with that
 // neighbour's own row span, so that the gather which proposes the next node also returns where
 // its adjacency lives and the walk never touches the row index again (16 bytes, one LDG.128).
-//   .x = id, low 32 bits   .y = degree of id   .z = row start of id   .w = id, high 32 bits
-// An id outside [0, n_nodes) gets degree 0, i.e. a node without out-edges, as load_row() treats it.
+//   .x = id, low 32 bits   .y = degree of id   .z = row start of id
+//   .w = degree 0: id, high 32 bits (an id outside [0, n_nodes) gets degree 0, i.e. a node without
+//        out-edges, as load_row() treats it -- only such an id can need a high word);
+//        degree > 0: the TRIANGLE BLOOM of the edge, see below.
+//
+// Triangle Bloom of entry (t -> v): 32 bits, bit bloom_bit(w) set for every w in adj(t) & adj(v)
+// (kBloomAll when it was not computed: one-shot calls, pairs of two hubs).  A node2vec step at v
+// coming from t asks "x in adj(t)?" for x drawn from adj(v); x can only be in adj(t) if it is a common
+// neighbour of t and v, so a clear bit bloom_bit(x) in the word of (t -> v) -- fetched for free when v
+// was proposed -- answers "no" without touching memory.  On a symmetric graph the word of (v -> x),
+// fetched with the proposal itself, gives a second, independent look at the same triangle through
+// bloom_bit(t).  Both are one-sided (a set bit means "ask the table"), so the walk is bit-identical.
+constexpr uint32_t kBloomAll = 0xFFFFFFFFu;
+__host__ __device__ __forceinline__ uint32_t bloom_bit(int64_t w) { return 1u << (((uint32_t)w * 0x9E3779B1u) >> 27); }
+__host__ __device__ __forceinline__ uint32_t record_last_word(uint64_t id, uint32_t deg, uint32_t bloom) {
+    return deg != 0 ? bloom : (uint32_t)(id >> 32);
+}
 
 struct CsrPrepared {
     const uint32_t* table = nullptr;     // membership table, or nullptr
@@ -157,6 +203,8 @@ struct CsrPrepared {
     const int* table_failed = nullptr;   // device flag: non-zero when a hub segment overflowed
     const unsigned long long* strict_counts = nullptr;  // [descents in col_idx, descents at row boundaries]
     const uint4* records = nullptr;      // edge records, or nullptr
+    EdgeFilter filter;                   // L2-resident edge filter (bits == nullptr: none)
+    const int* asymmetric = nullptr;     // device flag of the triangle-Bloom pass: non-zero when some (t -> v) has no (v -> t); nullptr: not checked
 };
 
 // Enqueues on `st` the per-call preparation of a CSR graph: the uint32 row index and (node2vec)
@@ -164,6 +212,6 @@ struct CsrPrepared {
 // increasing, i.e. sorted without duplicate edges.  build_mode: 2 = shared memory (default), 0 = global CAS.
 int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
                        const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, bool want_records,
-                       int build_mode, int device, cudaStream_t st, CsrPrepared* out);
+                       int build_mode, int device, cudaStream_t st, CsrPrepared* out, int64_t bloom_cap = 0);
 
 }  // namespace trw

@@ -170,6 +170,18 @@ __device__ __forceinline__ void stg64_hint(int64_t* p, int64_t v, uint64_t pol) 
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
 
+// 4-byte load of L2-resident side data (the edge filter): kept in L2 (evict_last policy), not
+// allocated in L1, where the in-flight gathers live.
+__device__ __forceinline__ uint32_t ldg32_l2keep(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+// Fire-and-forget OR into L2-resident side data (RED.OR, no return value), with an L2 policy.
+__device__ __forceinline__ void red_or32_hint(uint32_t* p, uint32_t bits, uint64_t pol) {
+    asm volatile("red.relaxed.gpu.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(bits), "l"(pol) : "memory");
+}
+
 // Coherent 16-byte load of memory other threads are updating with atomics.
 __device__ __forceinline__ uint4 ld_relaxed_u32x4(const uint32_t* p) {
     uint4 v;

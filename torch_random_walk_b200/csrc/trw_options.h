@@ -17,6 +17,10 @@ struct Options {
     int64_t el_table = 1;         // 1: edge-list node2vec walks test membership through the hashed table (needs workspace); 0: the reference's scan
     int64_t records = -1;         // 16-byte edge records (neighbour id + its row span; the walk then needs no row-index loads): 1 always, 0 never,
                                   // -1 kept graphs always, one-shot calls when the walk is long enough to repay one pass over col_idx (csr_one_shot_needs)
+    int64_t edge_filter_mb = 0;   // L2-resident edge filter in front of the membership table (member_table.cuh): size cap in MB, 0 = none
+                                  // (default: measured -8 % on the c3 walk alone, but nothing on top of the triangle Blooms, and 2.9 ms per build)
+    int64_t edge_bloom_cap = 256; // kept graphs: triangle Blooms in the edge records (member_table.cuh) for pairs whose shorter row has at most
+                                  // this many entries (the pass is quadratic in it); 0 = none
     int64_t build_mode = 2;       // table build: 2 assembled in shared memory (tiles + hub segments); 0 global CAS (A/B baseline)
     int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
@@ -35,7 +39,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap)
 
 Options& options();
 void count_launch(int n);

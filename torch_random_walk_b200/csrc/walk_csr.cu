@@ -53,11 +53,13 @@ __device__ __forceinline__ void load_row(const WalkArgs& a, int64_t v, int64_t& 
 // Proposal: the neighbour of v at a uniformly random position, or v itself when it has none
 // (rw_cuda.cu:8-31).  REC: the gather is an edge record and also returns the neighbour's own row
 // span in (xb, xe); otherwise (xb, xe) are left for the caller to load.
+// `bloom` receives the triangle Bloom of the edge (v -> result) when the record carries one, else kBloomAll.
 template <bool REC>
 __device__ __forceinline__ int64_t propose(const WalkArgs& a, int64_t v, int64_t b, int64_t e, uint32_t r0, uint32_t r1,
-                                           uint64_t pol_stream, int64_t& xb, int64_t& xe) {
+                                           uint64_t pol_stream, int64_t& xb, int64_t& xe, uint32_t& bloom) {
     const int64_t deg = e - b;
     const int64_t idx = deg > 0 ? b + bounded(r0, r1, deg) : -1;
+    bloom = kBloomAll;
     if ((uint64_t)idx >= (uint64_t)a.nnz) {  // no out-edge (or a span outside col_idx): the walk stays on v
         xb = b; xe = e;
         return v;
@@ -66,9 +68,32 @@ __device__ __forceinline__ int64_t propose(const WalkArgs& a, int64_t v, int64_t
         const uint4 rec = ldg_u32x4_hint(a.records + idx, pol_stream);
         xb = (int64_t)rec.z;
         xe = xb + (int64_t)rec.y;
-        return (int64_t)(((uint64_t)rec.w << 32) | rec.x);
+        if (rec.y != 0) { bloom = rec.w; return (int64_t)rec.x; }  // member_table.cuh: the last word is a Bloom ...
+        return (int64_t)(((uint64_t)rec.w << 32) | rec.x);         // ... or the high word of an id without out-edges
     }
     return ldg64_hint(a.col_idx + idx, pol_stream);
+}
+template <bool REC>
+__device__ __forceinline__ int64_t propose(const WalkArgs& a, int64_t v, int64_t b, int64_t e, uint32_t r0, uint32_t r1,
+                                           uint64_t pol_stream, int64_t& xb, int64_t& xe) {
+    uint32_t unused;
+    return propose<REC>(a, v, b, e, r0, r1, pol_stream, xb, xe, unused);
+}
+
+// The two free looks at the triangle (t, v, x) before any memory is touched (member_table.cuh): the Bloom of
+// (t -> v) carried along since v was proposed, and -- on a symmetric graph -- the Bloom that came with the
+// proposal of x.  false: x is certainly not in adj(t).
+__device__ __forceinline__ bool triangle_maybe(uint32_t carried, int64_t x, bool symmetric, uint32_t fresh, uint32_t other_bit) {
+    return (carried & bloom_bit(x)) != 0 && (!symmetric || (fresh & other_bit) != 0);
+}
+
+// "x in adj(row)?" where the usual answer is no: the L2-resident edge filter first (a clear bit is a
+// proof), the table sector only for a "maybe".  Identical answers with and without the filter.
+template <bool TABLE>
+__device__ __forceinline__ bool is_member_filtered(const WalkArgs& a, int64_t x, int64_t row, int64_t b, int64_t e,
+                                                   const uint32_t* table, uint64_t pol_stream, uint64_t pol_keep) {
+    if (TABLE && e > b && !filter_maybe(a.filter, row, x, pol_keep)) return false;
+    return is_member<TABLE>(x, b, e, a.col_idx, table, pol_stream);
 }
 
 // Output of one walk row: line-staged cooperative stores (STAGE) or plain 8-byte stores.  put() is a
@@ -157,16 +182,21 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
     // a table whose build reported an overflowing segment is not trusted: scan instead
     const uint32_t* table = (TABLE && a.table != nullptr && *a.table_failed == 0) ? a.table : nullptr;
+    // `symmetric`: every stored (t -> v) has its (v -> t), proven by the pass that built the triangle Blooms
+    // (which leaves them saturated and this flag down when the table build failed); then t is a neighbour of
+    // v at every step and a triangle may be looked at from its far side.
+    const bool symmetric = REC && TABLE && a.asymmetric != nullptr && *a.asymmetric == 0;
 
     int64_t t = live ? __ldg(a.targets + i) : 0;
     o.put(live, 0, t, L == 0);
     if (L == 0) return;
     int64_t tb = 0, te = 0, vb = 0, ve = 0, v = 0;
+    uint32_t ctx = kBloomAll;  // Bloom of adj(t) & adj(v) for the current (t, v), or all ones
     uint4 rnd = make_uint4(0, 0, 0, 0);
     if (live) {
         load_row<ROW32>(a, t, tb, te, pol_keep);
         rnd = philox4x32_10(make_uint4(wlo, whi, 1u, 0u), a.key);
-        v = propose<REC>(a, t, tb, te, rnd.x, rnd.z, pol_stream, vb, ve);  // first step is uniform (rw_cuda.cu:138)
+        v = propose<REC>(a, t, tb, te, rnd.x, rnd.z, pol_stream, vb, ve, ctx);  // first step is uniform (rw_cuda.cu:138)
     }
     o.put(live, 1, v, L == 1);
     if (L == 1) return;
@@ -190,6 +220,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
         // Plain rejection spends q trials per step on the far neighbours' low weight; here the envelope
         // exceeds the true mass only by the misses of B, so a step costs about one gather when deg(t)
         // is much smaller than deg(v) and never more than plain rejection does.
+        //
+        // The three terms share ONE gather site and ONE membership site: which row is drawn from and which
+        // question is asked are selected by predicates, not by branches, so the lanes of a warp issue their
+        // gathers (and then their probes) together whatever term each of them picked.
         const double c = a.fold_env, back = a.fold_excess;
         uint32_t thr_a = 0, thr_ab = 0;
         bool have_thr = false, t_side = false;
@@ -209,27 +243,28 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
                     have_thr = true;
                 }
                 rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
-                int64_t xb = 0, xe = 0;
-                if (dv <= 0) {  // no out-edge: the walk stays on v (rw_cuda.cu:25-30)
-                    x = v; xb = vb; xe = ve;
-                    accept = true;
-                } else if (rnd.z < thr_a) {
-                    x = propose<REC>(a, v, vb, ve, rnd.x, rnd.w, pol_stream, xb, xe);
-                    accept = true;
-                } else if (rnd.z < thr_ab) {
-                    if (t_side) {
-                        x = propose<REC>(a, t, tb, te, rnd.x, rnd.w, pol_stream, xb, xe);
-                        accept = x != t && is_member<TABLE>(x, vb, ve, a.col_idx, table, pol_stream);
-                    } else {
-                        x = propose<REC>(a, v, vb, ve, rnd.x, rnd.w, pol_stream, xb, xe);
-                        accept = x != t && is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream);
-                    }
-                } else {
-                    x = t; xb = tb; xe = te;
-                    accept = is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
-                }
+                int64_t xb = vb, xe = ve;
+                uint32_t xw = kBloomAll;
+                const bool stay = dv <= 0;  // no out-edge: the walk stays on v (rw_cuda.cu:25-30)
+                const bool term_a = !stay && rnd.z < thr_a;
+                const bool term_b = !stay && !term_a && rnd.z < thr_ab;
+                const bool term_c = !stay && !term_a && !term_b;
+                const bool from_t = term_b && t_side;  // B draws from the shorter row
+                x = v;
+                if (term_a || term_b) x = propose<REC>(a, from_t ? t : v, from_t ? tb : vb, from_t ? te : ve, rnd.x, rnd.w, pol_stream, xb, xe, xw);
+                if (term_c) { x = t; xb = tb; xe = te; }
+                // B asks whether x is also in the row it was NOT drawn from (the triangle Blooms look first);
+                // C asks whether t is a neighbour of v at all, which a symmetric graph has already answered
+                const bool ask = term_b ? (x != t && triangle_maybe(ctx, x, symmetric, xw, bloom_bit(from_t ? v : t))) : (term_c && !symmetric);
+                const bool in_v = from_t || term_c;
+                bool member = false;
+                if (ask) member = is_member_filtered<TABLE>(a, term_c ? t : x, in_v ? v : t, in_v ? vb : tb, in_v ? ve : te, table, pol_stream, pol_keep);
+                accept = stay || term_a || member || (term_c && symmetric);
                 if (accept) {
                     if (!REC && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
+                    // the Bloom of the new (t, v): the word that came with x when x was drawn from adj(v); the old one
+                    // after a return (adj(v) & adj(t) is the same set from either end); unknown otherwise
+                    ctx = (term_a || (term_b && !from_t)) ? xw : (term_c ? ctx : kBloomAll);
                     t = v; tb = vb; te = ve;
                     v = x; vb = xb; ve = xe;
                     ++s;
@@ -259,24 +294,30 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
                     have_extra = true;
                 }
                 rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
-                int64_t xb = 0, xe = 0;
-                if (ve <= vb) {  // no out-edge: the walk stays on v (rw_cuda.cu:25-30), nothing to sample
-                    x = v; xb = vb; xe = ve;
-                    accept = true;
-                } else if (rnd.z < thr_extra) {
-                    x = t; xb = tb; xe = te;
-                    accept = is_member<TABLE>(t, vb, ve, a.col_idx, table, pol_stream);
-                } else {
-                    x = propose<REC>(a, v, vb, ve, rnd.x, rnd.w, pol_stream, xb, xe);
-                    const uint32_t u = rnd.y;
-                    if (x == t || u < fthr_any) accept = true;
-                    else if (u >= fthr_top) accept = false;
-                    else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream) ? a.fthr1 : a.fthr2);
-                }
+                int64_t xb = vb, xe = ve;
+                uint32_t xw = kBloomAll;
+                const bool stay = ve <= vb;  // no out-edge: the walk stays on v (rw_cuda.cu:25-30), nothing to sample
+                const bool extra = !stay && rnd.z < thr_extra;  // the point fell into the extra bar of t
+                x = v;
+                if (!stay && !extra) x = propose<REC>(a, v, vb, ve, rnd.x, rnd.w, pol_stream, xb, xe, xw);
+                if (extra) { x = t; xb = tb; xe = te; xw = ctx; }  // adj(v) & adj(t) is the same set from either end
+                const uint32_t u = rnd.y;
+                // one membership site: "t in adj(v)?" for the extra bar (answered by symmetry when the graph has it),
+                // "x in adj(t)?" when the draw alone does not decide a regular bar
+                const bool regular = !stay && !extra && x != t && u >= fthr_any && u < fthr_top;
+                const bool ask = extra ? !symmetric : (regular && triangle_maybe(ctx, x, symmetric, xw, bloom_bit(t)));
+                bool member = false;
+                if (ask) member = is_member_filtered<TABLE>(a, extra ? t : x, extra ? v : t, extra ? vb : tb, extra ? ve : te, table, pol_stream, pol_keep);
+                if (stay) accept = true;
+                else if (extra) accept = symmetric || member;
+                else if (x == t || u < fthr_any) accept = true;
+                else if (u >= fthr_top) accept = false;
+                else accept = u < (member ? a.fthr1 : a.fthr2);
                 if (accept) {
                     if (!REC && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
                     t = v; tb = vb; te = ve;
                     v = x; vb = xb; ve = xe;
+                    ctx = xw;
                     ++s;
                     trial = 0;
                     have_extra = false;
@@ -303,7 +344,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
                 r = rnd.z; u = rnd.w; r_hi = rnd.x;
             }
             int64_t xb = 0, xe = 0;
-            x = propose<REC>(a, v, vb, ve, r, r_hi, pol_stream, xb, xe);
+            uint32_t xw;
+            x = propose<REC>(a, v, vb, ve, r, r_hi, pol_stream, xb, xe, xw);
             const bool back = (x == t);
             const bool possible = back ? (u < a.thr0) : (u < thr_far);
             if (!REC && SPECULATE && possible && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
@@ -311,11 +353,16 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
             else if (back) accept = u < a.thr0;
             else if (!possible) accept = false;
             else if (a.thr1 == a.thr2) accept = true;  // q == 1: membership cannot change the answer
-            else accept = u < (is_member<TABLE>(x, tb, te, a.col_idx, table, pol_stream) ? a.thr1 : a.thr2);
+            else {
+                const bool member = triangle_maybe(ctx, x, symmetric, xw, bloom_bit(t)) &&
+                                    is_member_filtered<TABLE>(a, x, t, tb, te, table, pol_stream, pol_keep);
+                accept = u < (member ? a.thr1 : a.thr2);
+            }
             if (accept) {
                 if (!REC && !SPECULATE && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
                 t = v; tb = vb; te = ve;
                 v = x; vb = xb; ve = xe;
+                ctx = xw;
                 ++s;
                 trial = 0;
             } else {
@@ -442,7 +489,7 @@ static void set_row_window(cudaStream_t st, const void* base, size_t bytes, int 
 // trw_walk_csr builds it per call).
 int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                       bool uniform, bool want_table, bool want_strict, bool want_records, void* workspace,
-                      size_t workspace_bytes, int device, cudaStream_t st) {
+                      size_t workspace_bytes, int device, cudaStream_t st, int64_t bloom_cap) {
     if (n_nodes < 0 || nnz < 0) { set_error("trw_walk_csr: negative size"); return TRW_ERR_ARG; }
     if (!row_ptr || (nnz > 0 && !col_idx)) { set_error("trw_walk_csr: null pointer"); return TRW_ERR_ARG; }
     const Options& opt = options();
@@ -458,7 +505,7 @@ int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_id
     timing_begin(0, st);
     const int rc = csr_prepare_device(row_ptr, col_idx, n_nodes, nnz, workspace, w, want_table && opt.n2v_table != 0,
                                       opt.row32 != 0, want_strict, want_records && opt.stage_output != 0,
-                                      (int)opt.build_mode, device, st, &g->prepared);
+                                      (int)opt.build_mode, device, st, &g->prepared, bloom_cap);
     timing_end(0, st);
     return rc;
 }
@@ -478,6 +525,8 @@ int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int 
     a.table_failed = g.prepared.table_failed;
     a.row32 = g.prepared.row32;
     a.records = g.prepared.records;
+    a.filter = g.prepared.filter;
+    a.asymmetric = g.prepared.asymmetric;
     a.strict_counts = g.prepared.strict_counts;
     plan->device = g.device;
     plan->uniform = (p == 1.0 && q == 1.0);  // rw_cuda.cu:226
@@ -510,8 +559,12 @@ int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int 
             a.fthr1 = threshold(1.0 / env);
             a.fthr2 = threshold(1.0 / q / env);
         }
-        plan->table = a.table != nullptr && a.thr1 != a.thr2;
+        // membership matters when common and far neighbours weigh differently (q != 1), and for the extra bar of the
+        // folded return edge ("is t a neighbour of v?"), which a scan of a hub row would make the whole cost of q == 1
+        plan->table = a.table != nullptr && (a.thr1 != a.thr2 || plan->fold);
         if (!plan->table) a.table = nullptr;
+        if (!plan->table || opt.edge_filter_mb <= 0) a.filter = EdgeFilter{};
+        if (!plan->table) a.asymmetric = nullptr;
     }
     return TRW_OK;
 }
@@ -523,8 +576,8 @@ void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int wa
                         bool* want_table, bool* want_strict, bool* want_records) {
     const Options& opt = options();
     *uniform = (p == 1.0 && q == 1.0);
-    *want_table = !*uniform && q != 1.0;  // thr1 == thr2 iff q == 1
     *want_strict = !*uniform && ((opt.n2v_fold != 0 && 1.0 / p > fmax(1.0, 1.0 / q)) || (opt.n2v_mix != 0 && q > 1.0 && p <= q));
+    *want_table = !*uniform && (q != 1.0 || *want_strict);  // thr1 == thr2 iff q == 1; folding asks "t in adj(v)?"
     // Records save about a tenth of the walk's gathers and cost one pass over col_idx: worth building
     // per call when the walk fetches more than ~3 random lines per CSR entry (measured break-even on
     // the benchmark graphs; lines per step: 1 first-order, ~1.5 for q <= 1, ~0.85 q + 0.8 for q > 1).
@@ -645,7 +698,7 @@ extern "C" int trw_csr_graph_prepare(const int64_t* row_ptr, const int64_t* col_
     if (!h) { set_error("trw_csr_graph_prepare: out of host memory"); return TRW_ERR_ARG; }
     const int rc = csr_graph_prepare(&h->g, row_ptr, col_idx, n_nodes, nnz, /*uniform=*/false, /*want_table=*/true,
                                      /*want_strict=*/true, /*want_records=*/options().records != 0, workspace,
-                                     workspace_bytes, d, (cudaStream_t)stream);
+                                     workspace_bytes, d, (cudaStream_t)stream, /*bloom_cap=*/options().edge_bloom_cap);
     if (rc) { delete h; return rc; }
     *out_graph = h;
     return TRW_OK;
@@ -667,3 +720,29 @@ extern "C" int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* 
 }
 
 extern "C" void trw_csr_graph_destroy(trw_csr_graph* graph) { delete graph; }
+
+extern "C" int trw_csr_graph_info(const trw_csr_graph* graph, void* stream, int64_t* out, int n_out) {
+    if (!graph || !out || n_out < 6) { set_error("trw_csr_graph_info: null argument or room for fewer than 6 values"); return TRW_ERR_ARG; }
+    DeviceGuard guard(graph->g.device);
+    if (!guard.ok) { set_error("trw_csr_graph_info: cudaSetDevice(%d) failed", graph->g.device); return TRW_ERR_DEVICE; }
+    const CsrPrepared& pr = graph->g.prepared;
+    cudaStream_t st = (cudaStream_t)stream;
+    int flags[2] = {0, 0};  // table_failed, asymmetric
+    if (pr.table_failed) {
+        int rc = check_cuda(cudaMemcpyAsync(&flags[0], pr.table_failed, sizeof(int), cudaMemcpyDeviceToHost, st), "read table flag");
+        if (rc) return rc;
+    }
+    if (pr.asymmetric) {
+        int rc = check_cuda(cudaMemcpyAsync(&flags[1], pr.asymmetric, sizeof(int), cudaMemcpyDeviceToHost, st), "read symmetry flag");
+        if (rc) return rc;
+    }
+    int rc = check_cuda(cudaStreamSynchronize(st), "trw_csr_graph_info");
+    if (rc) return rc;
+    out[0] = pr.table != nullptr;
+    out[1] = pr.records != nullptr;
+    out[2] = pr.filter.bits ? (int64_t)pr.filter.n_bits : 0;
+    out[3] = pr.asymmetric != nullptr;                       // triangle Blooms were computed
+    out[4] = pr.asymmetric ? (flags[1] == 0 ? 1 : 0) : -1;   // symmetric: 1 yes, 0 no, -1 not checked
+    out[5] = flags[0];
+    return TRW_OK;
+}

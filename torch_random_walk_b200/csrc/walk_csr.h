@@ -20,6 +20,8 @@ struct WalkArgs {
     const int* table_failed;  // device flag raised by the build when a hub segment overflowed
     const uint32_t* row32;  // uint32 copy of row_ptr (nullptr: read the int64 row_ptr)
     const uint4* records;   // edge records (member_table.cuh), or nullptr
+    EdgeFilter filter;      // L2-resident edge filter in front of the table (bits == nullptr: none)
+    const int* asymmetric;  // device flag of the triangle-Bloom pass (member_table.cuh); nullptr: symmetry unknown
     uint64_t thr0, thr1, thr2;  // acceptance thresholds on a 32-bit uniform, scaled by 2^32
     // return-edge folding (see node2vec_walk_kernel): envelope M', excess 1/p - M', thresholds 1/M', (1/q)/M'
     uint64_t fthr1, fthr2;
@@ -47,7 +49,7 @@ struct CsrWalkPlan {
 
 int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                       bool uniform, bool want_table, bool want_strict, bool want_records, void* workspace,
-                      size_t workspace_bytes, int device, cudaStream_t st);
+                      size_t workspace_bytes, int device, cudaStream_t st, int64_t bloom_cap = 0);
 int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int walk_length, int64_t seed);
 void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int walk_length, bool* uniform,
                         bool* want_table, bool* want_strict, bool* want_records);

@@ -80,6 +80,7 @@ __device__ __forceinline__ bool el_is_neighbor_table(const IndexedWalkArgs& a, i
     int64_t first, last;
     if (!row_range(a, t, first, last)) return false;
     if (last <= first) return false;  // one out-edge: the scanned range is empty
+    if ((uint64_t)x >= (uint64_t)kEmpty) return el_is_neighbor(a, x, t);  // an id the uint32 table never holds
     if (!is_member<true>(x, first, last + 1, a.col, a.table, pol_stream)) return false;
     if (ldg64_hint(a.col + last, pol_stream) != x) return true;
     return member_twice(x, first, last + 1, a.table, pol_stream);
@@ -107,8 +108,14 @@ __global__ void __launch_bounds__(256) edge_list_view_kernel(const int64_t* __re
     };
     for (int64_t v = gtid; v <= n_index_rows; v += gsz) {
         const int64_t b = lower_bound(v);
-        row_ptr[v] = v == n_index_rows ? n_rows : b;  // edges whose head lies outside the index belong to no row
-        if (v == n_index_rows) break;
+        row_ptr[v] = v == n_index_rows ? n_rows : b;
+        // edges whose head lies outside the index belong to no row of it: the CSR view would hand them to
+        // the first or last row, so such a list takes the reference's scan instead
+        if (v == 0 && b != 0) *mismatch = 1;
+        if (v == n_index_rows) {
+            if (b != n_rows) *mismatch = 1;
+            break;
+        }
         const int64_t e = lower_bound(v + 1);
         const int64_t first = __ldg(index + 2 * v), last = __ldg(index + 2 * v + 1);
         const bool has = !(first == -1 || last == -1);
@@ -245,7 +252,7 @@ struct EdgeListWorkspace {
 };
 static EdgeListWorkspace edge_list_workspace_layout(int64_t n_edges, int64_t n_index_rows) {
     EdgeListWorkspace l{};
-    l.w = csr_workspace_layout(n_index_rows, n_edges, /*uniform=*/false, /*records=*/false);
+    l.w = csr_workspace_layout(n_index_rows, n_edges, /*uniform=*/false, /*records=*/false, /*filter=*/false);
     size_t off = 0;
     l.col = off; off += align256((size_t)n_edges * 8);
     l.row_ptr = off; off += align256((size_t)(n_index_rows + 1) * 8);

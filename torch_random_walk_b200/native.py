@@ -47,6 +47,7 @@ def _load():
                                           _c_ptr]
     lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
     lib.trw_csr_graph_destroy.restype = None
+    lib.trw_csr_graph_info.argtypes = [_c_ptr, _c_ptr, ctypes.POINTER(_c_i64), _c_int]
     lib.trw_walk_csr.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
                                  _c_i64, _c_ptr, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr]
     lib.trw_walk_csr_host.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
@@ -67,7 +68,7 @@ def _load():
     lib.trw_windows_triples_cbow.argtypes = wint
     lib.trw_calib_gather.argtypes = [_c_ptr, _c_i64, _c_i64, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_ptr]
     lib.trw_device_check.argtypes = [_c_int]
-    if lib.trw_abi_version() != 2:
+    if lib.trw_abi_version() != 3:
         raise ImportError("libtrw_b200.so ABI version mismatch; rebuild with python -m torch_random_walk_b200._build")
     return lib
 
@@ -180,6 +181,19 @@ class PreparedCsr:
                                               int(walk_length), int(seed), _ptr(walks), walks.stride(0) if n else wl,
                                               _stream(dev)))
         return walks
+
+    def info(self):
+        """What the preparation built (trw_csr_graph_info; waits for the preparing stream)."""
+        vals = (_c_i64 * 6)()
+        with torch.cuda.device(self.device):
+            _check(_lib.trw_csr_graph_info(self._handle, ctypes.c_void_p(self._stream_id), vals, 6))
+        keys = ("table", "records", "edge_filter_bits", "triangle_blooms", "symmetric", "table_overflowed")
+        return dict(zip(keys, (int(v) for v in vals)))
+
+    @property
+    def symmetric(self):
+        """True when the triangle-Bloom pass proved that every stored (t -> v) has its (v -> t)."""
+        return self.info()["symmetric"] == 1
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
