@@ -100,9 +100,34 @@ size_t trw_csr_graph_workspace_bytes(int64_t n_nodes, int64_t nnz);
 int trw_csr_graph_prepare(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                           void* workspace, size_t workspace_bytes, int device, void* stream,
                           trw_csr_graph** out_graph);
+/* As above with the triangle-Bloom pass chosen per call: bloom_cap < 0 the library default (option
+ * edge_bloom_cap, 256), 0 none (trw_csr_graph_add_blooms can add them later), > 0 that cap. */
+int trw_csr_graph_prepare_ex(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                             void* workspace, size_t workspace_bytes, int device, void* stream,
+                             int64_t bloom_cap, trw_csr_graph** out_graph);
 int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* targets, int64_t n_walks,
                           int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
                           int64_t* out, int64_t out_row_stride, void* stream);
+/* The same walk with the CSR arrays at another address: for callers that have verified, with
+ * trw_csr_checksum, that (row_ptr, col_idx) hold exactly what the graph was prepared from.  This is how the
+ * Python binding keeps a prepared graph across rw.walk calls without holding on to the caller's tensors.
+ * Global walk ids (the Philox counters): local walk i is walk_id_offset + i, or, for a block-cyclic shard
+ * (walk_id_block > 0), walk_id_offset + (i / walk_id_block) * walk_id_stride + i % walk_id_block -- rank r of
+ * W ranks with blocks of B walks passes (r*B, B, W*B). */
+int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx,
+                             const int64_t* targets, int64_t n_walks,
+                             int64_t walk_id_offset, int64_t walk_id_block, int64_t walk_id_stride,
+                             double p, double q, int walk_length, int64_t seed,
+                             int64_t* out, int64_t out_row_stride, void* stream);
+/* Adds the triangle Blooms (a 32-bit Bloom of the common neighbours of every edge's endpoints,
+ * kept in the edge records) to a graph prepared without them; one pass, quadratic in `cap`, the longest
+ * "shorter row" it works out exactly (<= 0: the library default).  No-op when already present. */
+int trw_csr_graph_add_blooms(trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx, int64_t cap, void* stream);
+/* 64-bit position-sensitive checksum of (row_ptr[n_nodes+1], col_idx[nnz]) into *out_device (device memory):
+ * one streaming pass on `stream`.  Equal sizes and checksums identify the graph a kept preparation belongs
+ * to; the reference, being stateless (csrc/cuda/rw_cuda.cu:186-248), needs no such thing. */
+int trw_csr_checksum(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                     uint64_t* out_device, int device, void* stream);
 void trw_csr_graph_destroy(trw_csr_graph* graph);
 /* What a prepared graph holds, after waiting for `stream` (the stream it was prepared on):
  * out[0] membership table, out[1] edge records, out[2] bits of the L2-resident edge filter (0: none),

@@ -20,6 +20,39 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_block_cyclic_shards_partition_the_list():
+    for n in (0, 1, 4095, 4096, 4097, 100003):
+        for world in (1, 2, 3, 8):
+            for block in (1, 7, 4096):
+                parts = [trw_dist.block_cyclic_indices(n, r, world, block) for r in range(world)]
+                assert [p.numel() for p in parts] == [trw_dist.block_cyclic_count(n, r, world, block) for r in range(world)]
+                allidx = torch.cat(parts)
+                assert allidx.numel() == n and torch.equal(torch.sort(allidx).values, torch.arange(n))
+                sizes = [p.numel() for p in parts]
+                assert max(sizes) - min(sizes) <= block
+                # the (offset, block, stride) triple the kernels use reproduces the index list
+                for r, p in enumerate(parts):
+                    i = torch.arange(p.numel())
+                    assert torch.equal(p, r * block + (i // block) * (block * world) + i % block)
+
+
+def test_walk_digest_adds_up_over_any_partition():
+    g = torch.Generator().manual_seed(3)
+    walks = torch.randint(0, 1 << 40, (5000, 17), generator=g)
+    ids = torch.arange(5000)
+    whole = trw_dist.walk_digest(walks, ids)
+    for world, block in ((2, 64), (3, 4096), (8, 5)):
+        parts = [trw_dist.block_cyclic_indices(5000, r, world, block) for r in range(world)]
+        total = sum(int(trw_dist.walk_digest(walks[p], p)) for p in parts)
+        assert (total - int(whole)) % (1 << 64) == 0
+    perm = torch.randperm(5000, generator=g)
+    assert int(trw_dist.walk_digest(walks[perm], ids[perm])) == int(whole)
+    changed = walks.clone()
+    changed[123, 5] += 1
+    assert int(trw_dist.walk_digest(changed, ids)) != int(whole)
+    assert int(trw_dist.walk_digest(walks, ids + 1)) != int(whole)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -211,24 +211,65 @@ def test_prepared_graph_and_graph_cache(native, rw):
 
     native.set_graph_cache(True)
     try:
-        launches = []
-        for k in range(4):
+        launches, states = [], []
+        for k in range(6):
             native.reset_launch_count()
             assert torch.equal(rw.walk(rp, ci, nodes, 1.0, 0.5, 30, 11), base[1])
             launches.append(native.launch_count())
-        # call 1 one-shot (build + walk), call 2 prepares for keeps, calls 3+ are the walk kernel alone
-        assert launches[2] == 1 and launches[3] == 1 and launches[0] > 1 and launches[1] > launches[0]
+            states.append(native.graph_cache_state(rp.device))
+        # call 1 one-shot (checksum + build + walk), call 2 prepares for keeps, the call after two hits adds the
+        # triangle Blooms, every later call is checksum + walk kernel
+        assert launches[0] > 2 and launches[1] > launches[0]
+        assert [st["prepared"] for st in states] == [False, True, True, True, True, True]
+        assert [st["blooms"] for st in states] == [False, False, False, True, True, True]
+        assert launches[2] == 2 and launches[3] == 3 and launches[4] == 2 and launches[5] == 2
         assert torch.equal(rw.walk(rp, ci, nodes, 0.25, 4.0, 30, 11), base[3])  # same graph, other law: still cached
-        # an in-place edit bumps the version counter: the cached preparation must not be used
+        # the cache goes by content: a re-created tensor with the same bytes hits ...
+        native.reset_launch_count()
+        assert torch.equal(rw.walk(rp.clone(), ci.clone(), nodes, 0.5, 2.0, 30, 11), base[2])
+        assert native.launch_count() == 2
+        # ... and any write is seen, whether torch counts it (in-place op) or not (.data, a view made earlier)
         ci2 = ci.clone()
-        for _ in range(3):
+        for _ in range(4):
             ref = rw.walk(rp, ci2, nodes, 1.0, 0.5, 30, 11)
-        ci2[rp[5]:rp[6]] = ci2[rp[5]]  # all neighbours of node 5 become the same node
+        assert native.graph_cache_state(rp.device)["blooms"]
+        version = ci2._version
+        ci2.data[rp[5]:rp[6]] = ci2[rp[5]]  # all neighbours of node 5 become the same node; no version bump
+        assert ci2._version == version
         edited = rw.walk(rp, ci2, nodes, 1.0, 0.5, 30, 11)
         assert torch.equal(edited, native.walk(rp, ci2, nodes, 1.0, 0.5, 30, 11, cache=False))
         assert not torch.equal(edited, ref)
+        assert not native.graph_cache_state(rp.device)["prepared"]  # the stale preparation was dropped, not used
+        # the cache holds no reference to the caller's tensors
+        import weakref
+        probe = ci2.clone()
+        for _ in range(3):
+            rw.walk(rp, probe, nodes, 1.0, 0.5, 30, 11)
+        assert native.graph_cache_state(rp.device)["prepared"]
+        alive = weakref.ref(probe)
+        del probe
+        assert alive() is None
     finally:
         native.set_graph_cache(False)
+
+
+def test_checksum_sees_every_element(native):
+    rp, ci = cuda(*random_csr(8, 3000, 20))
+    base = native.csr_checksum(rp, ci)
+    assert base == native.csr_checksum(rp.clone(), ci.clone())
+    for arr in (rp, ci):
+        for pos in (0, 1, arr.numel() // 2, arr.numel() - 1):
+            keep = int(arr[pos])
+            arr[pos] = keep + 1
+            assert native.csr_checksum(rp, ci) != base
+            arr[pos] = keep
+    swapped = ci.clone()
+    i = int(rp[7])
+    if swapped[i] != swapped[i + 1]:
+        swapped[i], swapped[i + 1] = ci[i + 1], ci[i]
+        assert native.csr_checksum(rp, swapped) != base  # position-sensitive
+    assert native.csr_checksum(rp, ci[1:]) != base        # unaligned start, shorter array
+    assert native.csr_checksum(rp, ci) == base
 
 
 def _clustered_csr(seed, n, communities, avg_deg):

@@ -701,16 +701,24 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
         rc = check_cuda(cudaGetLastError(), "edge records launch");
         if (rc) return rc;
         out->records = records;
-        if (bloom_cap > 0 && out->table != nullptr && build_mode != 0) {
-            int* asymmetric = (int*)(ws + w.cells + 192);
-            edge_bloom_kernel<<<sms * 8, kBloomWarps * 32, 0, st>>>(col_idx, nnz, b.row32, n_nodes, records, out->table, out->filter,
-                                                                     (uint32_t)std::min<int64_t>(bloom_cap, 1 << 20), b.failed, asymmetric);
-            count_launch(1);
-            rc = check_cuda(cudaGetLastError(), "edge bloom launch");
-            if (rc) return rc;
-            out->asymmetric = asymmetric;
-        }
+        out->bloom_flag = (int*)(ws + w.cells + 192);
+        if (bloom_cap > 0 && build_mode != 0) return csr_add_blooms(out, col_idx, n_nodes, nnz, bloom_cap, device, st);
     }
+    return TRW_OK;
+}
+
+int csr_add_blooms(CsrPrepared* pr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, int64_t cap, int device, cudaStream_t st) {
+    if (pr->asymmetric != nullptr || cap <= 0) return TRW_OK;  // already there
+    if (!pr->table || !pr->records || !pr->row32 || !pr->bloom_flag || nnz <= 0) return TRW_OK;  // nothing to hang them on
+    int rc = check_cuda(cudaMemsetAsync(pr->bloom_flag, 0, sizeof(int), st), "bloom flag memset");
+    if (rc) return rc;
+    edge_bloom_kernel<<<sm_count(device) * 8, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, const_cast<uint4*>(pr->records),
+                                                                          pr->table, pr->filter, (uint32_t)std::min<int64_t>(cap, 1 << 20),
+                                                                          pr->table_failed, pr->bloom_flag);
+    count_launch(1);
+    rc = check_cuda(cudaGetLastError(), "edge bloom launch");
+    if (rc) return rc;
+    pr->asymmetric = pr->bloom_flag;
     return TRW_OK;
 }
 

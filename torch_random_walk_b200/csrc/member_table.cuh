@@ -205,6 +205,7 @@ struct CsrPrepared {
     const uint4* records = nullptr;      // edge records, or nullptr
     EdgeFilter filter;                   // L2-resident edge filter (bits == nullptr: none)
     const int* asymmetric = nullptr;     // device flag of the triangle-Bloom pass: non-zero when some (t -> v) has no (v -> t); nullptr: not checked
+    int* bloom_flag = nullptr;           // where that flag lives once the pass has run (workspace cell)
 };
 
 // Enqueues on `st` the per-call preparation of a CSR graph: the uint32 row index and (node2vec)
@@ -213,5 +214,9 @@ struct CsrPrepared {
 int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
                        const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, bool want_records,
                        int build_mode, int device, cudaStream_t st, CsrPrepared* out, int64_t bloom_cap = 0);
+
+// Adds the triangle Blooms to the edge records of a prepared graph (no-op when they are there, or when the
+// graph has no table / records to hang them on).
+int csr_add_blooms(CsrPrepared* pr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, int64_t cap, int device, cudaStream_t st);
 
 }  // namespace trw

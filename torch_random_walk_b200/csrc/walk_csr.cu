@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = i < a.n_walks;  // lanes past the end stay for the warp-collective stores
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
-    const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
+    const uint64_t wid = global_walk_id(a, i);
     RowOut<BLOCK, STAGE> o;
     o.init(ring, a.out + (live ? i : 0) * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
 
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = i < a.n_walks;  // lanes past the end stay for the warp-collective stores
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
-    const uint64_t wid = (uint64_t)(a.walk_id_offset + i);
+    const uint64_t wid = global_walk_id(a, i);
     RowOut<BLOCK, STAGE, SLOTS> o;
     o.init(ring, a.out + (live ? i : 0) * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
     const int L = a.walk_length;
@@ -587,10 +587,12 @@ void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int wa
 }
 
 int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
-                    int64_t* out, int64_t out_row_stride, cudaStream_t st) {
+                    int64_t* out, int64_t out_row_stride, cudaStream_t st, int64_t id_block, int64_t id_stride) {
     if (n_walks <= 0) return TRW_OK;
+    if (id_block < 0 || (id_block > 0 && id_stride < id_block)) { set_error("walk ids: stride must be at least one block"); return TRW_ERR_ARG; }
     WalkArgs a = plan.a;
     a.targets = targets; a.n_walks = n_walks; a.walk_id_offset = walk_id_offset;
+    a.id_block = id_block; a.id_stride = id_stride;
     a.out = out; a.out_row_stride = out_row_stride;
     const bool stage = plan.stage && (((uintptr_t)out & 7) == 0);
     const bool row32 = a.row32 != nullptr;
@@ -684,6 +686,12 @@ extern "C" size_t trw_csr_graph_workspace_bytes(int64_t n_nodes, int64_t nnz) {
 extern "C" int trw_csr_graph_prepare(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                                      void* workspace, size_t workspace_bytes, int device, void* stream,
                                      trw_csr_graph** out_graph) {
+    return trw_csr_graph_prepare_ex(row_ptr, col_idx, n_nodes, nnz, workspace, workspace_bytes, device, stream, -1, out_graph);
+}
+
+extern "C" int trw_csr_graph_prepare_ex(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                                        void* workspace, size_t workspace_bytes, int device, void* stream,
+                                        int64_t bloom_cap, trw_csr_graph** out_graph) {
     if (!out_graph) { set_error("trw_csr_graph_prepare: null out_graph"); return TRW_ERR_ARG; }
     *out_graph = nullptr;
     const int d = resolve_device(device);
@@ -698,7 +706,7 @@ extern "C" int trw_csr_graph_prepare(const int64_t* row_ptr, const int64_t* col_
     if (!h) { set_error("trw_csr_graph_prepare: out of host memory"); return TRW_ERR_ARG; }
     const int rc = csr_graph_prepare(&h->g, row_ptr, col_idx, n_nodes, nnz, /*uniform=*/false, /*want_table=*/true,
                                      /*want_strict=*/true, /*want_records=*/options().records != 0, workspace,
-                                     workspace_bytes, d, (cudaStream_t)stream, /*bloom_cap=*/options().edge_bloom_cap);
+                                     workspace_bytes, d, (cudaStream_t)stream, bloom_cap < 0 ? options().edge_bloom_cap : bloom_cap);
     if (rc) { delete h; return rc; }
     *out_graph = h;
     return TRW_OK;
@@ -717,6 +725,46 @@ extern "C" int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* 
     rc = csr_walk_plan(&plan, graph->g, p, q, walk_length, seed);
     if (rc) return rc;
     return csr_walk_launch(plan, targets, n_walks, walk_id_offset, out, out_row_stride, (cudaStream_t)stream);
+}
+
+// The same walk over a prepared graph whose CSR arrays now live at (row_ptr, col_idx): for callers that have
+// verified (trw_csr_checksum) that these arrays hold what was prepared.  Nothing of the handle is changed.
+extern "C" int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx,
+                                        const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, int64_t walk_id_block,
+                                        int64_t walk_id_stride, double p, double q, int walk_length, int64_t seed, int64_t* out,
+                                        int64_t out_row_stride, void* stream) {
+    if (!graph) { set_error("trw_walk_csr_prepared_at: null graph"); return TRW_ERR_ARG; }
+    if (!row_ptr || (graph->g.nnz > 0 && !col_idx)) { set_error("trw_walk_csr_prepared_at: null pointer"); return TRW_ERR_ARG; }
+    int rc = walk_args_check("trw_walk_csr_prepared_at", targets, n_walks, walk_length, out, out_row_stride);
+    if (rc) return rc;
+    if (n_walks == 0) return TRW_OK;
+    DeviceGuard guard(graph->g.device);
+    if (!guard.ok) { set_error("trw_walk_csr_prepared_at: cudaSetDevice(%d) failed", graph->g.device); return TRW_ERR_DEVICE; }
+    CsrGraph g = graph->g;
+    g.row_ptr = row_ptr;
+    g.col_idx = col_idx;
+    CsrWalkPlan plan;
+    rc = csr_walk_plan(&plan, g, p, q, walk_length, seed);
+    if (rc) return rc;
+    return csr_walk_launch(plan, targets, n_walks, walk_id_offset, out, out_row_stride, (cudaStream_t)stream, walk_id_block,
+                           walk_id_stride);
+}
+
+// Adds the triangle Blooms (member_table.cuh) to a graph that was prepared without them: one pass over the
+// edge records in the graph's workspace.  `cap` <= 0 selects option edge_bloom_cap.
+extern "C" int trw_csr_graph_add_blooms(trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx, int64_t cap,
+                                        void* stream) {
+    if (!graph) { set_error("trw_csr_graph_add_blooms: null graph"); return TRW_ERR_ARG; }
+    DeviceGuard guard(graph->g.device);
+    if (!guard.ok) { set_error("trw_csr_graph_add_blooms: cudaSetDevice(%d) failed", graph->g.device); return TRW_ERR_DEVICE; }
+    if (cap <= 0) cap = options().edge_bloom_cap;
+    if (cap <= 0) return TRW_OK;
+    timing_begin(0, (cudaStream_t)stream);
+    const int rc = csr_add_blooms(&graph->g.prepared, col_idx ? col_idx : graph->g.col_idx, graph->g.n_nodes, graph->g.nnz, cap,
+                                  graph->g.device, (cudaStream_t)stream);
+    timing_end(0, (cudaStream_t)stream);
+    (void)row_ptr;
+    return rc;
 }
 
 extern "C" void trw_csr_graph_destroy(trw_csr_graph* graph) { delete graph; }

@@ -11,6 +11,7 @@ struct WalkArgs {
     int64_t n_nodes, nnz;
     const int64_t* targets;
     int64_t n_walks, walk_id_offset;
+    int64_t id_block, id_stride;  // block-cyclic shards: local walk i has global id offset + (i / block) * stride + i % block (block 0: offset + i)
     int walk_length;
     int store_mode;  // experiment: L2 policy of the output stores (see output_policy)
     uint2 key;
@@ -54,6 +55,14 @@ int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int 
 void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int walk_length, bool* uniform,
                         bool* want_table, bool* want_strict, bool* want_records);
 int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
-                    int64_t* out, int64_t out_row_stride, cudaStream_t st);
+                    int64_t* out, int64_t out_row_stride, cudaStream_t st, int64_t id_block = 0, int64_t id_stride = 0);
+
+// Global id of local walk i (the Philox counter): contiguous shards add an offset, block-cyclic ones
+// (dist.py) own every stride-th block of `block` consecutive ids.
+__device__ __forceinline__ uint64_t global_walk_id(const WalkArgs& a, int64_t i) {
+    if (a.id_block <= 0) return (uint64_t)(a.walk_id_offset + i);
+    const int64_t blk = i / a.id_block;
+    return (uint64_t)(a.walk_id_offset + blk * a.id_stride + (i - blk * a.id_block));
+}
 
 }  // namespace trw

@@ -3,8 +3,11 @@ the CPU tests).  The reference has no distributed code; w
 independent, so the only collective is the one-off replication of the CSR, and start nodes are
 sharded with no traffic while walking.
 
-Each shard passes its global walk offset to the kernels, which key Philox by the *global* walk id:
-the concatenation of all shards is bit-identical to a single-GPU call for every world size.
+Each shard passes its global walk ids to the kernels, which key Philox by the *global* walk id:
+the union of all shards is bit-identical to a single-GPU call for every world size and for both
+shard layouts -- contiguous slices (the simplest drop-in) and block-cyclic (every world-th block of
+4096 walks: start nodes sorted by id are sorted by degree on R-MAT-like graphs, and interleaving
+blocks evens the ranks out).
 """
 import torch
 import torch.distributed as dist
@@ -23,6 +26,46 @@ def shard_targets(target_nodes: torch.Tensor, rank=None, world_size=None):
     world_size = dist.get_world_size() if world_size is None else world_size
     lo, hi = shard_bounds(target_nodes.size(0), rank, world_size)
     return target_nodes[lo:hi], lo
+
+
+DEFAULT_BLOCK = 4096
+
+
+def block_cyclic_count(n_items: int, rank: int, world_size: int, block: int = DEFAULT_BLOCK) -> int:
+    """Number of items rank `rank` owns when blocks of `block` consecutive items are dealt round-robin."""
+    n_items, block = int(n_items), int(block)
+    full_rounds, rest = divmod(n_items, block * world_size)
+    return full_rounds * block + min(max(rest - rank * block, 0), block)
+
+
+def block_cyclic_indices(n_items: int, rank: int, world_size: int, block: int = DEFAULT_BLOCK, device=None):
+    """Global indices of the items rank `rank` owns, in its local order: local item i is global
+    rank*block + (i // block) * (block*world_size) + i % block."""
+    m = block_cyclic_count(n_items, rank, world_size, block)
+    i = torch.arange(m, dtype=torch.int64, device=device)
+    blk = torch.div(i, block, rounding_mode="floor")
+    return rank * block + blk * (block * world_size) + (i - blk * block)
+
+
+def shard_targets_block_cyclic(target_nodes: torch.Tensor, rank=None, world_size=None, block: int = DEFAULT_BLOCK):
+    """-> (this rank's start nodes, (walk_id_offset, walk_id_block, walk_id_stride)) for a block-cyclic shard:
+    the triple is what the walk needs to number its local walks globally."""
+    rank = dist.get_rank() if rank is None else rank
+    world_size = dist.get_world_size() if world_size is None else world_size
+    idx = block_cyclic_indices(target_nodes.size(0), rank, world_size, block, device=target_nodes.device)
+    return target_nodes[idx].contiguous(), (rank * block, block, block * world_size)
+
+
+def walk_digest(walks: torch.Tensor, global_ids: torch.Tensor) -> torch.Tensor:
+    """Order- and partition-independent digest of walk rows: a wrapping int64 sum over rows of a hash of
+    (row content, global walk id).  The digests of the shards of any partition add up to the digest of the
+    single call, which is how bench.py checks on real multi-GPU runs that sharding changed nothing."""
+    cols = walks.size(1)
+    w = (torch.arange(1, cols + 1, dtype=torch.int64, device=walks.device) * 0x9E3779B1 + 0x7F4A7C15) | 1
+    h = (walks * w).sum(1) + global_ids.to(walks.device) * 0x632BE5AB
+    h = (h ^ (h >> 29)) * 0x2545F4914F6CDD1D
+    h = h ^ (h >> 32)
+    return h.sum()
 
 
 def replicate_csr(row_ptr, col_idx, src=0, device=None, group=None):
@@ -72,3 +115,40 @@ def walk_sharded(row_ptr, col_idx, target_nodes, p, q, walk_length, seed, gather
     if gather:
         return gather_walks(walks, target_nodes.size(0))
     return walks
+
+
+class ReplicatedCsr:
+    """The north star's multi-GPU form: one NCCL broadcast puts the CSR on every rank, each rank prepares it
+    once (native.prepare_csr: table, edge records, triangle Blooms) and then walks its shard of any start-node
+    list with global walk ids -- no traffic while walking.  The replica belongs to this object (the ranks
+    other than `src` never had another copy), so it is kept without per-call validation; `src`'s own
+    tensors must not be modified while it lives."""
+
+    def __init__(self, row_ptr, col_idx, src=0, device=None, group=None, blooms=True):
+        from . import native
+
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.row_ptr, self.col_idx = replicate_csr(row_ptr, col_idx, src=src, device=device, group=group)
+        self.graph = native.prepare_csr(self.row_ptr, self.col_idx, blooms=blooms)
+
+    def shard(self, target_nodes, layout="block_cyclic", block=DEFAULT_BLOCK):
+        """-> (local start nodes, walk_id_offset, walk_id_blocks or None, global ids of the local walks)."""
+        n = target_nodes.size(0)
+        if layout == "contiguous":
+            lo, hi = shard_bounds(n, self.rank, self.world)
+            return target_nodes[lo:hi].contiguous(), lo, None, torch.arange(lo, hi, device=target_nodes.device)
+        if layout != "block_cyclic":
+            raise ValueError("layout must be 'contiguous' or 'block_cyclic'")
+        local, (off, blk, stride) = shard_targets_block_cyclic(target_nodes, self.rank, self.world, block)
+        return local, off, (blk, stride), block_cyclic_indices(n, self.rank, self.world, block, device=target_nodes.device)
+
+    def walk(self, target_nodes, p, q, walk_length, seed, layout="block_cyclic", block=DEFAULT_BLOCK, out=None):
+        """Walks this rank's shard of `target_nodes` (the full list, identical on every rank)."""
+        local, off, blocks, _ = self.shard(target_nodes, layout, block)
+        return self.graph.walk(local, p, q, walk_length, seed, walk_id_offset=off, walk_id_blocks=blocks, out=out)
+
+    def walk_local(self, local_targets, p, q, walk_length, seed, walk_id_offset, walk_id_blocks=None, out=None):
+        """The same for a shard the caller has already cut (bench.py keeps the shard across calls)."""
+        return self.graph.walk(local_targets, p, q, walk_length, seed, walk_id_offset=walk_id_offset,
+                               walk_id_blocks=walk_id_blocks, out=out)

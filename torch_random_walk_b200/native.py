@@ -10,7 +10,7 @@ import of this module.
 """
 import ctypes
 import os
-import weakref
+import threading
 
 import torch
 
@@ -43,6 +43,12 @@ def _load():
     lib.trw_csr_graph_workspace_bytes.argtypes = [_c_i64, _c_i64]
     lib.trw_csr_graph_prepare.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr,
                                           ctypes.POINTER(_c_ptr)]
+    lib.trw_csr_graph_prepare_ex.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr, _c_i64,
+                                             ctypes.POINTER(_c_ptr)]
+    lib.trw_walk_csr_prepared_at.argtypes = [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
+                                             _c_i64, _c_ptr, _c_i64, _c_ptr]
+    lib.trw_csr_graph_add_blooms.argtypes = [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_ptr]
+    lib.trw_csr_checksum.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_int, _c_ptr]
     lib.trw_walk_csr_prepared.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_i64,
                                           _c_ptr]
     lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
@@ -143,43 +149,72 @@ def _check_out(out, n, wl, dev):
 
 class PreparedCsr:
     """A CSR graph prepared once for any number of walks (trw_csr_graph_prepare): the uint32 row
-    index, the membership table, the duplicate-edge check and the edge records live in a workspace
-    tensor this object owns.  It keeps `row_ptr` / `column_idx` alive; they must not be modified
-    while it is in use.  Walks through it are bit-identical to the one-shot call."""
+    index, the membership table, the duplicate-edge check, the edge records and (blooms=True) their
+    triangle Blooms live in a workspace tensor this object owns (24 bytes per CSR entry).  With
+    hold=True (the explicit prepare_csr handle) it keeps `row_ptr` / `column_idx` alive and they must
+    not be modified while it is in use; with hold=False every walk names the arrays it runs on, which
+    the caller has verified to hold the prepared content (the graph cache of `walk` does, by
+    checksum).  Walks through it are bit-identical to the one-shot call."""
 
-    def __init__(self, row_ptr, column_idx):
+    def __init__(self, row_ptr, column_idx, hold=True, blooms=True):
         _require_cuda(row_ptr, "row_ptr")
         _require_cuda(column_idx, "column_idx")
-        self.row_ptr, self.column_idx = row_ptr.contiguous(), column_idx.contiguous()
+        row_ptr, column_idx = row_ptr.contiguous(), column_idx.contiguous()
+        self.row_ptr, self.column_idx = (row_ptr, column_idx) if hold else (None, None)
         self.device = row_ptr.device
-        self.n_nodes, self.nnz = max(self.row_ptr.numel() - 1, 0), self.column_idx.numel()
+        self.n_nodes, self.nnz = max(row_ptr.numel() - 1, 0), column_idx.numel()
         self._handle = _c_ptr()
         self._destroy = _lib.trw_csr_graph_destroy  # bound now: module globals may be gone at interpreter exit
+        self.has_blooms = bool(blooms)
         with torch.cuda.device(self.device):
             need = _lib.trw_csr_graph_workspace_bytes(self.n_nodes, self.nnz)
             self.workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=self.device)
-            _check(_lib.trw_csr_graph_prepare(_ptr(self.row_ptr), _ptr(self.column_idx), self.n_nodes, self.nnz,
-                                              _ptr(self.workspace) if need else None, need, self.device.index,
-                                              _stream(self.device), ctypes.byref(self._handle)))
+            _check(_lib.trw_csr_graph_prepare_ex(_ptr(row_ptr), _ptr(column_idx), self.n_nodes, self.nnz,
+                                                 _ptr(self.workspace) if need else None, need, self.device.index,
+                                                 _stream(self.device), -1 if blooms else 0, ctypes.byref(self._handle)))
             self._ready = torch.cuda.Event()
             self._ready.record(torch.cuda.current_stream(self.device))
             self._stream_id = torch.cuda.current_stream(self.device).cuda_stream
 
-    def walk(self, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None):
+    def _order_after_preparation(self, stream):
+        if stream.cuda_stream != self._stream_id:  # prepared on another stream: order after it, tell the allocator
+            stream.wait_event(self._ready)
+            self.workspace.record_stream(stream)
+
+    def add_blooms(self, row_ptr=None, column_idx=None, cap=0):
+        """Adds the triangle Blooms to a graph prepared without them (trw_csr_graph_add_blooms): one pass,
+        ~0.3 s on a 0.5 G-entry R-MAT at the default cap, after which q != 1 walks probe memory far less."""
+        ci = self.column_idx if column_idx is None else column_idx
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            self._order_after_preparation(stream)
+            _check(_lib.trw_csr_graph_add_blooms(self._handle, None, _ptr(ci) if ci is not None else None, int(cap),
+                                                 ctypes.c_void_p(stream.cuda_stream)))
+            self._ready.record(stream)
+            self._stream_id = stream.cuda_stream
+        self.has_blooms = True
+
+    def walk(self, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None, csr=None, walk_id_blocks=None):
+        """`csr=(row_ptr, column_idx)`: the arrays this walk reads (required when the graph does not hold its own).
+        `walk_id_blocks=(block, stride)`: global ids of a block-cyclic shard (see dist.block_cyclic_shard)."""
+        id_block, id_stride = (0, 0) if walk_id_blocks is None else (int(walk_id_blocks[0]), int(walk_id_blocks[1]))
         _require_cuda(target_nodes, "target_nodes")
         dev = self.device
+        if target_nodes.device != dev:
+            raise RuntimeError(f"target_nodes is on {target_nodes.device}, the prepared graph on {dev}")
+        rp, ci = (self.row_ptr, self.column_idx) if csr is None else csr
+        if rp is None:
+            raise RuntimeError("this prepared graph does not hold its CSR arrays: pass csr=(row_ptr, column_idx)")
         target_nodes = target_nodes.contiguous()
         n, wl = target_nodes.size(0), int(walk_length) + 1
         _check_out(out, n, wl, dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
-            if stream.cuda_stream != self._stream_id:  # prepared on another stream: order after it, tell the allocator
-                stream.wait_event(self._ready)
-                self.workspace.record_stream(stream)
+            self._order_after_preparation(stream)
             walks = torch.empty((n, wl), dtype=torch.int64, device=dev) if out is None else out
-            _check(_lib.trw_walk_csr_prepared(self._handle, _ptr(target_nodes), n, int(walk_id_offset), float(p), float(q),
-                                              int(walk_length), int(seed), _ptr(walks), walks.stride(0) if n else wl,
-                                              _stream(dev)))
+            _check(_lib.trw_walk_csr_prepared_at(self._handle, _ptr(rp), _ptr(ci), _ptr(target_nodes), n, int(walk_id_offset),
+                                                 id_block, id_stride, float(p), float(q), int(walk_length), int(seed),
+                                                 _ptr(walks), walks.stride(0) if n else wl, _stream(dev)))
         return walks
 
     def info(self):
@@ -202,21 +237,52 @@ class PreparedCsr:
             destroy(h)
 
 
-def prepare_csr(row_ptr, column_idx):
-    """Explicit form of what rw.walk's graph cache does: prepare once, then `.walk(...)` many times."""
-    return PreparedCsr(row_ptr, column_idx)
+def prepare_csr(row_ptr, column_idx, blooms=True):
+    """Explicit form of what rw.walk's graph cache does: prepare once, then `.walk(...)` many times.  The
+    handle keeps the two tensors alive; they must not be modified while it is in use (no checksum here)."""
+    return PreparedCsr(row_ptr, column_idx, hold=True, blooms=blooms)
 
 
-# Graph cache of the drop-in `walk`: a user of the reference calls rw.walk(row_ptr, col_idx, ...) once
-# per epoch with the same tensors; the preparation of the graph is the same every time, so the last
-# graph per device is kept.  An entry is valid only for the very same tensor objects (held by weak
-# reference) at the same torch version counters, i.e. not modified in place since.  Writes that bypass
-# torch (raw pointers, other libraries) are not seen: call clear_graph_cache() after those, or switch
-# the cache off (set_graph_cache(False) or TRW_GRAPH_CACHE=0).  The cache holds
-# trw_csr_graph_workspace_bytes (24 bytes per CSR entry) of device memory per cached graph.
-_graph_cache = {}
-_seen_once = {}  # per device: signature of the last one-shot graph (a second call with it prepares the graph for keeps)
+def csr_checksum(row_ptr, column_idx):
+    """64-bit content checksum of a CSR graph on its device (trw_csr_checksum; one streaming pass, then a
+    host wait for 8 bytes).  Equal sizes and checksums identify the graph a kept preparation belongs to."""
+    dev = row_ptr.device
+    bufs = _checksum_bufs.get(dev.index)
+    if bufs is None:
+        bufs = (torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64).pin_memory(), torch.cuda.Event())
+        _checksum_bufs[dev.index] = bufs
+    d_buf, h_buf, done = bufs
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        _check(_lib.trw_csr_checksum(_ptr(row_ptr), _ptr(column_idx), max(row_ptr.numel() - 1, 0), column_idx.numel(),
+                                     _ptr(d_buf), dev.index, ctypes.c_void_p(stream.cuda_stream)))
+        h_buf.copy_(d_buf, non_blocking=True)
+        done.record(stream)
+        done.synchronize()
+    return int(h_buf.item())
+
+
+# Graph cache of the drop-in `walk`.  A user of the reference calls rw.walk(row_ptr, col_idx, ...) once
+# per epoch on the same graph; everything the walk derives from the graph is the same every time, so the
+# last graph per device is kept -- identified by CONTENT, not by tensor identity: every cached call first
+# checksums row_ptr and col_idx on the device (one streaming pass at HBM speed, 0.7 ms for the 4.3 GB of a
+# 0.5 G-entry graph, then a host wait for 8 bytes) and reuses a preparation only for equal sizes and equal
+# checksum.  Writes through `.data`, raw pointers, DLPack or another library are therefore seen like any
+# other, a re-created tensor with the same content hits, and the cache holds no reference to the caller's
+# tensors (they are named afresh by every call).  The preparation grows with use:
+#   call 1 on a graph   one-shot, everything built inside the call (the reference's stateless launcher)
+#   call 2              the graph is prepared for keeps (row index, table, edge records: ~10 ms on c3)
+#   call 2 + _BLOOM_AFTER_HITS   the triangle Blooms are added (~0.3 s on c3), later calls are the walk kernel alone
+# It costs trw_csr_graph_workspace_bytes (24 bytes per CSR entry) of device memory per device; when that
+# cannot be had the call falls back to the one-shot path.  clear_graph_cache(), set_graph_cache(False) or
+# TRW_GRAPH_CACHE=0 switch it off; the one-shot path needs no checksum.
+_graph_cache = {}   # device index -> dict(key=(n_nodes, nnz, checksum), graph=PreparedCsr, hits=int)
+_seen_once = {}     # device index -> key of the last one-shot graph (a second call with it prepares the graph for keeps)
+_no_room = {}       # device index -> key whose preparation ran out of memory (not retried)
+_checksum_bufs = {}
+_cache_lock = threading.RLock()
 _graph_cache_on = os.environ.get("TRW_GRAPH_CACHE", "1") != "0"
+_BLOOM_AFTER_HITS = int(os.environ.get("TRW_BLOOM_AFTER_HITS", "2"))
 
 
 def set_graph_cache(enabled):
@@ -231,48 +297,70 @@ def graph_cache_enabled():
 
 
 def clear_graph_cache():
-    _graph_cache.clear()
-    _seen_once.clear()
+    with _cache_lock:
+        _graph_cache.clear()
+        _seen_once.clear()
+        _no_room.clear()
 
 
-def _cached_graph(row_ptr, column_idx, create):
-    key = row_ptr.device.index
-    sig = (row_ptr.data_ptr(), row_ptr._version, row_ptr.numel(), column_idx.data_ptr(), column_idx._version,
-           column_idx.numel())
-    hit = _graph_cache.get(key)
-    if hit is not None:
-        rp_ref, ci_ref, old_sig, graph = hit
-        if rp_ref() is row_ptr and ci_ref() is column_idx and old_sig == sig:
-            return graph
-        del _graph_cache[key]  # frees the old workspace before the new one is allocated
-    if not create:
-        return None
-    graph = PreparedCsr(row_ptr, column_idx)
-    _graph_cache[key] = (weakref.ref(row_ptr), weakref.ref(column_idx), sig, graph)
-    return graph
+def graph_cache_state(device=None):
+    """For measurements and tests: what the cache holds for `device` (default: the current one)."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    with _cache_lock:
+        e = _graph_cache.get(idx)
+        if e is None:
+            return {"prepared": False, "hits": 0, "blooms": False}
+        return {"prepared": True, "hits": e["hits"], "blooms": e["graph"].has_blooms, "key": e["key"]}
+
+
+def _cached_walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_offset, out):
+    """The cached form of `walk`, or None when this call has to take the one-shot path."""
+    dev = row_ptr.device
+    key = (max(row_ptr.numel() - 1, 0), column_idx.numel(), csr_checksum(row_ptr, column_idx))
+    with _cache_lock:
+        entry = _graph_cache.get(dev.index)
+        if entry is not None and entry["key"] != key:
+            del _graph_cache[dev.index]  # another graph (or this one, modified): free the workspace before anything else is allocated
+            entry = None
+        if entry is None:
+            if _seen_once.get(dev.index) != key or _no_room.get(dev.index) == key:
+                _seen_once[dev.index] = key
+                return None
+            try:
+                graph = PreparedCsr(row_ptr, column_idx, hold=False, blooms=False)
+            except torch.cuda.OutOfMemoryError:
+                _no_room[dev.index] = key  # 24 bytes per entry do not fit beside the caller's data: stay one-shot
+                return None
+            entry = {"key": key, "graph": graph, "hits": 0}
+            _graph_cache[dev.index] = entry
+        else:
+            entry["hits"] += 1
+            if entry["hits"] >= _BLOOM_AFTER_HITS and not entry["graph"].has_blooms and not (p == 1.0 and q == 1.0):
+                entry["graph"].add_blooms(column_idx=column_idx)
+        graph = entry["graph"]
+    return graph.walk(target_nodes, p, q, walk_length, seed, walk_id_offset=walk_id_offset, out=out, csr=(row_ptr, column_idx))
 
 
 def walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None, cache=None):
     """csrc/rw_init.cpp:11-25 -> csrc/cuda/rw_cuda.cu:186-248.  Returns walks[n, walk_length+1] on
     row_ptr's device.  `walk_id_offset` / `out` are extensions for sharded callers; `cache` overrides
-    the graph cache for this call (None: the module setting).  The first call on a graph is one-shot
-    (everything built per call, like the reference's stateless launcher); the second call with the
-    same tensors prepares the graph for keeps, and later calls are the walk kernel alone.  Cached and
-    one-shot calls return identical walks."""
+    the graph cache for this call (None: the module setting).  With the cache, repeated calls on a graph
+    of the same content reuse its preparation (see the comment above _graph_cache); cached and one-shot
+    calls return identical walks."""
     _require_cuda(row_ptr, "row_ptr")
     _require_cuda(column_idx, "column_idx")
     _require_cuda(target_nodes, "target_nodes")
     dev = row_ptr.device
+    if column_idx.device != dev or target_nodes.device != dev:
+        raise RuntimeError(f"row_ptr, column_idx and target_nodes must be on one device (got {dev}, {column_idx.device}, "
+                           f"{target_nodes.device})")
     use_cache = _graph_cache_on if cache is None else bool(cache)
     n_nodes, nnz = max(row_ptr.numel() - 1, 0), column_idx.numel()
-    if use_cache and row_ptr.is_contiguous() and column_idx.is_contiguous() and nnz > 0 and target_nodes.size(0) > 0:
-        seen = _seen_once.get(dev.index)
-        sig = (row_ptr.data_ptr(), row_ptr._version, column_idx.data_ptr(), column_idx._version)
-        graph = _cached_graph(row_ptr, column_idx, create=(seen == sig))
-        if graph is not None:
-            return graph.walk(target_nodes, p, q, walk_length, seed, walk_id_offset=walk_id_offset, out=out)
-        _seen_once[dev.index] = sig
     row_ptr, column_idx, target_nodes = row_ptr.contiguous(), column_idx.contiguous(), target_nodes.contiguous()
+    if use_cache and nnz > 0 and target_nodes.size(0) > 0:
+        walks = _cached_walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_offset, out)
+        if walks is not None:
+            return walks
     n, wl = target_nodes.size(0), int(walk_length) + 1
     _check_out(out, n, wl, dev)
     with torch.cuda.device(dev):
