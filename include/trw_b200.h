@@ -139,11 +139,27 @@ int trw_csr_graph_info(const trw_csr_graph* graph, void* stream, int64_t* out, i
  * the start nodes to the device, walks in chunks and streams finished chunks back while the
  * next ones run.  Allocates its own device memory (kept between calls, grow-only, until
  * trw_release_cached_buffers) and returns after `out` is complete.  This is the end-to-end
- * path a caller holding CPU tensors uses. */
+ * path a caller holding CPU tensors uses.  A caller that comes back with the same host arrays finds
+ * the device replica of the graph kept: the walk starts on it at once while the host threads verify,
+ * by checksum, that the arrays still hold what was uploaded (a mismatch uploads afresh and walks again). */
 int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                       const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
                       double p, double q, int walk_length, int64_t seed,
                       int64_t* out, int device);
+
+/* The download half on its own, for a graph that is already on the device and prepared (each rank of a multi-GPU
+ * job runs this on its shard): start nodes from host memory, walks into host memory, chunks walked and copied back
+ * in a pipeline, uint32 on the wire when the ids fit and the host has the threads.  Global walk ids as in
+ * trw_walk_csr_prepared_at.  Returns after `out` is complete. */
+typedef struct trw_csr_graph_view {
+    const trw_csr_graph* graph; /* from trw_csr_graph_prepare                                              */
+    const int64_t* row_ptr;     /* device arrays holding the prepared content (NULL: those of the handle)  */
+    const int64_t* col_idx;
+    void* ready_stream;         /* stream the preparation was enqueued on (NULL: known to be complete)     */
+} trw_csr_graph_view;
+int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_t* targets, int64_t n_walks,
+                         int64_t walk_id_offset, int64_t walk_id_block, int64_t walk_id_stride,
+                         double p, double q, int walk_length, int64_t seed, int64_t* out);
 
 /* Frees the device buffers, streams and events trw_walk_csr_host keeps between calls. */
 void trw_release_cached_buffers(void);

@@ -712,6 +712,70 @@ def test_walk_host_matches_device_path(native):
         native.set_option("host_chunk_walks", 1 << 20)
 
 
+def test_walk_host_keeps_the_replica_and_notices_changes(native):
+    """The host entry keeps the device replica of the graph for a caller that comes back with the same arrays, grows
+    its preparation with use, and re-checks the arrays' content on every call: an in-place change of the host graph
+    must give the walks of the changed graph, never those of the stale replica."""
+    from torch_random_walk_b200 import rmat
+
+    rp, ci = rmat.rmat_csr(13, 16, seed=9)
+    rp, ci = rp.pin_memory(), ci.pin_memory()
+    n = rp.numel() - 1
+    nodes = torch.arange(n)
+    laws = ((1.0, 0.5), (0.5, 2.0), (1.0, 1.0))
+    expect = {law: native.walk(rp.cuda(), ci.cuda(), nodes.cuda(), law[0], law[1], 20, 3, cache=False).cpu() for law in laws}
+    saved = {k: native.get_option(k) for k in ("host_threads", "host_compress", "host_chunk_walks")}
+    try:
+        native.lib().trw_release_cached_buffers()
+        native.set_option("host_chunk_walks", 2048)
+        for threads, compress in ((2, 1), (12, 1), (12, 2)):
+            native.set_option("host_threads", threads)
+            native.set_option("host_compress", compress)
+            for rounds in range(6):  # fresh, full preparation, ..., triangle Blooms, steady
+                for law in laws:
+                    assert torch.equal(native.walk_host(rp, ci, nodes, law[0], law[1], 20, 3, device=0), expect[law]), (threads, compress, rounds, law)
+        # change the graph under the same pointers
+        lo, hi = int(rp[3]), int(rp[4])
+        ci[lo:hi] = ci[lo]
+        changed = native.walk(rp.cuda(), ci.cuda(), nodes.cuda(), 1.0, 0.5, 20, 3, cache=False).cpu()
+        assert not torch.equal(changed, expect[(1.0, 0.5)])
+        assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0), changed)
+        assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0), changed)
+        rp2 = rp.clone().pin_memory()  # same content at another address: a fresh upload, same walks
+        assert torch.equal(native.walk_host(rp2, ci, nodes, 1.0, 0.5, 20, 3, device=0), changed)
+        with pytest.raises(RuntimeError):
+            native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0, out=torch.empty((n, 20), dtype=torch.int64))
+    finally:
+        for k, v in saved.items():
+            native.set_option(k, v)
+        native.lib().trw_release_cached_buffers()
+
+
+def test_prepared_graph_walks_to_host(native):
+    from torch_random_walk_b200 import rmat
+    from torch_random_walk_b200.dist import block_cyclic_indices
+
+    rp, ci = rmat.rmat_csr(13, 16, device="cuda", seed=2)
+    n = rp.numel() - 1
+    nodes = torch.arange(n)
+    g = native.prepare_csr(rp, ci)
+    full = g.walk(nodes.cuda(), 1.0, 0.5, 25, 8).cpu()
+    saved = {k: native.get_option(k) for k in ("host_threads", "host_compress", "host_chunk_walks")}
+    try:
+        native.set_option("host_chunk_walks", 1024)
+        for threads, compress in ((1, 1), (12, 1), (12, 2), (12, 0)):
+            native.set_option("host_threads", threads)
+            native.set_option("host_compress", compress)
+            assert torch.equal(g.walk_to_host(nodes, 1.0, 0.5, 25, 8), full)
+            # a block-cyclic shard (rank 1 of 3, blocks of 256 walks) in several pipeline chunks
+            idx = block_cyclic_indices(n, 1, 3, 256)
+            part = g.walk_to_host(nodes[idx].contiguous(), 1.0, 0.5, 25, 8, walk_id_offset=256, walk_id_blocks=(256, 768))
+            assert torch.equal(part, full[idx])
+    finally:
+        for k, v in saved.items():
+            native.set_option(k, v)
+
+
 def test_walk_host_wire_formats_agree(native):
     """The host path sends col_idx and fetches the walks as uint32 when it has the threads for it; the
     int64 copies, the compressed path over several upload and download chunks, pageable and pinned

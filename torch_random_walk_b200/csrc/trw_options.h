@@ -25,9 +25,13 @@ struct Options {
     int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
     int64_t host_chunk_walks = 1 << 20;  // walks per pipelined chunk in trw_walk_csr_host
-    int64_t host_compress = 1;    // 1: trw_walk_csr_host sends col_idx and fetches the walks as uint32 when ids fit and >= 12 host threads are free
+    int64_t host_compress = 1;    // trw_walk_csr_host wire format when ids fit and >= 12 host threads are free: 1 col_idx up and walks back as uint32,
+                                  // 2 the same with every other chunk of walks copied as plain int64 (copy engine and host cores share the output), 0 plain
     int64_t host_threads = 0;     // host threads of the wire compression (0: the machine's, divided by LOCAL_WORLD_SIZE)
     int64_t host_up_chunk = 1 << 25;  // col_idx entries per compressed upload chunk
+    int64_t host_packed_share = -1; // of every 8 download chunks, how many travel as uint32 (-1: 8 with >= 12 host threads, else 0; host_compress = 2: 4)
+    int64_t host_keep_graph = 1;  // 1: trw_walk_csr_host keeps the device replica of the graph between calls (same host arrays, content
+                                  // checked by checksum on every call); needs host_cache_buffers
     int64_t host_cache_buffers = 1;  // 1: trw_walk_csr_host keeps its device buffers between calls
     int64_t store_mode = 0;       // output-store L2 policy experiment: 0 evict_first, 1 normal, 2 evict_last, 3 no stores
     int64_t smem_carveout_kb = 0; // > 0: preferred shared-memory carve-out (KB per SM) of the CSR walk kernels
@@ -39,7 +43,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share)
 
 Options& options();
 void count_launch(int n);

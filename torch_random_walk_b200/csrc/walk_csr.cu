@@ -626,6 +626,14 @@ struct trw_csr_graph {
     CsrGraph g;
 };
 
+namespace trw {
+int csr_graph_of_handle(const trw_csr_graph* h, CsrGraph* out) {
+    if (!h || !out) { set_error("null prepared graph"); return TRW_ERR_ARG; }
+    *out = h->g;
+    return TRW_OK;
+}
+}  // namespace trw
+
 extern "C" size_t trw_walk_csr_workspace_bytes(int64_t n_nodes, int64_t nnz, double p, double q) {
     if (n_nodes < 0 || nnz < 0) return 0;
     // sized for the larger of the two one-shot layouts (with records), so the auto rule never outgrows it

@@ -51,6 +51,7 @@ struct CsrWalkPlan {
 int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                       bool uniform, bool want_table, bool want_strict, bool want_records, void* workspace,
                       size_t workspace_bytes, int device, cudaStream_t st, int64_t bloom_cap = 0);
+int csr_graph_of_handle(const trw_csr_graph* h, CsrGraph* out);  // the graph behind a C-ABI handle (walk_csr.cu)
 int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int walk_length, int64_t seed);
 void csr_one_shot_needs(double p, double q, int64_t nnz, int64_t n_walks, int walk_length, bool* uniform,
                         bool* want_table, bool* want_strict, bool* want_records);

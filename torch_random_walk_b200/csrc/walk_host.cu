@@ -1,19 +1,23 @@
-// trw_walk_csr_host: the CSR walk for callers whose tensors live in host memory.
+// trw_walk_csr_host / trw_walk_csr_to_host: the CSR walk for callers whose tensors live in host memory.
 //
 // The reference has no such path (a CPU tensor simply ran csrc/cpu); a drop-in user who holds
 // CPU tensors still has to get them to the GPU and the walks back, and that round trip is what
 // an end-to-end measurement pays for.  So it is engineered rather than left to three blocking
-// copies: the graph goes up once, the start nodes are walked in chunks on one stream, and each
-// finished chunk is copied back on a second stream while the next chunk is being walked
-// (PCIe is full duplex and the copy engines run beside the SMs).
-//
-// What is left is the wire: 4.4 GB up and 5.7 GB back per C3 call at ~55 GB/s.  Node ids and CSR
-// entries fit 32 bits for every graph the fast paths take, and the host can narrow/widen at ~100 GB/s
-// with its cores (tools/host_bandwidth_probe.py), so with enough threads col_idx crosses PCIe as uint32
-// (narrowed chunk by chunk into pinned staging while the previous chunk is in flight, widened on the
-// device) and the walks come back as uint32 (narrowed on the device, widened by the host threads into
-// the caller's buffer while the next chunk is in flight).  Any id that does not fit falls back to the
-// plain copies.
+// copies:
+//   * the start nodes are walked in chunks on one stream and each finished chunk is copied back on a
+//     second stream while the next chunk is being walked (PCIe is full duplex, the copy engines run
+//     beside the SMs);
+//   * node ids fit 32 bits for every graph the fast paths take and the host can narrow/widen at
+//     ~100 GB/s with its cores, so with enough threads col_idx goes up and the walks come back as
+//     uint32, converted chunk by chunk while the neighbouring chunk is in flight; any id that does
+//     not fit falls back to plain copies;
+//   * the graph does not cross PCIe again when the caller comes back with the same arrays: the device
+//     replica and its preparation are kept per device, keyed by the host pointers and sizes and
+//     VALIDATED BY CONTENT on every call -- the host threads checksum row_ptr and col_idx (the same
+//     64-bit position-sensitive sum the device computed over the replica when it was uploaded,
+//     csr_checksum.cu) while the walk already runs on the kept replica; a mismatch throws that work
+//     away, uploads afresh and walks again.  Like the device-side graph cache the preparation grows
+//     with use (per-call needs, then the full kept preparation, then the triangle Blooms).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -45,7 +49,20 @@ struct HostWalkCache {
     size_t pinned_cap[kNumPinned] = {};
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t walked[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}, uploaded[2] = {nullptr, nullptr};
+    std::mutex mu;  // one host-path call at a time per device
+    // the kept replica: which host arrays it mirrors, its device-side checksum, and what has been prepared on it
+    const void* key_row_ptr = nullptr;
+    const void* key_col_idx = nullptr;
+    int64_t key_n_nodes = -1, key_nnz = -1;
+    uint64_t replica_checksum = 0;
+    bool have_replica = false;
+    int level = -1;       // -1 nothing prepared, 0 what one call's (p, q) needed, 1 the full kept preparation, 2 with triangle Blooms
+    int needs_sig = 0;    // level 0: the needs it was prepared for
+    int hits = 0;
+    CsrGraph graph;
+    void forget_replica() { have_replica = false; level = -1; hits = 0; key_row_ptr = key_col_idx = nullptr; key_n_nodes = key_nnz = -1; }
     void release() {
+        forget_replica();
         if (compute) cudaStreamSynchronize(compute);
         if (copy) cudaStreamSynchronize(copy);
         for (int k = 0; k < kNumBufs; ++k) {
@@ -199,13 +216,169 @@ __global__ void __launch_bounds__(256) narrow_i64_kernel(const int64_t* __restri
     if (bad) *overflow = 1;
 }
 static HostWalkCache g_host_cache[64];
-static std::mutex g_host_mutex;
 
 #define TRW_TRY(expr, what)                       \
     do {                                          \
         int rc__ = check_cuda((expr), what);      \
         if (rc__) return rc__;                    \
     } while (0)
+
+// The host twin of csr_checksum_kernel (csr_checksum.cu): same sum, so a host array can be compared with its device replica.
+static inline uint64_t mix64_host(uint64_t z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+static uint64_t checksum_range(const int64_t* v, int64_t lo, int64_t hi, uint64_t golden) {
+    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // four independent chains keep the multipliers busy
+    int64_t i = lo;
+    for (; i + 4 <= hi; i += 4) {
+        a0 += mix64_host((uint64_t)v[i] + golden * (uint64_t)(i + 1));
+        a1 += mix64_host((uint64_t)v[i + 1] + golden * (uint64_t)(i + 2));
+        a2 += mix64_host((uint64_t)v[i + 2] + golden * (uint64_t)(i + 3));
+        a3 += mix64_host((uint64_t)v[i + 3] + golden * (uint64_t)(i + 4));
+    }
+    for (; i < hi; ++i) a0 += mix64_host((uint64_t)v[i] + golden * (uint64_t)(i + 1));
+    return a0 + a1 + a2 + a3;
+}
+static uint64_t host_csr_checksum(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, int n_threads) {
+    std::vector<uint64_t> part((size_t)std::max(n_threads, 1), 0);
+    parallel_for(std::max(n_threads, 1), [&](int tid, int nt) {
+        uint64_t acc = checksum_range(col_idx, nnz * tid / nt, nnz * (tid + 1) / nt, 0x9E3779B97F4A7C15ull);
+        const int64_t n_row = n_nodes + 1;
+        acc += checksum_range(row_ptr, n_row * tid / nt, n_row * (tid + 1) / nt, 0xD6E8FEB86659FD93ull);
+        part[(size_t)tid] = acc;
+    });
+    uint64_t total = 0;
+    for (uint64_t x : part) total += x;
+    return total;
+}
+
+constexpr int kRetryPlain = 1;  // host_pipeline: a walk entry did not fit the uint32 wire format
+
+struct HostCallShape {
+    int64_t n_walks, walk_id_offset, id_block, id_stride;
+    int walk_length;
+};
+
+// Walks `shape.n_walks` start nodes (already on the device) in chunks and streams the chunks into host memory.
+// `mode` of every 8 chunks are narrowed on the device, copied as uint32 and widened by `n_threads` host threads while the
+// next chunk is in flight; the others are int64 rows copied straight into `out` -- 0: plain copies, 8: everything packed,
+// in between the copy engine and the host cores each carry part of the output.  Waits for everything before it returns.
+static int host_pipeline(HostWalkCache& r, int d, const CsrWalkPlan& plan, const int64_t* d_targets, const HostCallShape& sh,
+                         int64_t* out, int mode, int n_threads) {
+    const int64_t row_len = (int64_t)sh.walk_length + 1;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(options().host_chunk_walks, sh.n_walks));
+    if (sh.id_block > 0 && chunk % sh.id_block != 0 && sh.n_walks > chunk) {
+        set_error("host walk: host_chunk_walks must be a multiple of the walk-id block (%lld)", (long long)sh.id_block);
+        return TRW_ERR_ARG;
+    }
+    const int n_buf = sh.n_walks > chunk ? 2 : 1;
+    int rc = TRW_OK;
+    for (int k = 0; k < n_buf && !rc; ++k) rc = r.reserve(kBufOut0 + k, (size_t)chunk * row_len * 8, "cudaMalloc walks");
+    if (mode != 0) {
+        const size_t down_bytes = (size_t)chunk * row_len * 4;
+        for (int k = 0; k < n_buf && !rc; ++k) {
+            rc = r.reserve(kBufDown0 + k, down_bytes + 256, "cudaMalloc download staging");
+            if (!rc) rc = r.reserve_pinned(kPinDown0 + k, down_bytes, "cudaHostAlloc download staging");
+        }
+    }
+    if (rc) return rc;
+    void* const d_out[2] = {r.ptr[kBufOut0], r.ptr[kBufOut1]};
+    int* d_overflow = mode != 0 ? (int*)((char*)r.ptr[kBufDown0] + (size_t)chunk * row_len * 4) : nullptr;  // the 256 spare bytes
+    if (mode != 0) TRW_TRY(cudaMemsetAsync(d_overflow, 0, sizeof(int), r.compute), "overflow flag memset");
+    // widen a chunk that has landed in pinned staging into the caller's buffer with the host threads
+    auto widen_to_caller = [&](int b, int64_t first_walk, int64_t m) {
+        const uint32_t* stage = (const uint32_t*)r.pinned[kPinDown0 + b];
+        int64_t* dst = out + first_walk * row_len;
+        const int64_t n_el = m * row_len;
+        parallel_for(n_threads, [&](int tid, int nt) {
+            const int64_t lo = n_el * tid / nt, hi = n_el * (tid + 1) / nt;
+            widen_to_i64(stage + lo, dst + lo, hi - lo);
+        });
+    };
+    int64_t done = 0, prev_first = 0, prev_m = 0;
+    int prev_b = -1;  // a compressed chunk whose widening is still owed
+    for (int c = 0; done < sh.n_walks; ++c) {
+        const int b = c & 1;
+        const int64_t m = std::min(chunk, sh.n_walks - done);
+        const bool packed = ((c + 1) * mode) / 8 != (c * mode) / 8;  // `mode` of every 8 chunks, evenly spread
+        if (c >= 2) TRW_TRY(cudaStreamWaitEvent(r.compute, r.copied[b], 0), "wait copied");
+        // ids of this chunk: contiguous shards advance the offset; block-cyclic ones advance it by whole strides
+        const int64_t off = sh.id_block > 0 ? sh.walk_id_offset + (done / sh.id_block) * sh.id_stride : sh.walk_id_offset + done;
+        rc = csr_walk_launch(plan, d_targets + done, m, off, (int64_t*)d_out[b], row_len, r.compute, sh.id_block, sh.id_stride);
+        if (rc) return rc;
+        if (packed) {
+            narrow_i64_kernel<<<sm_count(d) * 8, 256, 0, r.compute>>>((const int64_t*)d_out[b], (uint32_t*)r.ptr[kBufDown0 + b],
+                                                                     m * row_len, d_overflow);
+            count_launch(1);
+        }
+        TRW_TRY(cudaEventRecord(r.walked[b], r.compute), "record walked");
+        TRW_TRY(cudaStreamWaitEvent(r.copy, r.walked[b], 0), "wait walked");
+        if (packed)
+            TRW_TRY(cudaMemcpyAsync(r.pinned[kPinDown0 + b], r.ptr[kBufDown0 + b], (size_t)m * row_len * 4, cudaMemcpyDeviceToHost,
+                                    r.copy), "D2H walks (uint32)");
+        else
+            TRW_TRY(cudaMemcpyAsync(out + done * row_len, d_out[b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy),
+                    "D2H walks");
+        TRW_TRY(cudaEventRecord(r.copied[b], r.copy), "record copied");
+        if (prev_b >= 0) {  // the previous packed chunk has landed (or lands now): widen it while this one walks and copies
+            TRW_TRY(cudaEventSynchronize(r.copied[prev_b]), "wait previous chunk");
+            widen_to_caller(prev_b, prev_first, prev_m);
+            prev_b = -1;
+        }
+        if (packed) { prev_b = b; prev_first = done; prev_m = m; }
+        done += m;
+    }
+    TRW_TRY(cudaStreamSynchronize(r.compute), "sync compute");
+    TRW_TRY(cudaStreamSynchronize(r.copy), "sync copy");
+    if (prev_b >= 0) widen_to_caller(prev_b, prev_first, prev_m);
+    if (mode != 0) {
+        int overflow = 0;
+        TRW_TRY(cudaMemcpy(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost), "read overflow flag");
+        if (overflow) return kRetryPlain;  // an id beyond 32 bits came out of the graph: the caller walks again with plain copies
+    }
+    return TRW_OK;
+}
+static int host_pipeline_any(HostWalkCache& r, int d, const CsrWalkPlan& plan, const int64_t* d_targets, const HostCallShape& sh,
+                             int64_t* out, int mode, int n_threads) {
+    int rc = host_pipeline(r, d, plan, d_targets, sh, out, mode, n_threads);
+    if (rc == kRetryPlain) rc = host_pipeline(r, d, plan, d_targets, sh, out, 0, n_threads);
+    return rc;
+}
+
+// On any failure nothing may still be writing into the caller's buffers when the call returns.
+struct StreamDrain {
+    HostWalkCache* c;
+    ~StreamDrain() {
+        if (c->compute) cudaStreamSynchronize(c->compute);
+        if (c->copy) cudaStreamSynchronize(c->copy);
+        cudaGetLastError();
+    }
+};
+
+static int ensure_streams(HostWalkCache& r) {
+    if (r.compute) return TRW_OK;
+    TRW_TRY(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking), "stream create");
+    TRW_TRY(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking), "stream create");
+    for (int k = 0; k < 2; ++k) {
+        TRW_TRY(cudaEventCreateWithFlags(&r.walked[k], cudaEventDisableTiming), "event create");
+        TRW_TRY(cudaEventCreateWithFlags(&r.copied[k], cudaEventDisableTiming), "event create");
+        TRW_TRY(cudaEventCreateWithFlags(&r.uploaded[k], cudaEventDisableTiming), "event create");
+    }
+    return TRW_OK;
+}
+
+// Download mode for this call: option host_compress 0 plain, 1 packed (needs the threads), 2 alternating; ids must fit.
+static int download_mode(int n_threads, int64_t n_nodes, bool ids_fit) {
+    const int64_t want = options().host_compress;
+    if (want == 0 || !ids_fit || (uint64_t)n_nodes >= 0xFFFFFFFFull) return 0;
+    const int share = (int)options().host_packed_share;  // of 8 chunks, how many travel packed (-1: by thread count)
+    if (share >= 0) return share > 8 ? 8 : share;
+    if (n_threads >= kMinCompressThreads) return want == 2 ? 4 : 8;
+    return n_threads >= 4 && want == 2 ? 2 : 0;
+}
 
 }  // namespace trw
 
@@ -227,15 +400,9 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     if (n_walks == 0) return TRW_OK;
     DeviceGuard guard(d);
     if (!guard.ok) { set_error("trw_walk_csr_host: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }
-
-    const int64_t row_len = (int64_t)walk_length + 1;
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(options().host_chunk_walks, n_walks));
     if (!(p > 0.0) || !(q > 0.0)) { set_error("trw_walk_csr_host: p and q must be positive"); return TRW_ERR_ARG; }
-    bool uniform, want_table, want_strict, want_records;
-    csr_one_shot_needs(p, q, nnz, n_walks, walk_length, &uniform, &want_table, &want_strict, &want_records);
-    const size_t ws_bytes = csr_workspace_layout(n_nodes, nnz, uniform, want_records).total;
 
-    // TRW_HOST_TIMING=1 prints where an end-to-end call spends its time (adds one stream sync after the uploads).
+    // TRW_HOST_TIMING=1 prints where an end-to-end call spends its time.
     const bool timing = getenv("TRW_HOST_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
@@ -243,67 +410,106 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     };
     const auto t_start = now();
 
-    std::lock_guard<std::mutex> lock(g_host_mutex);
     HostWalkCache local;  // used (and released on return) when caching is off or the ordinal is unusual
     const bool cached = options().host_cache_buffers != 0 && d < 64;
     HostWalkCache& r = cached ? g_host_cache[d] : local;
+    std::lock_guard<std::mutex> lock(r.mu);
     struct Releaser {
         HostWalkCache* c;
         ~Releaser() { if (c) c->release(); }
     } releaser{cached ? nullptr : &local};
-    if (!r.compute) {
-        TRW_TRY(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking), "stream create");
-        TRW_TRY(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking), "stream create");
-        for (int k = 0; k < 2; ++k) {
-            TRW_TRY(cudaEventCreateWithFlags(&r.walked[k], cudaEventDisableTiming), "event create");
-            TRW_TRY(cudaEventCreateWithFlags(&r.copied[k], cudaEventDisableTiming), "event create");
-            TRW_TRY(cudaEventCreateWithFlags(&r.uploaded[k], cudaEventDisableTiming), "event create");
+    int rc = ensure_streams(r);
+    if (rc) return rc;
+    StreamDrain drain{&r};
+
+    const int n_threads = host_thread_count();
+    const HostCallShape shape{n_walks, walk_id_offset, 0, 0, walk_length};
+    bool uniform, want_table, want_strict, want_records;
+    csr_one_shot_needs(p, q, nnz, n_walks, walk_length, &uniform, &want_table, &want_strict, &want_records);
+    const int needs_sig = (uniform ? 1 : 0) | (want_table ? 2 : 0) | (want_strict ? 4 : 0) | (want_records ? 8 : 0);
+
+    rc = r.reserve(kBufTargets, (size_t)n_walks * 8, "cudaMalloc targets");
+    if (rc) return rc;
+    TRW_TRY(cudaMemcpyAsync(r.ptr[kBufTargets], targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
+    std::atomic<int> wide_targets{0};  // start nodes travel as int64, but their values come back inside the walks
+    if (options().host_compress != 0 && n_threads >= kMinCompressThreads)
+        parallel_for(n_threads, [&](int tid, int nt) {
+            bool bad = false;
+            for (int64_t i = n_walks * tid / nt, e = n_walks * (tid + 1) / nt; i < e; ++i) bad |= (uint64_t)targets[i] > 0xFFFFFFFFull;
+            if (bad) wide_targets.store(1, std::memory_order_relaxed);
+        });
+
+    // ---- the kept replica: same host arrays as last time?  Then walk on it at once and check its content meanwhile.
+    const bool keep = cached && options().host_keep_graph != 0;
+    if (keep && r.have_replica && r.key_row_ptr == row_ptr && r.key_col_idx == col_idx && r.key_n_nodes == n_nodes && r.key_nnz == nnz) {
+        const auto t_hit = now();
+        ++r.hits;
+        // grow the preparation with use: the full kept form on the first hit, the triangle Blooms two hits later
+        if (r.level < 1) {
+            const size_t ws_bytes = csr_workspace_layout(n_nodes, nnz, false, options().records != 0).total;
+            rc = r.reserve(kBufWorkspace, ws_bytes, "cudaMalloc workspace");
+            if (!rc) rc = csr_graph_prepare(&r.graph, (const int64_t*)r.ptr[kBufRowPtr], (const int64_t*)r.ptr[kBufColIdx], n_nodes, nnz,
+                                            /*uniform=*/false, /*want_table=*/true, /*want_strict=*/true, options().records != 0,
+                                            r.ptr[kBufWorkspace], ws_bytes, d, r.compute, /*bloom_cap=*/0);
+            if (rc) { r.forget_replica(); return rc; }
+            r.level = 1;
+        } else if (r.level == 1 && r.hits >= 3 && !uniform && options().edge_bloom_cap > 0) {
+            rc = csr_add_blooms(&r.graph.prepared, (const int64_t*)r.ptr[kBufColIdx], n_nodes, nnz, options().edge_bloom_cap, d, r.compute);
+            if (rc) { r.forget_replica(); return rc; }
+            r.level = 2;
         }
+        CsrWalkPlan plan;
+        rc = csr_walk_plan(&plan, r.graph, p, q, walk_length, seed);
+        if (rc) return rc;
+        // the content check runs on half of the host threads beside the pipeline (which widens with the other half)
+        const int check_threads = std::max(1, n_threads / 2);
+        uint64_t host_sum = 0;
+        std::thread checker([&] { host_sum = host_csr_checksum(row_ptr, col_idx, n_nodes, nnz, check_threads); });
+        // plain copies here: the checksum already keeps the host's memory system busy, and widening packed chunks beside it
+        // measured slower than the 55 GB/s the copy engine moves on its own (profiles/r02_host_path.md); option
+        // host_packed_share overrides
+        const int mode = options().host_packed_share >= 0 ? download_mode(n_threads, n_nodes, wide_targets.load() == 0) : 0;
+        rc = host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, mode, std::max(1, n_threads - check_threads));
+        checker.join();  // (the pipeline returns on every path; nothing above can throw)
+        if (rc) return rc;
+        if (host_sum == r.replica_checksum) {
+            if (timing)
+                fprintf(stderr, "[trw_walk_csr_host] kept replica (level %d, hit %d), download mode %d, %d host threads | total %.1f ms\n",
+                        r.level, r.hits, mode, n_threads, ms_since(t_hit));
+            return TRW_OK;
+        }
+        r.forget_replica();  // the arrays changed under the same pointers: upload afresh and walk again
     }
+
+    // ---- fresh upload
+    r.forget_replica();
+    const size_t ws_bytes = csr_workspace_layout(n_nodes, nnz, uniform, want_records).total;
     // Wire compression: ids and CSR entries must fit 32 bits (checked value by value on the way up) and the
     // host needs threads to spare (kMinCompressThreads).
-    const int n_threads = host_thread_count();
     bool compress = options().host_compress != 0 && n_threads >= kMinCompressThreads && (uint64_t)n_nodes < 0xFFFFFFFFull && nnz > 0;
     const int64_t up_chunk = std::max<int64_t>(1 << 16, options().host_up_chunk);
-
-    const int n_buf = n_walks > chunk ? 2 : 1;
-    int rc = r.reserve(kBufRowPtr, (size_t)(n_nodes + 1) * 8, "cudaMalloc row_ptr");
+    rc = r.reserve(kBufRowPtr, (size_t)(n_nodes + 1) * 8, "cudaMalloc row_ptr");
     if (!rc) rc = r.reserve(kBufColIdx, (size_t)nnz * 8, "cudaMalloc col_idx");
-    if (!rc) rc = r.reserve(kBufTargets, (size_t)n_walks * 8, "cudaMalloc targets");
     if (!rc && ws_bytes) rc = r.reserve(kBufWorkspace, ws_bytes, "cudaMalloc workspace");
-    for (int k = 0; k < n_buf && !rc; ++k) rc = r.reserve(kBufOut0 + k, (size_t)chunk * row_len * 8, "cudaMalloc walks");
     if (compress) {
-        const size_t up_bytes = (size_t)std::min<int64_t>(up_chunk, nnz) * 4, down_bytes = (size_t)chunk * row_len * 4;
+        const size_t up_bytes = (size_t)std::min<int64_t>(up_chunk, nnz) * 4;
         for (int k = 0; k < 2 && !rc; ++k) {
             rc = r.reserve(kBufUp0 + k, up_bytes, "cudaMalloc upload staging");
             if (!rc) rc = r.reserve_pinned(kPinUp0 + k, up_bytes, "cudaHostAlloc upload staging");
-        }
-        for (int k = 0; k < n_buf && !rc; ++k) {
-            rc = r.reserve(kBufDown0 + k, down_bytes + 256, "cudaMalloc download staging");
-            if (!rc) rc = r.reserve_pinned(kPinDown0 + k, down_bytes, "cudaHostAlloc download staging");
         }
     }
     if (rc) return rc;
     void* const d_row_ptr = r.ptr[kBufRowPtr];
     void* const d_col_idx = r.ptr[kBufColIdx];
-    void* const d_targets = r.ptr[kBufTargets];
     void* const d_workspace = ws_bytes ? r.ptr[kBufWorkspace] : nullptr;
-    void* const d_out[2] = {r.ptr[kBufOut0], r.ptr[kBufOut1]};
 
     const double ms_alloc = ms_since(t_start);
     const auto t_up = now();
     TRW_TRY(cudaMemcpyAsync(d_row_ptr, row_ptr, (size_t)(n_nodes + 1) * 8, cudaMemcpyHostToDevice, r.compute), "H2D row_ptr");
-    TRW_TRY(cudaMemcpyAsync(d_targets, targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
     if (compress) {
-        // start nodes travel as int64, but their values come back inside the uint32 walks
         std::atomic<int> wide{0};
-        parallel_for(n_threads, [&](int tid, int nt) {
-            bool bad = false;
-            for (int64_t i = n_walks * tid / nt, e = n_walks * (tid + 1) / nt; i < e; ++i) bad |= (uint64_t)targets[i] > 0xFFFFFFFFull;
-            if (bad) wide.store(1, std::memory_order_relaxed);
-        });
         int64_t sent = 0;
-        for (int k = 0; sent < nnz && !wide.load(); ++k) {
+        for (int k = 0; sent < nnz; ++k) {
             const int b = k & 1;
             const int64_t m = std::min(up_chunk, nnz - sent);
             if (k >= 2) TRW_TRY(cudaEventSynchronize(r.uploaded[b]), "wait upload staging");
@@ -334,81 +540,101 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         ms_upload = ms_since(t_up);
     }
     const auto t_walk = now();
-    CsrGraph graph;
-    rc = csr_graph_prepare(&graph, (const int64_t*)d_row_ptr, (const int64_t*)d_col_idx, n_nodes, nnz, uniform, want_table,
+    rc = csr_graph_prepare(&r.graph, (const int64_t*)d_row_ptr, (const int64_t*)d_col_idx, n_nodes, nnz, uniform, want_table,
                            want_strict, want_records, d_workspace, ws_bytes, d, r.compute);
     if (rc) return rc;
-    CsrWalkPlan plan;
-    rc = csr_walk_plan(&plan, graph, p, q, walk_length, seed);
-    if (rc) return rc;
-
-    int* d_overflow = compress ? (int*)((char*)r.ptr[kBufDown0] + (size_t)chunk * row_len * 4) : nullptr;  // the 256 spare bytes
-    if (compress) TRW_TRY(cudaMemsetAsync(d_overflow, 0, sizeof(int), r.compute), "overflow flag memset");
-    // widen chunk c (already in pinned staging) into the caller's buffer with the host threads
-    auto widen_to_caller = [&](int b, int64_t first_walk, int64_t m) {
-        const uint32_t* stage = (const uint32_t*)r.pinned[kPinDown0 + b];
-        int64_t* dst = out + first_walk * row_len;
-        const int64_t n_el = m * row_len;
-        parallel_for(n_threads, [&](int tid, int nt) {
-            const int64_t lo = n_el * tid / nt, hi = n_el * (tid + 1) / nt;
-            widen_to_i64(stage + lo, dst + lo, hi - lo);
-        });
-    };
-    int64_t done = 0, prev_first = 0, prev_m = 0;
-    int prev_b = -1;
-    for (int c = 0; done < n_walks; ++c) {
-        const int b = c & 1;
-        const int64_t m = std::min(chunk, n_walks - done);
-        if (c >= 2) TRW_TRY(cudaStreamWaitEvent(r.compute, r.copied[b], 0), "wait copied");
-        rc = csr_walk_launch(plan, (const int64_t*)d_targets + done, m, walk_id_offset + done, (int64_t*)d_out[b],
-                             row_len, r.compute);
+    if (keep) {
+        // the replica's own checksum (device side: it is what the host arrays will be compared with next time)
+        rc = r.reserve(kBufUp0, 256, "cudaMalloc checksum cell");
+        if (!rc) rc = r.reserve_pinned(kPinUp0, 256, "cudaHostAlloc checksum cell");
         if (rc) return rc;
-        if (compress) {
-            narrow_i64_kernel<<<sm_count(d) * 8, 256, 0, r.compute>>>((const int64_t*)d_out[b], (uint32_t*)r.ptr[kBufDown0 + b],
-                                                                     m * row_len, d_overflow);
-            count_launch(1);
-        }
-        TRW_TRY(cudaEventRecord(r.walked[b], r.compute), "record walked");
-        TRW_TRY(cudaStreamWaitEvent(r.copy, r.walked[b], 0), "wait walked");
-        if (compress)
-            TRW_TRY(cudaMemcpyAsync(r.pinned[kPinDown0 + b], r.ptr[kBufDown0 + b], (size_t)m * row_len * 4, cudaMemcpyDeviceToHost,
-                                    r.copy), "D2H walks (uint32)");
-        else
-            TRW_TRY(cudaMemcpyAsync(out + done * row_len, d_out[b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy),
-                    "D2H walks");
-        TRW_TRY(cudaEventRecord(r.copied[b], r.copy), "record copied");
-        if (compress && prev_b >= 0) {  // the previous chunk has landed (or lands now): widen it while this one walks and copies
-            TRW_TRY(cudaEventSynchronize(r.copied[prev_b]), "wait previous chunk");
-            widen_to_caller(prev_b, prev_first, prev_m);
-        }
-        prev_b = b; prev_first = done; prev_m = m;
-        done += m;
+        rc = trw_csr_checksum((const int64_t*)d_row_ptr, (const int64_t*)d_col_idx, n_nodes, nnz, (uint64_t*)r.ptr[kBufUp0], d, r.compute);
+        if (rc) return rc;
+        TRW_TRY(cudaMemcpyAsync(r.pinned[kPinUp0], r.ptr[kBufUp0], 8, cudaMemcpyDeviceToHost, r.compute), "D2H checksum");
     }
-    TRW_TRY(cudaStreamSynchronize(r.compute), "sync compute");
-    TRW_TRY(cudaStreamSynchronize(r.copy), "sync copy");
-    if (compress) {
-        if (prev_b >= 0) widen_to_caller(prev_b, prev_first, prev_m);
-        int overflow = 0;
-        TRW_TRY(cudaMemcpy(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost), "read overflow flag");
-        if (overflow) { set_error("trw_walk_csr_host: a walk entry did not fit the 32-bit wire format (internal error)"); return TRW_ERR_CUDA; }
+    CsrWalkPlan plan;
+    rc = csr_walk_plan(&plan, r.graph, p, q, walk_length, seed);
+    if (rc) return rc;
+    const int mode = download_mode(n_threads, n_nodes, compress && wide_targets.load() == 0);
+    rc = host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, mode, n_threads);
+    if (rc) return rc;
+    if (keep) {
+        r.replica_checksum = *(const uint64_t*)r.pinned[kPinUp0];  // the pipeline has synchronised the stream
+        r.key_row_ptr = row_ptr; r.key_col_idx = col_idx; r.key_n_nodes = n_nodes; r.key_nnz = nnz;
+        r.have_replica = true;
+        r.level = 0;
+        r.needs_sig = needs_sig;
+        r.hits = 0;
     }
     if (timing) {
         const double h2d_gb = ((double)(n_nodes + 1) + (double)nnz * (compress ? 0.5 : 1.0) + (double)n_walks) * 8 / 1e9;
-        const double d2h_gb = (double)n_walks * row_len * (compress ? 4 : 8) / 1e9;
-        fprintf(stderr, "[trw_walk_csr_host] %s, %d host threads | alloc %.1f ms | upload %.1f ms (%.2f GB, %.1f GB/s) | "
-                        "walk+download %.1f ms (%.2f GB back) | total %.1f ms\n",
-                compress ? "uint32 wire format" : "int64 copies", n_threads, ms_alloc, ms_upload, h2d_gb,
-                ms_upload > 0 ? h2d_gb / (ms_upload / 1e3) : 0.0, ms_since(t_walk), d2h_gb, ms_since(t_start));
+        fprintf(stderr, "[trw_walk_csr_host] fresh upload, %s up, download mode %d, %d host threads | alloc %.1f ms | upload %.1f ms "
+                        "(%.2f GB, %.1f GB/s) | prepare+walk+download %.1f ms | total %.1f ms\n",
+                compress ? "uint32" : "int64", mode, n_threads, ms_alloc, ms_upload, h2d_gb,
+                ms_upload > 0 ? h2d_gb / (ms_upload / 1e3) : 0.0, ms_since(t_walk), ms_since(t_start));
     }
     return TRW_OK;
 }
 
+// The download half on its own: the graph is already on the device and prepared (trw_csr_graph_prepare), the start
+// nodes and the walks live in host memory.  This is what each rank of a multi-GPU job runs on its shard.
+extern "C" int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_t* targets, int64_t n_walks,
+                                    int64_t walk_id_offset, int64_t walk_id_block, int64_t walk_id_stride, double p, double q,
+                                    int walk_length, int64_t seed, int64_t* out) {
+    if (!view || !view->graph) { set_error("trw_walk_csr_to_host: null graph"); return TRW_ERR_ARG; }
+    if (n_walks < 0 || walk_length < 0) { set_error("trw_walk_csr_to_host: negative size"); return TRW_ERR_ARG; }
+    if (n_walks > 0 && (!targets || !out)) { set_error("trw_walk_csr_to_host: null pointer"); return TRW_ERR_ARG; }
+    if (n_walks == 0) return TRW_OK;
+    CsrGraph g;
+    int rc = csr_graph_of_handle(view->graph, &g);
+    if (rc) return rc;
+    if (view->row_ptr) g.row_ptr = view->row_ptr;
+    if (view->col_idx) g.col_idx = view->col_idx;
+    const int d = g.device;
+    DeviceGuard guard(d);
+    if (!guard.ok) { set_error("trw_walk_csr_to_host: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }
+    HostWalkCache local;
+    const bool cached = options().host_cache_buffers != 0 && d < 64;
+    HostWalkCache& r = cached ? g_host_cache[d] : local;
+    std::lock_guard<std::mutex> lock(r.mu);
+    struct Releaser {
+        HostWalkCache* c;
+        ~Releaser() { if (c) c->release(); }
+    } releaser{cached ? nullptr : &local};
+    rc = ensure_streams(r);
+    if (rc) return rc;
+    StreamDrain drain{&r};
+    if (view->ready_stream) {  // order after whatever prepared the graph
+        TRW_TRY(cudaEventRecord(r.uploaded[0], (cudaStream_t)view->ready_stream), "record ready");
+        TRW_TRY(cudaStreamWaitEvent(r.compute, r.uploaded[0], 0), "wait ready");
+    }
+    rc = r.reserve(kBufTargets, (size_t)n_walks * 8, "cudaMalloc targets");
+    if (rc) return rc;
+    TRW_TRY(cudaMemcpyAsync(r.ptr[kBufTargets], targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
+    const int n_threads = host_thread_count();
+    bool ids_fit = true;
+    if (options().host_compress != 0 && n_threads >= kMinCompressThreads) {
+        std::atomic<int> wide{0};
+        parallel_for(n_threads, [&](int tid, int nt) {
+            bool bad = false;
+            for (int64_t i = n_walks * tid / nt, e = n_walks * (tid + 1) / nt; i < e; ++i) bad |= (uint64_t)targets[i] > 0xFFFFFFFFull;
+            if (bad) wide.store(1, std::memory_order_relaxed);
+        });
+        ids_fit = wide.load() == 0;
+    }
+    CsrWalkPlan plan;
+    rc = csr_walk_plan(&plan, g, p, q, walk_length, seed);
+    if (rc) return rc;
+    const HostCallShape shape{n_walks, walk_id_offset, walk_id_block, walk_id_stride, walk_length};
+    return host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, download_mode(n_threads, g.n_nodes, ids_fit), n_threads);
+}
+
 extern "C" void trw_release_cached_buffers(void) {
-    std::lock_guard<std::mutex> lock(g_host_mutex);
     int prev = -1;
     cudaGetDevice(&prev);
     for (int d = 0; d < 64; ++d) {
         HostWalkCache& c = g_host_cache[d];
+        std::lock_guard<std::mutex> lock(c.mu);
         bool used = c.compute != nullptr;
         for (int k = 0; k < kNumBufs; ++k) used |= c.ptr[k] != nullptr;
         if (!used) continue;

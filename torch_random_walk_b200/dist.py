@@ -148,6 +148,11 @@ class ReplicatedCsr:
         local, off, blocks, _ = self.shard(target_nodes, layout, block)
         return self.graph.walk(local, p, q, walk_length, seed, walk_id_offset=off, walk_id_blocks=blocks, out=out)
 
+    def walk_local_to_host(self, local_targets_host, p, q, walk_length, seed, walk_id_offset, walk_id_blocks=None, out=None):
+        """The rank's shard for start nodes and walks in HOST memory (native.PreparedCsr.walk_to_host)."""
+        return self.graph.walk_to_host(local_targets_host, p, q, walk_length, seed, walk_id_offset=walk_id_offset,
+                                       walk_id_blocks=walk_id_blocks, out=out)
+
     def walk_local(self, local_targets, p, q, walk_length, seed, walk_id_offset, walk_id_blocks=None, out=None):
         """The same for a shard the caller has already cut (bench.py keeps the shard across calls)."""
         return self.graph.walk(local_targets, p, q, walk_length, seed, walk_id_offset=walk_id_offset,

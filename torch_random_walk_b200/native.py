@@ -23,6 +23,11 @@ _c_ptr = ctypes.c_void_p
 _c_size = ctypes.c_size_t
 
 
+class _GraphView(ctypes.Structure):
+    """trw_csr_graph_view (include/trw_b200.h)."""
+    _fields_ = [("graph", ctypes.c_void_p), ("row_ptr", ctypes.c_void_p), ("col_idx", ctypes.c_void_p), ("ready_stream", ctypes.c_void_p)]
+
+
 def _load():
     path = _build.LIB_PATH
     if not os.path.exists(path):
@@ -49,6 +54,8 @@ def _load():
                                              _c_i64, _c_ptr, _c_i64, _c_ptr]
     lib.trw_csr_graph_add_blooms.argtypes = [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_ptr]
     lib.trw_csr_checksum.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_int, _c_ptr]
+    lib.trw_walk_csr_to_host.argtypes = [ctypes.POINTER(_GraphView), _c_ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
+                                         _c_i64, _c_ptr]
     lib.trw_walk_csr_prepared.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_i64,
                                           _c_ptr]
     lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
@@ -216,6 +223,21 @@ class PreparedCsr:
                                                  id_block, id_stride, float(p), float(q), int(walk_length), int(seed),
                                                  _ptr(walks), walks.stride(0) if n else wl, _stream(dev)))
         return walks
+
+    def walk_to_host(self, target_nodes, p, q, walk_length, seed, walk_id_offset=0, walk_id_blocks=None, out=None, csr=None):
+        """The walk for start nodes and walks that live in HOST memory (trw_walk_csr_to_host): the graph stays on the
+        device, chunks are walked and copied back in a pipeline.  Blocks until `out` is complete."""
+        rp, ci = (self.row_ptr, self.column_idx) if csr is None else csr
+        if rp is None:
+            raise RuntimeError("this prepared graph does not hold its CSR arrays: pass csr=(row_ptr, column_idx)")
+        target_nodes = _host_int64(target_nodes, "target_nodes")
+        n, wl = target_nodes.size(0), int(walk_length) + 1
+        out = _host_out(out, n, wl)
+        id_block, id_stride = (0, 0) if walk_id_blocks is None else (int(walk_id_blocks[0]), int(walk_id_blocks[1]))
+        view = _GraphView(self._handle, rp.data_ptr(), ci.data_ptr() if ci.numel() else None, self._stream_id)
+        _check(_lib.trw_walk_csr_to_host(ctypes.byref(view), _ptr(target_nodes), n, int(walk_id_offset), id_block, id_stride,
+                                         float(p), float(q), int(walk_length), int(seed), _ptr(out)))
+        return out
 
     def info(self):
         """What the preparation built (trw_csr_graph_info; waits for the preparing stream)."""
@@ -476,17 +498,33 @@ def to_windows_triples_cbow(walks, window_size, num_nodes, padding_idx, triples,
     return _triple_windows(_lib.trw_windows_triples_cbow, walks, window_size, num_nodes, padding_idx, triples, seed, True)
 
 
+def _host_int64(t, name):
+    if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.int64:
+        raise RuntimeError(f"(*{name}) must be an int64 CPU tensor for the host path")
+    return t.contiguous()
+
+
+def _host_out(out, n, wl):
+    """`out=` of the host entries: the C side writes n*wl int64 values through a raw pointer, so anything but a
+    contiguous int64 CPU tensor of exactly that shape is refused here."""
+    if out is None:
+        return torch.empty((n, wl), dtype=torch.int64, pin_memory=True)
+    if not (isinstance(out, torch.Tensor) and not out.is_cuda and out.dtype == torch.int64 and out.dim() == 2 and
+            out.size(0) == n and out.size(1) == wl and out.is_contiguous()):
+        raise RuntimeError(f"out must be a contiguous int64 CPU tensor of shape ({n}, {wl})")
+    return out
+
+
 def walk_host(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, device=0, walk_id_offset=0, out=None):
     """End-to-end entry for callers holding CPU tensors (trw_walk_csr_host): the graph and start
     nodes are copied to `device`, walked in chunks, and the walks are streamed back into a (pinned)
-    CPU tensor.  Still the CUDA path -- there is no CPU implementation to fall back to."""
-    for t, name in ((row_ptr, "row_ptr"), (column_idx, "column_idx"), (target_nodes, "target_nodes")):
-        if t.is_cuda or t.dtype != torch.int64:
-            raise RuntimeError(f"(*{name}) must be an int64 CPU tensor for walk_host")
-    row_ptr, column_idx, target_nodes = row_ptr.contiguous(), column_idx.contiguous(), target_nodes.contiguous()
+    CPU tensor.  A caller that comes back with the same arrays finds the device replica kept (its content
+    is re-checked by checksum on every call).  Still the CUDA path -- there is no CPU implementation to
+    fall back to."""
+    row_ptr, column_idx = _host_int64(row_ptr, "row_ptr"), _host_int64(column_idx, "column_idx")
+    target_nodes = _host_int64(target_nodes, "target_nodes")
     n, wl = target_nodes.size(0), int(walk_length) + 1
-    if out is None:
-        out = torch.empty((n, wl), dtype=torch.int64, pin_memory=True)
+    out = _host_out(out, n, wl)
     _check(_lib.trw_walk_csr_host(_ptr(row_ptr), _ptr(column_idx), max(row_ptr.numel() - 1, 0), column_idx.numel(),
                                   _ptr(target_nodes), n, int(walk_id_offset), float(p), float(q), int(walk_length),
                                   int(seed), _ptr(out), int(device)))
