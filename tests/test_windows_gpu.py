@@ -152,6 +152,24 @@ def test_row_fast_paths_equal_the_element_path(rw):
     assert int(fast[2].min()) >= 0 and int(fast[2].max()) < nodes
 
 
+def test_bulk_store_path_of_the_triple_windows_equals_plain_stores(rw):
+    """Option win_bulk hands every warp's staged rows to the copy engine (cp.async.bulk) instead of storing them
+    from the lanes; the tensors must be the same, for full tiles, a ragged last tile and odd row counts."""
+    from torch_random_walk_b200 import native
+
+    triples = torch.randint(0, 5000, (20011, 3), device="cuda")
+    for n, wl, W in ((1001, 81, 5), (37, 7, 2), (5, 3, 1), (64, 21, 3)):
+        walks = torch.randint(0, 5000, (n, wl), device="cuda")
+        plain = rw.to_windows_triples(walks, W, 5000, 4999, triples, 3) + rw.to_windows_triples_cbow(walks, W, 5000, 4999, triples, 3)
+        native.set_option("win_bulk", 1)
+        try:
+            bulk = rw.to_windows_triples(walks, W, 5000, 4999, triples, 3) + rw.to_windows_triples_cbow(walks, W, 5000, 4999, triples, 3)
+        finally:
+            native.set_option("win_bulk", 0)
+        for a, b in zip(plain, bulk):
+            assert torch.equal(a, b), (n, wl, W)
+
+
 def test_window_outputs_stay_inside_their_tensors(rw):
     """Guard bands around every output of the four window kernels (see the walk test of the same name)."""
     import ctypes

@@ -29,7 +29,11 @@ def timed(fn, reps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--walks", type=int, default=2_000_000)
+    ap.add_argument("--option", action="append", default=[], help="library option name=value")
     args = ap.parse_args()
+    for kv in args.option:
+        native.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+        print("option", kv, flush=True)
     n_nodes = 1 << 24
     walks = torch.randint(0, n_nodes, (args.walks, 81), dtype=torch.int64, device="cuda")
     for name, fn in (("to_windows W=5", lambda: native.to_windows(walks, 5, n_nodes, 1)),

@@ -38,6 +38,7 @@ struct WinArgs {
     int per_walk;  // windows (skip-gram/CBOW) or target triples per walk
     int tile_walks;
     int use_smem;
+    int bulk;          // triple modes: the warps' stages leave as bulk stores (cp.async.bulk) instead of 16-byte stores
     int64_t num_nodes, pad;
     const int64_t* triples;
     int64_t n_triples;
@@ -104,19 +105,46 @@ __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_
 // written directly would touch every 128-byte line of the warp's span three times, and requests,
 // not bytes, are what the memory system charges for.
 // ------------------------------------------------------------------------------------------
+constexpr size_t kMaxTileSmem = 176 * 1024;  // dynamic shared memory of a tile: 227 KiB per CTA less the 40 KiB of static stages, with room to spare
 constexpr int kNegChunkRows = 2048;  // negative rows drawn per round (8 KiB of row indices)
 constexpr int kWarpRows = 64;  // rows a warp stages per round: 1536 bytes, three 16-byte pieces per lane
 
 // Every warp takes blocks of kWarpRows consecutive rows of the segment: row_fn(row, stage_slot) writes one row's three
 // values, two rows per lane; then the warp streams its 1.5 KB to dst.  Only warp-level synchronisation.
-template <int BLOCK, class RowFn>
-__device__ __forceinline__ void emit_rows(int64_t* __restrict__ dst, uint32_t n_rows, int64_t* __restrict__ stage, RowFn row_fn) {
+//
+// BULK: the warp's 1.5 KB leave as ONE bulk store of the copy engine (cp.async.bulk.global.shared::cta, TMA's linear
+// form, SASS UBLKCP) issued by lane 0 from one of two stages per warp, instead of 16-byte stores from every lane.
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
+}
+
+template <int BLOCK, bool BULK, class RowFn>
+__device__ __forceinline__ void emit_rows(int64_t* __restrict__ dst, uint32_t n_rows, int64_t* __restrict__ stage, uint32_t& round,
+                                          RowFn row_fn) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t* wstage = stage + warp * (kWarpRows * 3);
     const bool vec = (((uintptr_t)dst) & 15) == 0;
     for (uint32_t first = warp * kWarpRows; first < n_rows; first += (BLOCK / 32) * kWarpRows) {
         const uint32_t cnt = min((uint32_t)kWarpRows, n_rows - first);
+        int64_t* wstage = stage + (warp * (BULK ? 2 : 1) + (BULK ? (round & 1u) : 0u)) * (kWarpRows * 3);
+        if (BULK) {  // this stage was handed to the copy engine two rounds ago
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
         for (uint32_t g = lane; g < cnt; g += 32) row_fn(first + g, wstage + 3u * g);
+        if (BULK && vec) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the lanes' writes -> visible to the copy engine
+            __syncwarp();
+            int64_t* out = dst + (uint64_t)first * 3u;
+            const uint32_t even = cnt & ~1u;  // the engine moves multiples of 16 bytes: an odd last row goes by hand
+            if (lane == 0) {
+                if (even) bulk_store(out, wstage, even * 24u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (cnt != even && lane < 3) out[(uint64_t)even * 3u + lane] = wstage[(size_t)even * 3u + lane];
+            ++round;
+            continue;
+        }
         __syncwarp();
         const uint32_t n_el = cnt * 3u;
         int64_t* out = dst + (uint64_t)first * 3u;  // first is even: 16-byte alignment carries over from dst
@@ -131,13 +159,13 @@ __device__ __forceinline__ void emit_rows(int64_t* __restrict__ dst, uint32_t n_
     }
 }
 
-template <int MODE, int BLOCK>
-__device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* tile, int64_t i0, int tw) {
-    __shared__ __align__(16) int64_t stage[(BLOCK / 32) * kWarpRows * 3];
+template <int MODE, int BLOCK, bool BULK>
+__device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* tile, int64_t i0, int tw, int64_t* stage) {
+    uint32_t round = 0;
     const uint32_t K = (uint32_t)a.per_walk, R = (uint32_t)(2 * a.W);
     const int pos_out = (MODE == kTriples) ? 1 : 2, neg_out = (MODE == kTriples) ? 2 : 1;
     // targets / pos_triples: row (i, ti) = walk[i][2*ti .. 2*ti+2]
-    emit_rows<BLOCK>(a.out[0] + (uint64_t)i0 * K * 3u, (uint32_t)tw * K, stage, [&](uint32_t row, int64_t* o) {
+    emit_rows<BLOCK, BULK>(a.out[0] + (uint64_t)i0 * K * 3u, (uint32_t)tw * K, stage, round, [&](uint32_t row, int64_t* o) {
         uint32_t i, ti;
         a.by_per_walk.divmod(row, i, ti);
         const int64_t* w = tile + (size_t)i * a.wl + 2u * ti;
@@ -145,7 +173,7 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
     });
     // positive windows: row (i, ti, h), the three slots of triple_window_value() at once
     if (R > 0) {
-        emit_rows<BLOCK>(a.out[pos_out] + (uint64_t)i0 * K * R * 3u, (uint32_t)tw * K * R, stage, [&](uint32_t row, int64_t* o) {
+        emit_rows<BLOCK, BULK>(a.out[pos_out] + (uint64_t)i0 * K * R * 3u, (uint32_t)tw * K * R, stage, round, [&](uint32_t row, int64_t* o) {
             uint32_t k, h, i, ti;
             a.by_row.divmod(row, k, h);
             a.by_per_walk.divmod(k, i, ti);
@@ -201,7 +229,7 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
         }
     } else {
         // neg_triples: one row per target, redrawn while identical to the positive triple (windows_cuda.cu:485-505)
-        emit_rows<BLOCK>(a.out[neg_out] + (uint64_t)i0 * K * 3u, (uint32_t)tw * K, stage, [&](uint32_t row, int64_t* o) {
+        emit_rows<BLOCK, BULK>(a.out[neg_out] + (uint64_t)i0 * K * 3u, (uint32_t)tw * K, stage, round, [&](uint32_t row, int64_t* o) {
             uint32_t i, ti;
             a.by_per_walk.divmod(row, i, ti);
             const uint64_t grow = ((uint64_t)i0 + i) * K + ti;
@@ -217,9 +245,10 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
             o[0] = nh; o[1] = nr; o[2] = nt;
         });
     }
+    if (BULK && (threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stages must outlive their copies
 }
 
-template <int MODE, int BLOCK>
+template <int MODE, int BLOCK, bool BULK = false>
 __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
     extern __shared__ __align__(16) int64_t smem_tile[];
     const int64_t i0 = (int64_t)blockIdx.x * a.tile_walks;
@@ -241,7 +270,8 @@ __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
         tile = smem_tile;
     }
     if constexpr (MODE == kTriples || MODE == kTriplesCbow) {
-        triple_tile<MODE, BLOCK>(a, tile, i0, tw);
+        __shared__ __align__(128) int64_t stage[(BLOCK / 32) * kWarpRows * 3 * (BULK ? 2 : 1)];  // per warp: one stage, two for bulk stores
+        triple_tile<MODE, BLOCK, BULK>(a, tile, i0, tw, stage);
     } else {
 #pragma unroll
     for (int which = 0; which < 3; ++which) {
@@ -344,21 +374,29 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     if (tw < 4) tw = 4;
     size_t smem = (size_t)tw * walk_cols * 8;
     a.use_smem = 1;
-    if (smem > 200 * 1024) { a.use_smem = 0; smem = 0; }
+    if (smem > kMaxTileSmem) { a.use_smem = 0; smem = 0; }
     a.tile_walks = (int)tw;
-    if (smem > 24 * 1024) {  // static shared memory (the negative-row chunk) counts against the 48 KiB default too
-        // raise the opt-in limit once per device and mode; the call is far too slow to repeat per launch
-        static size_t opted_in[64];
-        if (d >= 64 || opted_in[d] < smem) {
-            int rc = check_cuda(cudaFuncSetAttribute(windows_kernel<MODE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     200 * 1024), name);
+    // bulk stores need 16-byte aligned segments: true for whole tensors from any allocator worth the name and for
+    // tiles that start on a multiple of four walks
+    a.bulk = 0;
+    if (kTripleMode && options().win_bulk != 0 && (((uintptr_t)o0 | (uintptr_t)o1 | (uintptr_t)o2) & 15) == 0) a.bulk = 1;
+    const bool bulk = kTripleMode && a.bulk != 0;
+    if (kTripleMode || smem > 24 * 1024) {  // static shared memory (stages, drawn row indices) counts against the 48 KiB default too
+        // raise the opt-in limit once per device and kernel; the call is far too slow to repeat per launch
+        static size_t opted_in[64][2];
+        if (d >= 64 || opted_in[d][bulk] < smem) {
+            int rc = bulk ? check_cuda(cudaFuncSetAttribute(windows_kernel<MODE, BLOCK, kTripleMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                            (int)kMaxTileSmem), name)
+                          : check_cuda(cudaFuncSetAttribute(windows_kernel<MODE, BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                            (int)kMaxTileSmem), name);
             if (rc) return rc;
-            if (d < 64) opted_in[d] = 200 * 1024;
+            if (d < 64) opted_in[d][bulk] = kMaxTileSmem;
         }
     }
     const int64_t tiles = (n_walks + tw - 1) / tw;
     if (tiles > 0x7FFFFFFFll) { set_error("%s: too many tiles", name); return TRW_ERR_ARG; }
-    windows_kernel<MODE, BLOCK><<<(unsigned)tiles, BLOCK, smem, (cudaStream_t)stream>>>(a);
+    if (bulk) windows_kernel<MODE, BLOCK, kTripleMode><<<(unsigned)tiles, BLOCK, smem, (cudaStream_t)stream>>>(a);
+    else windows_kernel<MODE, BLOCK, false><<<(unsigned)tiles, BLOCK, smem, (cudaStream_t)stream>>>(a);
     count_launch(1);
     return check_cuda(cudaGetLastError(), name);
 }
