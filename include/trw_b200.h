@@ -114,7 +114,7 @@ int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* targets, in
  * Global walk ids (the Philox counters): local walk i is walk_id_offset + i, or, for a block-cyclic shard
  * (walk_id_block > 0), walk_id_offset + (i / walk_id_block) * walk_id_stride + i % walk_id_block -- rank r of
  * W ranks with blocks of B walks passes (r*B, B, W*B). */
-int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx,
+int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const void* row_ptr, const void* col_idx,
                              const int64_t* targets, int64_t n_walks,
                              int64_t walk_id_offset, int64_t walk_id_block, int64_t walk_id_stride,
                              double p, double q, int walk_length, int64_t seed,
@@ -122,13 +122,33 @@ int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const int64_t* row_ptr,
 /* Adds the triangle Blooms (a 32-bit Bloom of the common neighbours of every edge's endpoints,
  * kept in the edge records) to a graph prepared without them; one pass, quadratic in `cap`, the longest
  * "shorter row" it works out exactly (<= 0: the library default).  No-op when already present. */
-int trw_csr_graph_add_blooms(trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx, int64_t cap, void* stream);
+int trw_csr_graph_add_blooms(trw_csr_graph* graph, const void* row_ptr, const void* col_idx, int64_t cap, void* stream);
 /* 64-bit position-sensitive checksum of (row_ptr[n_nodes+1], col_idx[nnz]) into *out_device (device memory):
  * one streaming pass on `stream`.  Equal sizes and checksums identify the graph a kept preparation belongs
  * to; the reference, being stateless (csrc/cuda/rw_cuda.cu:186-248), needs no such thing. */
 int trw_csr_checksum(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                      uint64_t* out_device, int device, void* stream);
 void trw_csr_graph_destroy(trw_csr_graph* graph);
+
+/* ---------------------------------------------------------------------------------------
+ * CSR arrays with 32-bit elements.  The reference's accessors are int64-only
+ * (csrc/cuda/rw_cuda.cu:206-209: an int32 tensor raises); these entries take row_ptr and col_idx
+ * with 4- or 8-byte elements each (signed), which halves the graph in HBM and on PCIe.  Start
+ * nodes and walks stay int64, and the walks are bit-identical to the int64 call on the same
+ * values.  A graph prepared from typed arrays remembers their widths: trw_walk_csr_prepared_at,
+ * trw_csr_graph_add_blooms and trw_csr_graph_view take pointers to arrays of those same widths.
+ * ------------------------------------------------------------------------------------- */
+int trw_walk_csr_typed(const void* row_ptr, int row_ptr_bytes, const void* col_idx, int col_idx_bytes,
+                       int64_t n_nodes, int64_t nnz,
+                       const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
+                       double p, double q, int walk_length, int64_t seed,
+                       int64_t* out, int64_t out_row_stride,
+                       void* workspace, size_t workspace_bytes, int device, void* stream);
+int trw_csr_graph_prepare_typed(const void* row_ptr, int row_ptr_bytes, const void* col_idx, int col_idx_bytes,
+                                int64_t n_nodes, int64_t nnz, void* workspace, size_t workspace_bytes,
+                                int device, void* stream, int64_t bloom_cap, trw_csr_graph** out_graph);
+int trw_csr_checksum_typed(const void* row_ptr, int row_ptr_bytes, const void* col_idx, int col_idx_bytes,
+                           int64_t n_nodes, int64_t nnz, uint64_t* out_device, int device, void* stream);
 /* What a prepared graph holds, after waiting for `stream` (the stream it was prepared on):
  * out[0] membership table, out[1] edge records, out[2] bits of the L2-resident edge filter (0: none),
  * out[3] triangle Blooms computed, out[4] graph symmetric (1 yes, 0 no, -1 not checked),
@@ -153,8 +173,8 @@ int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_
  * trw_walk_csr_prepared_at.  Returns after `out` is complete. */
 typedef struct trw_csr_graph_view {
     const trw_csr_graph* graph; /* from trw_csr_graph_prepare                                              */
-    const int64_t* row_ptr;     /* device arrays holding the prepared content (NULL: those of the handle)  */
-    const int64_t* col_idx;
+    const void* row_ptr;        /* device arrays holding the prepared content, in the element widths the   */
+    const void* col_idx;        /* graph was prepared with (NULL: those of the handle)                     */
     void* ready_stream;         /* stream the preparation was enqueued on (NULL: known to be complete)     */
 } trw_csr_graph_view;
 int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_t* targets, int64_t n_walks,

@@ -253,6 +253,41 @@ def test_prepared_graph_and_graph_cache(native, rw):
         native.set_graph_cache(False)
 
 
+def test_int32_csr_gives_the_int64_walks(native, rw):
+    """f4 of SURVEY section 8: row_ptr / col_idx may be int32 (each on its own).  Same values, same walks -- one-shot,
+    through a prepared graph with triangle Blooms, through the content cache, for every law."""
+    from torch_random_walk_b200 import rmat
+
+    rp, ci = rmat.rmat_csr(15, 16, device="cuda", seed=13)
+    n = rp.numel() - 1
+    nodes = torch.arange(n, device="cuda")
+    laws = ((1.0, 1.0), (1.0, 0.5), (0.5, 2.0), (0.25, 0.5), (2.0, 1.0))
+    base = [native.walk(rp, ci, nodes, p_, q_, 30, 11, cache=False) for p_, q_ in laws]
+    for rp_t, ci_t in ((rp.int(), ci.int()), (rp, ci.int()), (rp.int(), ci)):
+        for (p_, q_), b in zip(laws, base):
+            w = native.walk(rp_t, ci_t, nodes, p_, q_, 30, 11, cache=False)
+            assert w.dtype == torch.int64 and torch.equal(w, b), (rp_t.dtype, ci_t.dtype, p_, q_)
+        g = native.prepare_csr(rp_t, ci_t)
+        assert g.symmetric
+        for (p_, q_), b in zip(laws, base):
+            assert torch.equal(g.walk(nodes, p_, q_, 30, 11), b)
+        del g
+        assert native.csr_checksum(rp_t, ci_t) == native.csr_checksum(rp, ci)  # a checksum of the values, not of the bytes
+    native.set_graph_cache(True)
+    try:
+        rp32, ci32 = rp.int(), ci.int()
+        for _ in range(5):
+            assert torch.equal(rw.walk(rp32, ci32, nodes, 1.0, 0.5, 30, 11), base[1])
+        assert native.graph_cache_state(rp.device)["blooms"]
+        assert torch.equal(rw.walk(rp, ci, nodes, 1.0, 0.5, 30, 11), base[1])  # int64 arrays: another key, same walks
+    finally:
+        native.set_graph_cache(False)
+    with pytest.raises(RuntimeError):
+        native.walk(rp.short(), ci, nodes, 1.0, 0.5, 30, 11)
+    with pytest.raises(RuntimeError):
+        native.walk(rp, ci, nodes.int(), 1.0, 0.5, 30, 11)
+
+
 def test_checksum_sees_every_element(native):
     rp, ci = cuda(*random_csr(8, 3000, 20))
     base = native.csr_checksum(rp, ci)
@@ -427,8 +462,11 @@ def test_edge_cases(rw, native):
     ref = native.walk(rp, ci, nodes, 0.5, 2.0, 8, 11)
     assert torch.equal(out, ref)
     assert (big[:, 0] == -7).all() and (big[:, 10:] == -7).all()
-    with pytest.raises(RuntimeError, match="Long"):
-        rw.walk(rp.int(), ci, nodes, 1.0, 1.0, 3, 1)
+    # dtypes: the reference's accessors raise on anything but int64; int32 CSR arrays are accepted here as an extension
+    # (test_int32_csr_gives_the_int64_walks), everything else still raises the reference's way
+    for bad_rp, bad_ci, bad_nodes in ((rp.short(), ci, nodes), (rp, ci.double(), nodes), (rp, ci, nodes.int())):
+        with pytest.raises(RuntimeError, match="Long"):
+            rw.walk(bad_rp, bad_ci, bad_nodes, 1.0, 1.0, 3, 1)
     for bad in (torch.empty((100, 8), dtype=torch.int64, device="cuda"), torch.empty((99, 9), dtype=torch.int64, device="cuda"),
                 torch.empty((100, 9), dtype=torch.int32, device="cuda"), torch.empty((100, 9), dtype=torch.int64),
                 torch.empty((100, 18), dtype=torch.int64, device="cuda")[:, ::2]):

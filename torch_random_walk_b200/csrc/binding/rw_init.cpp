@@ -8,7 +8,7 @@
 //
 // Optional: the shipped Python binding (torch_random_walk_b200/native.py, ctypes) needs no compiler
 // on the user's machine; this file is the drop-in for a maintainer who keeps the reference's
-// extension layout.  Built by torch_random_walk_b200/_build_ext.py, tested in tests/test_ext_gpu.py.
+// extension layout.  Built by torch_random_walk_b200/_build_ext.py, tested in tests/test_ext.py.
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>

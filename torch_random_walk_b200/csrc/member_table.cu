@@ -43,8 +43,8 @@ struct SegmentWork {
 };
 
 struct BuildArgs {
-    const int64_t* row_ptr;
-    const int64_t* col_idx;
+    IdxPtr row_ptr;
+    IdxPtr col_idx;
     int64_t n_nodes, nnz;
     uint32_t* table;
     int64_t* tile_row0;              // [n_tiles + 1]: row holding the first entry of each tile
@@ -80,11 +80,11 @@ __device__ __forceinline__ void filter_insert(uint32_t* __restrict__ filter, uin
 }
 
 // Largest r with row_ptr[r] <= e (the non-empty row that holds CSR entry e).
-__device__ __forceinline__ int64_t row_of_entry(const int64_t* __restrict__ row_ptr, int64_t n_nodes, int64_t e) {
+__device__ __forceinline__ int64_t row_of_entry(IdxPtr row_ptr, int64_t n_nodes, int64_t e) {
     int64_t lo = 0, hi = n_nodes;  // invariant: row_ptr[lo] <= e < row_ptr[hi]
     while (hi - lo > 1) {
         int64_t mid = (lo + hi) >> 1;
-        if (__ldg(row_ptr + mid) <= e) lo = mid; else hi = mid;
+        if (ldg_idx(row_ptr + mid) <= e) lo = mid; else hi = mid;
     }
     return lo;
 }
@@ -100,10 +100,10 @@ __global__ void __launch_bounds__(256) csr_prepass_kernel(const BuildArgs a) {
         }
     }
     for (int64_t r = gtid; r <= a.n_nodes; r += gsz) {
-        const int64_t b = __ldg(a.row_ptr + r);
+        const int64_t b = ldg_idx(a.row_ptr + r);
         if (a.row32) a.row32[r] = (uint32_t)b;
         if (a.hubs && r < a.n_nodes) {
-            const int64_t e = __ldg(a.row_ptr + r + 1);
+            const int64_t e = ldg_idx(a.row_ptr + r + 1);
             if (e - b >= kHubDeg) {
                 int64_t first, nb;
                 table_span(b, e, first, nb);
@@ -149,7 +149,9 @@ __device__ __forceinline__ bool smem_insert(uint32_t* __restrict__ image, uint32
 // Short rows.  A CTA owns the rows that start inside its tile and are shorter than kHubDeg; such
 // a row ends less than kHubDeg entries past the tile, so the CTA works on a window of kBuildRange
 // entries.  The row of every entry is recovered with a max-scan over "a row starts here" codes.
+template <bool WIDE>
 __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const BuildArgs a) {
+    const IdxPtrT<WIDE> col_idx(a.col_idx);
     extern __shared__ __align__(16) uint32_t tiled_smem[];
     uint32_t* head = tiled_smem;                // [kHeadWords] row code of each entry of the window (index through head_at)
     uint32_t* image = tiled_smem + kHeadWords;  // [kBuildRange / 4 buckets][8 slots]; kHeadWords is a multiple of 4
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
     // Rows that start in [e0, e1): short ones get the code r - r0 + 1; a hub gets kNotOurs (nothing
     // else can start after it inside the tile: it is at least as long as the tile).
     for (int64_t r = r0 + tid; r <= r1; r += kBuildThreads) {
-        const int64_t b = __ldg(a.row_ptr + r), e = __ldg(a.row_ptr + r + 1);
+        const int64_t b = ldg_idx(a.row_ptr + r), e = ldg_idx(a.row_ptr + r + 1);
         if (e > b && b >= e0 && b < e1) {
             if (e - b >= kHubDeg) {
                 head[head_at((int)(b - e0))] = kNotOurs;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
         const int idx = k * kBuildThreads + tid;
         const uint32_t code = head[head_at(idx)];
         const bool ours = code != 0 && code != kNotOurs && e0 + idx < own_end;
-        xs[k] = ours ? slot_id(ldg64_stream(a.col_idx + e0 + idx)) : kEmpty;
+        xs[k] = ours ? slot_id(ldg64_stream(col_idx + (e0 + idx))) : kEmpty;
     }
     int64_t cur_row = -1, first = 0, nb = 0;
     bool ok = true;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
         if (a.filter) filter_insert(a.filter, a.filter_bits, (uint32_t)r, xs[k], pol_keep);
         if (r != cur_row) {
             cur_row = r;
-            const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
+            const int64_t b = ldg_idx(a.row_ptr + r), en = ldg_idx(a.row_ptr + r + 1);
             if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
         }
         // a short row is a single segment: probing wraps over the whole row, capacity is guaranteed
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
 
 // Hub rows: persistent CTAs (one per SM: the segment image takes 144 KB of shared memory), which
 // pull segments from a shared counter so that the few very long rows do not unbalance the grid.
+template <bool WIDE>
 __global__ void __launch_bounds__(kHubThreads, 1) build_hub_kernel(const BuildArgs a) {
+    const IdxPtrT<WIDE> col_idx(a.col_idx);
     extern __shared__ __align__(16) uint32_t hub_image[];  // up to 2*kSegBuckets-1 buckets
     uint32_t* hub_count = hub_image + 2 * kSegBuckets * 8;
     __shared__ unsigned long long s_next;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(kHubThreads, 1) build_hub_kernel(const BuildAr
         const int64_t c = (int64_t)s_next;
         if (c >= n_segments) break;
         const SegmentWork work = a.segments[c];
-        const int64_t b = __ldg(a.row_ptr + work.row), e = __ldg(a.row_ptr + work.row + 1);
+        const int64_t b = ldg_idx(a.row_ptr + work.row), e = ldg_idx(a.row_ptr + work.row + 1);
         int64_t first, nb;
         table_span(b, e, first, nb);
         const int64_t nseg = segment_count(nb);
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(kHubThreads, 1) build_hub_kernel(const BuildAr
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int64_t idx = i + (int64_t)u * kHubThreads;
-                x[u] = idx < e ? slot_id(__ldg(a.col_idx + idx)) : kEmpty;
+                x[u] = idx < e ? slot_id(ldg_idx(col_idx + idx)) : kEmpty;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -328,7 +332,9 @@ __device__ __forceinline__ bool global_insert(uint32_t* __restrict__ table, int6
     return false;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kBuildThreads, 4) build_flat_kernel(const BuildArgs a) {
+    const IdxPtrT<WIDE> col_idx(a.col_idx);
     __shared__ uint32_t head[kBuildTile];
     __shared__ uint32_t warp_max[kBuildThreads / 32];
     const int tid = threadIdx.x;
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_flat_kernel(const Buil
     for (int k = 0; k < kBuildPerThread; ++k) head[k * kBuildThreads + tid] = 0;
     __syncthreads();
     for (int64_t r = r0 + 1 + tid; r <= r1; r += kBuildThreads) {
-        const int64_t b = __ldg(a.row_ptr + r), e = __ldg(a.row_ptr + r + 1);
+        const int64_t b = ldg_idx(a.row_ptr + r), e = ldg_idx(a.row_ptr + r + 1);
         if (e > b && b < e1) head[b - e0] = (uint32_t)(r - r0);
     }
     __syncthreads();
@@ -373,10 +379,10 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_flat_kernel(const Buil
         const int64_t r = r0 + max(before, own[k]);
         if (r != cur_row) {
             cur_row = r;
-            const int64_t b = __ldg(a.row_ptr + r), en = __ldg(a.row_ptr + r + 1);
+            const int64_t b = ldg_idx(a.row_ptr + r), en = ldg_idx(a.row_ptr + r + 1);
             if (en - b >= kMinTableDeg) table_span(b, en, first, nb); else nb = 0;
         }
-        const uint32_t x = slot_id(ldg64_stream(a.col_idx + mine + k));
+        const uint32_t x = slot_id(ldg64_stream(col_idx + (mine + k)));
         if (nb > 0 && x != kEmpty) ok &= global_insert(a.table, first, nb, x);
     }
     if (!ok) *a.failed = 1;
@@ -386,24 +392,25 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_flat_kernel(const Buil
 // knowing which row an entry belongs to: descents anywhere in col_idx (col[i] >= col[i+1]) can only
 // sit on row boundaries of such a graph, so the rows are strict iff the number of descents equals
 // the number of descents found AT row boundaries.
-__global__ void __launch_bounds__(256) strict_descents_kernel(const int64_t* __restrict__ col_idx, int64_t nnz,
+template <bool WIDE>
+__global__ void __launch_bounds__(256) strict_descents_kernel(IdxPtr col_any, int64_t nnz,
                                                               unsigned long long* counts) {
+    const IdxPtrT<WIDE> col_idx(col_any);
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
     unsigned long long n = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < nnz; i += gsz)
-        n += ldg64_stream(col_idx + i) >= __ldg(col_idx + i + 1) ? 1 : 0;
+        n += ldg64_stream(col_idx + i) >= ldg_idx(col_idx + i + 1) ? 1 : 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(counts, n);
 }
-__global__ void __launch_bounds__(256) strict_boundaries_kernel(const int64_t* __restrict__ row_ptr,
-                                                                const int64_t* __restrict__ col_idx, int64_t n_nodes,
+__global__ void __launch_bounds__(256) strict_boundaries_kernel(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes,
                                                                 int64_t nnz, unsigned long long* counts) {
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
     unsigned long long n = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_nodes; r += gsz) {
-        const int64_t b = __ldg(row_ptr + r), e = __ldg(row_ptr + r + 1);
-        if (e > b && e < nnz) n += __ldg(col_idx + e - 1) >= __ldg(col_idx + e) ? 1 : 0;
+        const int64_t b = ldg_idx(row_ptr + r), e = ldg_idx(row_ptr + r + 1);
+        if (e > b && e < nnz) n += ldg_idx(col_idx + e - 1) >= ldg_idx(col_idx + e) ? 1 : 0;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
@@ -413,12 +420,13 @@ __global__ void __launch_bounds__(256) strict_boundaries_kernel(const int64_t* _
 // Packed uint32 copies of the rows too short for a hashed table (member_table.cuh).  Runs after the
 // table build, whose whole-bucket writes leave EMPTY over these rows' bytes; a short row's bytes are
 // its own, so nothing of a neighbouring row's table is touched.
-__global__ void __launch_bounds__(256) short_rows_kernel(const int64_t* __restrict__ row_ptr,
-                                                         const int64_t* __restrict__ col_idx, int64_t n_nodes,
+template <bool WIDE>
+__global__ void __launch_bounds__(256) short_rows_kernel(IdxPtr row_ptr, IdxPtr col_any, int64_t n_nodes,
                                                          uint32_t* __restrict__ table) {
+    const IdxPtrT<WIDE> col_idx(col_any);
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_nodes; r += gsz) {
-        const int64_t b = __ldg(row_ptr + r), e = __ldg(row_ptr + r + 1);
+        const int64_t b = ldg_idx(row_ptr + r), e = ldg_idx(row_ptr + r + 1);
         const int64_t d = e - b;
         if (d <= 0 || d >= kMinTableDeg) continue;
         uint32_t ids[kMinTableDeg];
@@ -433,9 +441,11 @@ __global__ void __launch_bounds__(256) short_rows_kernel(const int64_t* __restri
 
 // Edge records (member_table.cuh): one streaming pass over col_idx; the two row-index reads per
 // entry hit the L2-resident uint32 index (evict_last), the 16-byte records leave coalesced.
-__global__ void __launch_bounds__(256) edge_records_kernel(const int64_t* __restrict__ col_idx, int64_t nnz,
+template <bool WIDE>
+__global__ void __launch_bounds__(256) edge_records_kernel(IdxPtr col_any, int64_t nnz,
                                                            const uint32_t* __restrict__ row32, int64_t n_nodes,
                                                            uint4* __restrict__ records) {
+    const IdxPtrT<WIDE> col_idx(col_any);
     constexpr int kBatch = 4;  // independent entries per thread and round
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
@@ -472,12 +482,14 @@ __global__ void __launch_bounds__(256) edge_records_kernel(const int64_t* __rest
 // the walk needs before it may look at a triangle from its far side.
 constexpr int kBloomWarps = 8;
 constexpr int kBloomUnroll = 2;
-__global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(const int64_t* __restrict__ col_idx, int64_t nnz,
+template <bool WIDE>
+__global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col_any, int64_t nnz,
                                                                       const uint32_t* __restrict__ row32, int64_t n_nodes,
                                                                       uint4* __restrict__ records,
                                                                       const uint32_t* __restrict__ table, EdgeFilter filter,
                                                                       uint32_t cap, const int* __restrict__ table_failed,
                                                                       int* __restrict__ asymmetric) {
+    const IdxPtrT<WIDE> col_idx(col_any);
     __shared__ uint32_t s_bloom[kBloomWarps][32];
     __shared__ uint32_t s_mirror[kBloomWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -611,7 +623,7 @@ CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bo
     return w;
 }
 
-int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
+int csr_prepare_device(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
                        const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, bool want_records,
                        int build_mode, int device, cudaStream_t st, CsrPrepared* out, int64_t bloom_cap) {
     want_table = want_table && w.has_table;
@@ -651,7 +663,8 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
     const int sms = sm_count(device);
     if (want_strict) {
         unsigned long long* counts = (unsigned long long*)(ws + w.cells + 128);
-        strict_descents_kernel<<<sms * 8, 256, 0, st>>>(col_idx, nnz, counts);
+        if (col_idx.wide()) strict_descents_kernel<true><<<sms * 8, 256, 0, st>>>(col_idx, nnz, counts);
+        else strict_descents_kernel<false><<<sms * 8, 256, 0, st>>>(col_idx, nnz, counts);
         strict_boundaries_kernel<<<sms * 8, 256, 0, st>>>(row_ptr, col_idx, n_nodes, nnz, counts);
         count_launch(2);
         rc = check_cuda(cudaGetLastError(), "strict-rows check launch");
@@ -667,25 +680,35 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
         if (build_mode == 0) {
             rc = check_cuda(cudaMemsetAsync(b.table, 0xFF, (size_t)w.n_buckets * 32, st), "table memset");
             if (rc) return rc;
-            build_flat_kernel<<<(unsigned)w.n_tiles, kBuildThreads, 0, st>>>(b);
+            if (col_idx.wide()) build_flat_kernel<true><<<(unsigned)w.n_tiles, kBuildThreads, 0, st>>>(b);
+            else build_flat_kernel<false><<<(unsigned)w.n_tiles, kBuildThreads, 0, st>>>(b);
             count_launch(1);
         } else {
             static bool attr_set[64];
             if (device >= 64 || !attr_set[device]) {
-                rc = check_cuda(cudaFuncSetAttribute(build_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                rc = check_cuda(cudaFuncSetAttribute(build_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int)kTiledSmemBytes), "tiled build smem attribute");
-                if (rc) return rc;
-                rc = check_cuda(cudaFuncSetAttribute(build_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)kHubSmemBytes), "hub build smem attribute");
+                if (!rc) rc = check_cuda(cudaFuncSetAttribute(build_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                              (int)kTiledSmemBytes), "tiled build smem attribute");
+                if (!rc) rc = check_cuda(cudaFuncSetAttribute(build_hub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                              (int)kHubSmemBytes), "hub build smem attribute");
+                if (!rc) rc = check_cuda(cudaFuncSetAttribute(build_hub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                              (int)kHubSmemBytes), "hub build smem attribute");
                 if (rc) return rc;
                 if (device < 64) attr_set[device] = true;
             }
             hub_segments_kernel<<<sms, 256, 0, st>>>(b);
-            build_tiled_kernel<<<(unsigned)w.n_tiles, kBuildThreads, kTiledSmemBytes, st>>>(b);
-            build_hub_kernel<<<sms, kHubThreads, kHubSmemBytes, st>>>(b);
+            if (col_idx.wide()) {
+                build_tiled_kernel<true><<<(unsigned)w.n_tiles, kBuildThreads, kTiledSmemBytes, st>>>(b);
+                build_hub_kernel<true><<<sms, kHubThreads, kHubSmemBytes, st>>>(b);
+            } else {
+                build_tiled_kernel<false><<<(unsigned)w.n_tiles, kBuildThreads, kTiledSmemBytes, st>>>(b);
+                build_hub_kernel<false><<<sms, kHubThreads, kHubSmemBytes, st>>>(b);
+            }
             count_launch(3);
         }
-        short_rows_kernel<<<sms * 8, 256, 0, st>>>(row_ptr, col_idx, n_nodes, b.table);
+        if (col_idx.wide()) short_rows_kernel<true><<<sms * 8, 256, 0, st>>>(row_ptr, col_idx, n_nodes, b.table);
+        else short_rows_kernel<false><<<sms * 8, 256, 0, st>>>(row_ptr, col_idx, n_nodes, b.table);
         count_launch(1);
         rc = check_cuda(cudaGetLastError(), "membership table build launch");
         if (rc) return rc;
@@ -696,7 +719,8 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
     out->row32 = b.row32;
     if (want_records) {
         uint4* records = (uint4*)(ws + w.records);
-        edge_records_kernel<<<sms * 16, 256, 0, st>>>(col_idx, nnz, b.row32, n_nodes, records);
+        if (col_idx.wide()) edge_records_kernel<true><<<sms * 16, 256, 0, st>>>(col_idx, nnz, b.row32, n_nodes, records);
+        else edge_records_kernel<false><<<sms * 16, 256, 0, st>>>(col_idx, nnz, b.row32, n_nodes, records);
         count_launch(1);
         rc = check_cuda(cudaGetLastError(), "edge records launch");
         if (rc) return rc;
@@ -707,14 +731,20 @@ int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n
     return TRW_OK;
 }
 
-int csr_add_blooms(CsrPrepared* pr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, int64_t cap, int device, cudaStream_t st) {
+int csr_add_blooms(CsrPrepared* pr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz, int64_t cap, int device, cudaStream_t st) {
     if (pr->asymmetric != nullptr || cap <= 0) return TRW_OK;  // already there
     if (!pr->table || !pr->records || !pr->row32 || !pr->bloom_flag || nnz <= 0) return TRW_OK;  // nothing to hang them on
     int rc = check_cuda(cudaMemsetAsync(pr->bloom_flag, 0, sizeof(int), st), "bloom flag memset");
     if (rc) return rc;
-    edge_bloom_kernel<<<sm_count(device) * 8, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, const_cast<uint4*>(pr->records),
-                                                                          pr->table, pr->filter, (uint32_t)std::min<int64_t>(cap, 1 << 20),
-                                                                          pr->table_failed, pr->bloom_flag);
+    const unsigned grid = (unsigned)sm_count(device) * 8;
+    uint4* records = const_cast<uint4*>(pr->records);
+    const uint32_t cap32 = (uint32_t)std::min<int64_t>(cap, 1 << 20);
+    if (col_idx.wide())
+        edge_bloom_kernel<true><<<grid, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, records, pr->table, pr->filter, cap32,
+                                                                  pr->table_failed, pr->bloom_flag);
+    else
+        edge_bloom_kernel<false><<<grid, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, records, pr->table, pr->filter, cap32,
+                                                                   pr->table_failed, pr->bloom_flag);
     count_launch(1);
     rc = check_cuda(cudaGetLastError(), "edge bloom launch");
     if (rc) return rc;

@@ -54,7 +54,7 @@ __device__ __forceinline__ void probe_segment(int64_t nb, int64_t home, int64_t&
 
 // x in adj(t)?  (b,e) = row span of t.  table == nullptr (or TABLE == false) selects the scan.
 template <bool TABLE>
-__device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, const int64_t* __restrict__ col_idx,
+__device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, IdxPtr col_idx,
                                           const uint32_t* __restrict__ table, uint64_t pol_stream) {
     // Table slots hold uint32 ids below kEmpty; an id that does not fit (out-of-graph, possible only in a
     // hand-built col_idx) is never stored there, so the table cannot speak for it: such an x is scanned.
@@ -211,12 +211,12 @@ struct CsrPrepared {
 // Enqueues on `st` the per-call preparation of a CSR graph: the uint32 row index and (node2vec)
 // the membership table, and (want_strict) the two counters that tell whether every row is strictly
 // increasing, i.e. sorted without duplicate edges.  build_mode: 2 = shared memory (default), 0 = global CAS.
-int csr_prepare_device(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
+int csr_prepare_device(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz, void* workspace,
                        const CsrWorkspace& w, bool want_table, bool want_row32, bool want_strict, bool want_records,
                        int build_mode, int device, cudaStream_t st, CsrPrepared* out, int64_t bloom_cap = 0);
 
 // Adds the triangle Blooms to the edge records of a prepared graph (no-op when they are there, or when the
 // graph has no table / records to hang them on).
-int csr_add_blooms(CsrPrepared* pr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, int64_t cap, int device, cudaStream_t st);
+int csr_add_blooms(CsrPrepared* pr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz, int64_t cap, int device, cudaStream_t st);
 
 }  // namespace trw

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "trw_common.cuh"
 #include "trw_options.h"
@@ -43,20 +44,40 @@ Options& options() {
     return o;
 }
 
-static cudaEvent_t g_ev[2][2];
-static bool g_ev_used[2];
+// Event pairs of option time_kernels: per device (an event belongs to the device it was created on), guarded by a
+// mutex; slot 0 = graph preparation, slot 1 = walk kernel of the last CSR walk on that device.
+struct TimingSlot {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used = false;
+};
+static TimingSlot g_timing[64][2];
+static std::mutex g_timing_mu;
+static int g_timing_last_device = 0;
+
+static TimingSlot* timing_slot(int slot) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) { cudaGetLastError(); return nullptr; }
+    g_timing_last_device = d;
+    return &g_timing[d][slot];
+}
 
 void timing_begin(int slot, cudaStream_t st) {
     if (!options().time_kernels) return;
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    TimingSlot* t = timing_slot(slot);
+    if (!t) return;
     for (int k = 0; k < 2; ++k)
-        if (!g_ev[slot][k]) cudaEventCreate(&g_ev[slot][k]);
-    cudaEventRecord(g_ev[slot][0], st);
+        if (!t->ev[k] && cudaEventCreate(&t->ev[k]) != cudaSuccess) { cudaGetLastError(); t->ev[k] = nullptr; return; }
+    if (cudaEventRecord(t->ev[0], st) != cudaSuccess) cudaGetLastError();  // a failed measurement must not fail the walk
 }
 
 void timing_end(int slot, cudaStream_t st) {
     if (!options().time_kernels) return;
-    cudaEventRecord(g_ev[slot][1], st);
-    g_ev_used[slot] = true;
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    TimingSlot* t = timing_slot(slot);
+    if (!t || !t->ev[0] || !t->ev[1]) return;
+    if (cudaEventRecord(t->ev[1], st) != cudaSuccess) { cudaGetLastError(); return; }
+    t->used = true;
 }
 
 int resolve_device(int device) {
@@ -199,16 +220,28 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
 
 int trw_last_kernel_ms(float* build_ms, float* walk_ms) {
     float* dst[2] = {build_ms, walk_ms};
+    cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool used[2] = {false, false};
+    int d = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_timing_mu);
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) { cudaGetLastError(); d = g_timing_last_device; }
+        for (int slot = 0; slot < 2; ++slot) {
+            used[slot] = g_timing[d][slot].used;
+            ev[slot][0] = g_timing[d][slot].ev[0];
+            ev[slot][1] = g_timing[d][slot].ev[1];
+        }
+        g_timing[d][0].used = false;  // a walk on a kept graph leaves the preparation slot unused
+    }
     for (int slot = 0; slot < 2; ++slot) {
         if (!dst[slot]) continue;
         *dst[slot] = 0.0f;
-        if (!g_ev_used[slot]) continue;
-        int rc = check_cuda(cudaEventSynchronize(g_ev[slot][1]), "trw_last_kernel_ms");
+        if (!used[slot]) continue;
+        int rc = check_cuda(cudaEventSynchronize(ev[slot][1]), "trw_last_kernel_ms");
         if (rc) return rc;
-        rc = check_cuda(cudaEventElapsedTime(dst[slot], g_ev[slot][0], g_ev[slot][1]), "trw_last_kernel_ms");
+        rc = check_cuda(cudaEventElapsedTime(dst[slot], ev[slot][0], ev[slot][1]), "trw_last_kernel_ms");
         if (rc) return rc;
     }
-    g_ev_used[0] = false;  // a uniform walk leaves the build slot unused
     return TRW_OK;
 }
 

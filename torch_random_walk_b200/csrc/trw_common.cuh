@@ -182,6 +182,75 @@ __device__ __forceinline__ void red_or32_hint(uint32_t* p, uint32_t bits, uint64
     asm volatile("red.relaxed.gpu.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(bits), "l"(pol) : "memory");
 }
 
+// ---------------------------------------------------------------- CSR arrays of either width
+// The reference's accessors are int64-only (csrc/cuda/rw_cuda.cu:206-209).  Here row_ptr and col_idx may be int64 or
+// int32 arrays: IdxPtr carries the element size beside the address, every load widens to int64 (sign-extending), and
+// the width test is uniform over the grid.  An int64 pointer converts implicitly, so int64 callers read as before.
+struct IdxPtr {
+    const char* base = nullptr;
+    int shift = 3;  // log2 of the element size: 3 = int64, 2 = int32
+    __host__ __device__ IdxPtr() {}
+    __host__ __device__ IdxPtr(const int64_t* p) : base(reinterpret_cast<const char*>(p)), shift(3) {}
+    __host__ __device__ IdxPtr(const int32_t* p) : base(reinterpret_cast<const char*>(p)), shift(2) {}
+    __host__ __device__ IdxPtr(const void* p, int elem_bytes) : base(reinterpret_cast<const char*>(p)), shift(elem_bytes == 4 ? 2 : 3) {}
+    __host__ __device__ IdxPtr operator+(int64_t i) const { IdxPtr r = *this; r.base += i * ((int64_t)1 << shift); return r; }
+    __host__ __device__ IdxPtr operator-(int64_t i) const { return *this + (-i); }
+    __host__ __device__ explicit operator bool() const { return base != nullptr; }
+    __host__ __device__ bool wide() const { return shift == 3; }
+    __host__ __device__ const int64_t* as64() const { return reinterpret_cast<const int64_t*>(base); }
+    __host__ __device__ const int32_t* as32() const { return reinterpret_cast<const int32_t*>(base); }
+};
+// The same with the width fixed at compile time: what the streaming kernels use inside their loops (a run-time
+// width test in front of every load keeps the compiler from issuing a thread's loads together).
+template <bool WIDE>
+struct IdxPtrT {
+    const char* base;
+    __device__ explicit IdxPtrT(IdxPtr p) : base(p.base) {}
+    __device__ IdxPtrT(const char* b) : base(b) {}
+    __device__ IdxPtrT operator+(int64_t i) const { return IdxPtrT(base + i * (WIDE ? 8 : 4)); }
+    __device__ IdxPtrT operator-(int64_t i) const { return IdxPtrT(base - i * (WIDE ? 8 : 4)); }
+    __device__ operator IdxPtr() const { return IdxPtr(base, WIDE ? 8 : 4); }
+};
+template <bool WIDE>
+__device__ __forceinline__ int64_t ldg_idx(IdxPtrT<WIDE> p) {
+    if (WIDE) return __ldg(reinterpret_cast<const int64_t*>(p.base));
+    return (int64_t)__ldg(reinterpret_cast<const int32_t*>(p.base));
+}
+template <bool WIDE>
+__device__ __forceinline__ int64_t ldg64_stream(IdxPtrT<WIDE> p) {
+    if (WIDE) return ldg64_stream(reinterpret_cast<const int64_t*>(p.base));
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p.base));
+    return (int64_t)v;
+}
+template <bool WIDE>
+__device__ __forceinline__ int64_t ldg64_hint(IdxPtrT<WIDE> p, uint64_t pol) {
+    if (WIDE) return ldg64_hint(reinterpret_cast<const int64_t*>(p.base), pol);
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p.base), "l"(pol));
+    return (int64_t)v;
+}
+
+__device__ __forceinline__ int64_t ldg_idx(IdxPtr p) { return p.wide() ? __ldg(p.as64()) : (int64_t)__ldg(p.as32()); }
+__device__ __forceinline__ int64_t ldg64_stream(IdxPtr p) {
+    if (p.wide()) return ldg64_stream(p.as64());
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p.base));
+    return (int64_t)v;
+}
+__device__ __forceinline__ int64_t ldg64_hint(IdxPtr p, uint64_t pol) {
+    if (p.wide()) return ldg64_hint(p.as64(), pol);
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p.base), "l"(pol));
+    return (int64_t)v;
+}
+__device__ __forceinline__ int64_t ldg64_keep(IdxPtr p, uint64_t pol) {
+    if (p.wide()) return ldg64_keep(p.as64(), pol);
+    int32_t v;
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p.base), "l"(pol));
+    return (int64_t)v;
+}
+
 // Coherent 16-byte load of memory other threads are updating with atomics.
 __device__ __forceinline__ uint4 ld_relaxed_u32x4(const uint32_t* p) {
     uint4 v;

@@ -119,7 +119,7 @@ struct RowOutSmem {
 // First-order walk: one thread per walk, two dependent gathers per step (row span from L2, then
 // the chosen col_idx entry from HBM), one Philox block per four steps.
 template <int BLOCK, bool STAGE, bool ROW32, bool REC>
-__global__ void __launch_bounds__(BLOCK, 8) uniform_walk_kernel(const WalkArgs a) {
+__global__ void __launch_bounds__(BLOCK, 4) uniform_walk_kernel(const WalkArgs a) {  // four resident CTAs: what its carve-out targets (launchers below)
     __shared__ int64_t ring[RowOutSmem<BLOCK, STAGE>::kWords];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = i < a.n_walks;  // lanes past the end stay for the warp-collective stores
@@ -487,7 +487,7 @@ static void set_row_window(cudaStream_t st, const void* base, size_t bytes, int 
 // the same `uniform` and `want_records`).  Independent of p, q, the seed and the start nodes, so one
 // prepared graph serves any number of walk calls (trw_csr_graph_* keeps it across calls;
 // trw_walk_csr builds it per call).
-int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+int csr_graph_prepare(CsrGraph* g, IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz,
                       bool uniform, bool want_table, bool want_strict, bool want_records, void* workspace,
                       size_t workspace_bytes, int device, cudaStream_t st, int64_t bloom_cap) {
     if (n_nodes < 0 || nnz < 0) { set_error("trw_walk_csr: negative size"); return TRW_ERR_ARG; }
@@ -599,7 +599,7 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
     const bool rec = a.records != nullptr && row32 && stage;
     if (plan.persist) {
         if (row32) set_row_window(st, a.row32, (size_t)(a.n_nodes + 1) * 4, plan.device, true);
-        else set_row_window(st, a.row_ptr, (size_t)(a.n_nodes + 1) * 8, plan.device, true);
+        else set_row_window(st, a.row_ptr.base, (size_t)(a.n_nodes + 1) << a.row_ptr.shift, plan.device, true);
     }
     timing_begin(1, st);
     if (plan.uniform) {
@@ -658,10 +658,18 @@ static int walk_args_check(const char* fn, const int64_t* targets, int64_t n_wal
     return TRW_OK;
 }
 
-extern "C" int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
-                            const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, double p, double q,
-                            int walk_length, int64_t seed, int64_t* out, int64_t out_row_stride, void* workspace,
-                            size_t workspace_bytes, int device, void* stream) {
+static int elem_bytes_ok(const char* fn, int row_ptr_bytes, int col_idx_bytes) {
+    if ((row_ptr_bytes != 4 && row_ptr_bytes != 8) || (col_idx_bytes != 4 && col_idx_bytes != 8)) {
+        set_error("%s: CSR elements must be 4 or 8 bytes wide (got %d, %d)", fn, row_ptr_bytes, col_idx_bytes);
+        return TRW_ERR_ARG;
+    }
+    return TRW_OK;
+}
+
+static int walk_csr_one_shot(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz,
+                             const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, double p, double q,
+                             int walk_length, int64_t seed, int64_t* out, int64_t out_row_stride, void* workspace,
+                             size_t workspace_bytes, int device, void* stream) {
     int rc = walk_args_check("trw_walk_csr", targets, n_walks, walk_length, out, out_row_stride);
     if (rc) return rc;
     const int d = resolve_device(device);
@@ -686,6 +694,24 @@ extern "C" int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int6
     return csr_walk_launch(plan, targets, n_walks, walk_id_offset, out, out_row_stride, st);
 }
 
+extern "C" int trw_walk_csr(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                            const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, double p, double q,
+                            int walk_length, int64_t seed, int64_t* out, int64_t out_row_stride, void* workspace,
+                            size_t workspace_bytes, int device, void* stream) {
+    return walk_csr_one_shot(IdxPtr(row_ptr), IdxPtr(col_idx), n_nodes, nnz, targets, n_walks, walk_id_offset, p, q, walk_length, seed,
+                             out, out_row_stride, workspace, workspace_bytes, device, stream);
+}
+
+extern "C" int trw_walk_csr_typed(const void* row_ptr, int row_ptr_bytes, const void* col_idx, int col_idx_bytes,
+                                  int64_t n_nodes, int64_t nnz, const int64_t* targets, int64_t n_walks,
+                                  int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed, int64_t* out,
+                                  int64_t out_row_stride, void* workspace, size_t workspace_bytes, int device, void* stream) {
+    const int rc = elem_bytes_ok("trw_walk_csr_typed", row_ptr_bytes, col_idx_bytes);
+    if (rc) return rc;
+    return walk_csr_one_shot(IdxPtr(row_ptr, row_ptr_bytes), IdxPtr(col_idx, col_idx_bytes), n_nodes, nnz, targets, n_walks,
+                             walk_id_offset, p, q, walk_length, seed, out, out_row_stride, workspace, workspace_bytes, device, stream);
+}
+
 extern "C" size_t trw_csr_graph_workspace_bytes(int64_t n_nodes, int64_t nnz) {
     if (n_nodes < 0 || nnz < 0) return 0;
     return csr_workspace_layout(n_nodes, nnz, false, options().records != 0).total;
@@ -697,9 +723,27 @@ extern "C" int trw_csr_graph_prepare(const int64_t* row_ptr, const int64_t* col_
     return trw_csr_graph_prepare_ex(row_ptr, col_idx, n_nodes, nnz, workspace, workspace_bytes, device, stream, -1, out_graph);
 }
 
+static int graph_prepare_impl(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz, void* workspace, size_t workspace_bytes,
+                              int device, void* stream, int64_t bloom_cap, trw_csr_graph** out_graph);
+
 extern "C" int trw_csr_graph_prepare_ex(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                                         void* workspace, size_t workspace_bytes, int device, void* stream,
                                         int64_t bloom_cap, trw_csr_graph** out_graph) {
+    return graph_prepare_impl(IdxPtr(row_ptr), IdxPtr(col_idx), n_nodes, nnz, workspace, workspace_bytes, device, stream, bloom_cap,
+                              out_graph);
+}
+
+extern "C" int trw_csr_graph_prepare_typed(const void* row_ptr, int row_ptr_bytes, const void* col_idx, int col_idx_bytes,
+                                           int64_t n_nodes, int64_t nnz, void* workspace, size_t workspace_bytes, int device,
+                                           void* stream, int64_t bloom_cap, trw_csr_graph** out_graph) {
+    const int rc = elem_bytes_ok("trw_csr_graph_prepare_typed", row_ptr_bytes, col_idx_bytes);
+    if (rc) return rc;
+    return graph_prepare_impl(IdxPtr(row_ptr, row_ptr_bytes), IdxPtr(col_idx, col_idx_bytes), n_nodes, nnz, workspace, workspace_bytes,
+                              device, stream, bloom_cap, out_graph);
+}
+
+static int graph_prepare_impl(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz, void* workspace, size_t workspace_bytes,
+                              int device, void* stream, int64_t bloom_cap, trw_csr_graph** out_graph) {
     if (!out_graph) { set_error("trw_csr_graph_prepare: null out_graph"); return TRW_ERR_ARG; }
     *out_graph = nullptr;
     const int d = resolve_device(device);
@@ -737,7 +781,7 @@ extern "C" int trw_walk_csr_prepared(const trw_csr_graph* graph, const int64_t* 
 
 // The same walk over a prepared graph whose CSR arrays now live at (row_ptr, col_idx): for callers that have
 // verified (trw_csr_checksum) that these arrays hold what was prepared.  Nothing of the handle is changed.
-extern "C" int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx,
+extern "C" int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const void* row_ptr, const void* col_idx,
                                         const int64_t* targets, int64_t n_walks, int64_t walk_id_offset, int64_t walk_id_block,
                                         int64_t walk_id_stride, double p, double q, int walk_length, int64_t seed, int64_t* out,
                                         int64_t out_row_stride, void* stream) {
@@ -748,9 +792,9 @@ extern "C" int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const int64_
     if (n_walks == 0) return TRW_OK;
     DeviceGuard guard(graph->g.device);
     if (!guard.ok) { set_error("trw_walk_csr_prepared_at: cudaSetDevice(%d) failed", graph->g.device); return TRW_ERR_DEVICE; }
-    CsrGraph g = graph->g;
-    g.row_ptr = row_ptr;
-    g.col_idx = col_idx;
+    CsrGraph g = graph->g;  // the arrays move, their element widths are those the graph was prepared with
+    g.row_ptr.base = reinterpret_cast<const char*>(row_ptr);
+    g.col_idx.base = reinterpret_cast<const char*>(col_idx);
     CsrWalkPlan plan;
     rc = csr_walk_plan(&plan, g, p, q, walk_length, seed);
     if (rc) return rc;
@@ -760,7 +804,7 @@ extern "C" int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const int64_
 
 // Adds the triangle Blooms (member_table.cuh) to a graph that was prepared without them: one pass over the
 // edge records in the graph's workspace.  `cap` <= 0 selects option edge_bloom_cap.
-extern "C" int trw_csr_graph_add_blooms(trw_csr_graph* graph, const int64_t* row_ptr, const int64_t* col_idx, int64_t cap,
+extern "C" int trw_csr_graph_add_blooms(trw_csr_graph* graph, const void* row_ptr, const void* col_idx, int64_t cap,
                                         void* stream) {
     if (!graph) { set_error("trw_csr_graph_add_blooms: null graph"); return TRW_ERR_ARG; }
     DeviceGuard guard(graph->g.device);
@@ -768,7 +812,9 @@ extern "C" int trw_csr_graph_add_blooms(trw_csr_graph* graph, const int64_t* row
     if (cap <= 0) cap = options().edge_bloom_cap;
     if (cap <= 0) return TRW_OK;
     timing_begin(0, (cudaStream_t)stream);
-    const int rc = csr_add_blooms(&graph->g.prepared, col_idx ? col_idx : graph->g.col_idx, graph->g.n_nodes, graph->g.nnz, cap,
+    IdxPtr ci = graph->g.col_idx;
+    if (col_idx) ci.base = reinterpret_cast<const char*>(col_idx);
+    const int rc = csr_add_blooms(&graph->g.prepared, ci, graph->g.n_nodes, graph->g.nnz, cap,
                                   graph->g.device, (cudaStream_t)stream);
     timing_end(0, (cudaStream_t)stream);
     (void)row_ptr;

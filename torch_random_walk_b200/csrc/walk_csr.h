@@ -6,8 +6,8 @@
 namespace trw {
 
 struct WalkArgs {
-    const int64_t* row_ptr;
-    const int64_t* col_idx;
+    IdxPtr row_ptr;
+    IdxPtr col_idx;
     int64_t n_nodes, nnz;
     const int64_t* targets;
     int64_t n_walks, walk_id_offset;
@@ -34,8 +34,8 @@ struct WalkArgs {
 // A CSR graph as the walk kernels see it: the caller's arrays plus what csr_graph_prepare derived
 // from them into the workspace (all optional: a null member selects the slower generic path).
 struct CsrGraph {
-    const int64_t* row_ptr = nullptr;
-    const int64_t* col_idx = nullptr;
+    IdxPtr row_ptr;
+    IdxPtr col_idx;
     int64_t n_nodes = 0, nnz = 0;
     int device = 0;
     CsrPrepared prepared;
@@ -48,7 +48,7 @@ struct CsrWalkPlan {
     bool uniform, table, speculate, stage, persist, fold;
 };
 
-int csr_graph_prepare(CsrGraph* g, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+int csr_graph_prepare(CsrGraph* g, IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz,
                       bool uniform, bool want_table, bool want_strict, bool want_records, void* workspace,
                       size_t workspace_bytes, int device, cudaStream_t st, int64_t bloom_cap = 0);
 int csr_graph_of_handle(const trw_csr_graph* h, CsrGraph* out);  // the graph behind a C-ABI handle (walk_csr.cu)

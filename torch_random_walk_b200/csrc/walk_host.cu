@@ -588,8 +588,8 @@ extern "C" int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_
     CsrGraph g;
     int rc = csr_graph_of_handle(view->graph, &g);
     if (rc) return rc;
-    if (view->row_ptr) g.row_ptr = view->row_ptr;
-    if (view->col_idx) g.col_idx = view->col_idx;
+    if (view->row_ptr) g.row_ptr.base = reinterpret_cast<const char*>(view->row_ptr);
+    if (view->col_idx) g.col_idx.base = reinterpret_cast<const char*>(view->col_idx);
     const int d = g.device;
     DeviceGuard guard(d);
     if (!guard.ok) { set_error("trw_walk_csr_to_host: cudaSetDevice(%d) failed", d); return TRW_ERR_DEVICE; }

@@ -54,6 +54,11 @@ def _load():
                                              _c_i64, _c_ptr, _c_i64, _c_ptr]
     lib.trw_csr_graph_add_blooms.argtypes = [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_ptr]
     lib.trw_csr_checksum.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_int, _c_ptr]
+    lib.trw_csr_checksum_typed.argtypes = [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_i64, _c_ptr, _c_int, _c_ptr]
+    lib.trw_csr_graph_prepare_typed.argtypes = [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr, _c_i64,
+                                                ctypes.POINTER(_c_ptr)]
+    lib.trw_walk_csr_typed.argtypes = [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
+                                       _c_i64, _c_ptr, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr]
     lib.trw_walk_csr_to_host.argtypes = [ctypes.POINTER(_GraphView), _c_ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
                                          _c_i64, _c_ptr]
     lib.trw_walk_csr_prepared.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_i64,
@@ -100,12 +105,14 @@ def _check(status):
         raise RuntimeError(_lib.trw_last_error().decode("utf-8", "replace") or f"libtrw_b200 status {status}")
 
 
-def _require_cuda(t, name):
+def _require_cuda(t, name, int32_too=False):
     # message convention of the reference's CHECK_CUDA (csrc/cuda/utils.cuh:7)
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
     if not t.is_cuda:
         raise RuntimeError(f"(*{name}) must be a CUDA tensor")
+    if int32_too and t.dtype == torch.int32:
+        return  # extension: row_ptr / col_idx of the CSR walk may be int32 (the reference raises, csrc/cuda/rw_cuda.cu:206-209)
     if t.dtype != torch.int64:
         # the reference's packed_accessor64<int64_t> raises the same way
         raise RuntimeError(f"expected scalar type Long but found {str(t.dtype).replace('torch.', '')} ({name})")
@@ -164,8 +171,8 @@ class PreparedCsr:
     checksum).  Walks through it are bit-identical to the one-shot call."""
 
     def __init__(self, row_ptr, column_idx, hold=True, blooms=True):
-        _require_cuda(row_ptr, "row_ptr")
-        _require_cuda(column_idx, "column_idx")
+        _require_cuda(row_ptr, "row_ptr", int32_too=True)
+        _require_cuda(column_idx, "column_idx", int32_too=True)
         row_ptr, column_idx = row_ptr.contiguous(), column_idx.contiguous()
         self.row_ptr, self.column_idx = (row_ptr, column_idx) if hold else (None, None)
         self.device = row_ptr.device
@@ -176,9 +183,11 @@ class PreparedCsr:
         with torch.cuda.device(self.device):
             need = _lib.trw_csr_graph_workspace_bytes(self.n_nodes, self.nnz)
             self.workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=self.device)
-            _check(_lib.trw_csr_graph_prepare_ex(_ptr(row_ptr), _ptr(column_idx), self.n_nodes, self.nnz,
-                                                 _ptr(self.workspace) if need else None, need, self.device.index,
-                                                 _stream(self.device), -1 if blooms else 0, ctypes.byref(self._handle)))
+            self.dtypes = (row_ptr.dtype, column_idx.dtype)
+            _check(_lib.trw_csr_graph_prepare_typed(_ptr(row_ptr), row_ptr.element_size(), _ptr(column_idx), column_idx.element_size(),
+                                                    self.n_nodes, self.nnz, _ptr(self.workspace) if need else None, need,
+                                                    self.device.index, _stream(self.device), -1 if blooms else 0,
+                                                    ctypes.byref(self._handle)))
             self._ready = torch.cuda.Event()
             self._ready.record(torch.cuda.current_stream(self.device))
             self._stream_id = torch.cuda.current_stream(self.device).cuda_stream
@@ -212,6 +221,8 @@ class PreparedCsr:
         rp, ci = (self.row_ptr, self.column_idx) if csr is None else csr
         if rp is None:
             raise RuntimeError("this prepared graph does not hold its CSR arrays: pass csr=(row_ptr, column_idx)")
+        if (rp.dtype, ci.dtype) != self.dtypes:
+            raise RuntimeError("csr arrays must have the dtypes the graph was prepared with")
         target_nodes = target_nodes.contiguous()
         n, wl = target_nodes.size(0), int(walk_length) + 1
         _check_out(out, n, wl, dev)
@@ -276,8 +287,9 @@ def csr_checksum(row_ptr, column_idx):
     d_buf, h_buf, done = bufs
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
-        _check(_lib.trw_csr_checksum(_ptr(row_ptr), _ptr(column_idx), max(row_ptr.numel() - 1, 0), column_idx.numel(),
-                                     _ptr(d_buf), dev.index, ctypes.c_void_p(stream.cuda_stream)))
+        _check(_lib.trw_csr_checksum_typed(_ptr(row_ptr), row_ptr.element_size(), _ptr(column_idx), column_idx.element_size(),
+                                           max(row_ptr.numel() - 1, 0), column_idx.numel(), _ptr(d_buf), dev.index,
+                                           ctypes.c_void_p(stream.cuda_stream)))
         h_buf.copy_(d_buf, non_blocking=True)
         done.record(stream)
         done.synchronize()
@@ -338,7 +350,7 @@ def graph_cache_state(device=None):
 def _cached_walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_offset, out):
     """The cached form of `walk`, or None when this call has to take the one-shot path."""
     dev = row_ptr.device
-    key = (max(row_ptr.numel() - 1, 0), column_idx.numel(), csr_checksum(row_ptr, column_idx))
+    key = (max(row_ptr.numel() - 1, 0), column_idx.numel(), row_ptr.dtype, column_idx.dtype, csr_checksum(row_ptr, column_idx))
     with _cache_lock:
         entry = _graph_cache.get(dev.index)
         if entry is not None and entry["key"] != key:
@@ -368,9 +380,11 @@ def walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_off
     row_ptr's device.  `walk_id_offset` / `out` are extensions for sharded callers; `cache` overrides
     the graph cache for this call (None: the module setting).  With the cache, repeated calls on a graph
     of the same content reuse its preparation (see the comment above _graph_cache); cached and one-shot
-    calls return identical walks."""
-    _require_cuda(row_ptr, "row_ptr")
-    _require_cuda(column_idx, "column_idx")
+    calls return identical walks.  Extension: row_ptr and column_idx may each be int32 (half the graph in
+    HBM; the reference raises on anything but int64) -- start nodes and walks stay int64 and the walks
+    equal those of the int64 call on the same values."""
+    _require_cuda(row_ptr, "row_ptr", int32_too=True)
+    _require_cuda(column_idx, "column_idx", int32_too=True)
     _require_cuda(target_nodes, "target_nodes")
     dev = row_ptr.device
     if column_idx.device != dev or target_nodes.device != dev:
@@ -389,10 +403,10 @@ def walk(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, walk_id_off
         walks = torch.empty((n, wl), dtype=torch.int64, device=dev) if out is None else out
         need = _lib.trw_walk_csr_workspace_bytes_for(n_nodes, nnz, float(p), float(q), n, int(walk_length)) if n else 0
         ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
-        _check(_lib.trw_walk_csr(_ptr(row_ptr), _ptr(column_idx), n_nodes, nnz, _ptr(target_nodes), n,
-                                 int(walk_id_offset), float(p), float(q), int(walk_length), int(seed), _ptr(walks),
-                                 walks.stride(0) if n else wl, _ptr(ws) if ws is not None else None, need, dev.index,
-                                 _stream(dev)))
+        _check(_lib.trw_walk_csr_typed(_ptr(row_ptr), row_ptr.element_size(), _ptr(column_idx), column_idx.element_size(), n_nodes,
+                                       nnz, _ptr(target_nodes), n, int(walk_id_offset), float(p), float(q), int(walk_length),
+                                       int(seed), _ptr(walks), walks.stride(0) if n else wl, _ptr(ws) if ws is not None else None,
+                                       need, dev.index, _stream(dev)))
     return walks
 
 
