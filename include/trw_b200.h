@@ -185,6 +185,25 @@ int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_t* targets,
 void trw_release_cached_buffers(void);
 
 /* ---------------------------------------------------------------------------------------
+ * Multi-GPU helpers over NCCL (the reference has no distributed code).
+ * Walks are independent: one broadcast replicates the CSR at set-up, every rank then walks its shard of
+ * the start nodes with global walk ids (walk_id_offset / walk_id_block / walk_id_stride above) and no
+ * traffic, and the shards may be gathered afterwards.  `nccl_comm` is the caller's ncclComm_t; NCCL is
+ * resolved at run time (from the process, else libnccl.so.2), so the library itself does not link it.
+ *
+ * trw_replicate_csr: broadcasts row_ptr[n_nodes+1] and col_idx[nnz] (4- or 8-byte elements) from `root`
+ *   into the same-sized device buffers of every other rank, on `stream`.
+ * trw_gather_walks: out[sum(rows_per_rank), row_len] on every rank = the ranks' contiguous shards in rank
+ *   order (`local` holds rows_per_rank[rank] rows; rows_per_rank is a host array of `world` entries).
+ * trw_nccl_available: 1 when the NCCL entry points were found.
+ * ------------------------------------------------------------------------------------- */
+int trw_nccl_available(void);
+int trw_replicate_csr(void* nccl_comm, int root, void* row_ptr, int row_ptr_bytes, int64_t n_nodes,
+                      void* col_idx, int col_idx_bytes, int64_t nnz, void* stream);
+int trw_gather_walks(void* nccl_comm, int rank, int world, const int64_t* local, int64_t row_len,
+                     int64_t* out, const int64_t* rows_per_rank, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Edge-list walks.   Replaces walk_edge_list() -> walk_edge_list_gpu():
  * csrc/rw_init.cpp:27-45, csrc/cuda/rw_cuda_edge_list.cu:243-308 (kernels :42-96, :126-240).
  *

@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "--use_fast_math",
     "-Xlinker", "-soname=libtrw_b200.so",
     "-shared",
+    "-ldl",
 ]
 
 
