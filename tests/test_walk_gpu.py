@@ -556,6 +556,72 @@ def test_second_order_statistics_match_analytic_and_oracle(rw, native, orc, gold
     assert chi2_pvalue(chi2_2, dof_2) > 0.01, ("vs oracle", chi2_2, dof_2)
 
 
+@pytest.mark.parametrize("p,q", [(0.5, 2.0), (1.0, 0.5), (0.25, 4.0), (2.0, 1.0)])
+def test_warp_per_walk_exact_cdf_kernel_samples_the_same_law(native, orc, golden, p, q):
+    """The A/B kernel of option n2v_warp (one warp per walk, exact CDF by prefix sum up to 64 neighbours, lock-step
+    rejection above): other draws, same law -- analytic chi-square / TV on karate (every row takes the CDF), and
+    acceptance classes against the analytic law and the oracle on a graph whose rows take the rejection branch."""
+    rp, ci = T(golden["utils/karate/row_ptr"]), T(golden["utils/karate/col_idx"])
+    n = 34
+    nodes = torch.arange(n).repeat_interleave(3000)
+    native.set_option("n2v_warp", 1)
+    try:
+        g = native.prepare_csr(rp.cuda(), ci.cuda())
+        walks = g.walk(nodes.cuda(), p, q, 100, 77)
+        del g
+        rp2, ci2 = random_csr(21, 400, 130)  # rows of ~110 neighbours: the rejection branch
+        assert int((rp2[1:] - rp2[:-1]).min()) > 64
+        g2 = native.prepare_csr(rp2.cuda(), ci2.cuda())
+        walks2 = g2.walk(torch.arange(400).repeat_interleave(250).cuda(), p, q, 100, 78)
+        native.set_option("n2v_warp", 0)
+        shipped2 = g2.walk(torch.arange(400).repeat_interleave(250).cuda(), p, q, 100, 79)  # the thread-per-walk kernel, other seed
+        del g2
+    finally:
+        native.set_option("n2v_warp", 0)
+    check_walks_follow_edges(walks, rp, ci, nodes)
+    got = second_order_counts(walks, n)
+    chi2, dof, tv = chi2_and_tv(got, node2vec_probs(rp, ci, p, q), n)
+    assert sum(got.values()) >= 10_000_000
+    assert chi2_pvalue(chi2, dof) > 0.01, (chi2, dof)
+    assert tv < 1e-2, tv
+    got2 = second_order_counts(walks2, 400)
+    # 44 k contexts share 1e7 samples, so the per-context class TV is sampling noise (~0.03) for any exact sampler: the
+    # warp kernel must sit where the shipped kernel sits, and be homogeneous with it and with the oracle
+    ship2 = second_order_counts(shipped2, 400)
+    assert abs(_class_tv(got2, rp2, ci2, p, q, 400) - _class_tv(ship2, rp2, ci2, p, q, 400)) < 2e-3
+    ref2 = second_order_counts(orc.walk(rp2, ci2, torch.arange(400).repeat_interleave(25), p, q, 100, 3), 400)
+    # homogeneity per context on the three acceptance classes (a per-neighbour table would have ~2 samples per cell here)
+    for other, what in ((ship2, "shipped kernel"), (ref2, "oracle")):
+        chi2_s, dof_s = _two_sample_class_chi2(got2, other, rp2, ci2, 400)
+        assert dof_s > 10_000 and chi2_pvalue(chi2_s, dof_s) > 0.01, (what, chi2_s, dof_s)
+
+
+def _two_sample_class_chi2(counts_a, counts_b, row_ptr, col_idx, n, min_total=20):
+    """Homogeneity of two sets of (t, v, x) counts on the acceptance classes (return / common neighbour / far) of
+    every (t, v) context: sum of the 2 x 3 contingency chi-squares.  Returns (chi2, dof)."""
+    from collections import defaultdict
+
+    rp, ci = row_ptr.numpy(), col_idx.numpy()
+    adj = [set(ci[rp[i]:rp[i + 1]].tolist()) for i in range(n)]
+    ctx = defaultdict(lambda: [[0, 0], [0, 0], [0, 0]])
+    for which, counts in enumerate((counts_a, counts_b)):
+        for key, c in counts.items():
+            tv_, x = divmod(key, n)
+            t, _ = divmod(tv_, n)
+            ctx[tv_][0 if x == t else (1 if x in adj[t] else 2)][which] += c
+    chi2, dof = 0.0, 0
+    for cells in ctx.values():
+        rows = [ab for ab in cells if ab[0] + ab[1] >= min_total]
+        na, nb = sum(a for a, _ in rows), sum(b for _, b in rows)
+        if len(rows) < 2 or na == 0 or nb == 0:
+            continue
+        for a, b in rows:
+            ea, eb = (a + b) * na / (na + nb), (a + b) * nb / (na + nb)
+            chi2 += (a - ea) ** 2 / ea + (b - eb) ** 2 / eb
+        dof += len(rows) - 1
+    return chi2, dof
+
+
 def _class_tv(counts, row_ptr, col_idx, p, q, n):
     """Count-weighted mean TV over the three acceptance classes (return / common neighbour / far)
     per (t,v) context: the quantity the rejection rule controls, and far less noisy than the

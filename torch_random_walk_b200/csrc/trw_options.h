@@ -12,6 +12,7 @@ struct Options {
     int64_t n2v_fold = 1;         // 1: fold the return edge out of the rejection envelope when 1/p > max(1, 1/q)
     int64_t n2v_slots = 8;        // A/B: 16 selects whole-line store pieces for the plain-rejection kernel with records (default 64-byte pieces)
     int64_t n2v_mix = 1;          // 1: two-sided mixture sampling when q > 1 and p <= q (duplicate-free rows; see node2vec_walk_kernel)
+    int64_t n2v_warp = 0;         // A/B: 1 runs node2vec walks on a kept graph with the warp-per-walk exact-CDF kernel (node2vec_warp_walk_kernel)
     int64_t n2v_min_ctas = -1;    // __launch_bounds__ min CTAs/SM of the node2vec kernel (4, 5 or 6; -1: 5 with edge records, else 4)
     int64_t row32 = 1;            // 1: re-encode row_ptr as uint32 offsets (needs workspace; the edge records depend on it)
     int64_t el_table = 1;         // 1: edge-list node2vec walks test membership through the hashed table (needs workspace); 0: the reference's scan
@@ -47,7 +48,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk) TRW_OPT(n2v_warp)
 
 Options& options();
 void count_launch(int n);

@@ -373,6 +373,109 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
     }
 }
 
+// ------------------------------------------------------------------------------------------ A/B: one warp per walk
+// The design BASELINE.json's north star sketches: a warp owns a walk; at a node of up to kCdfMax neighbours it reads the
+// whole neighbourhood cooperatively (one coalesced record load per lane), weighs every neighbour (1/p, 1, 1/q -- membership
+// through the same Blooms and table as the shipped kernel), and samples from the exact CDF by a shuffle prefix sum; above
+// that it falls back to rejection, which all lanes run in lock step (same addresses: one request per load).  Exact (same
+// law, other draws: statistics tested).  Kept as option n2v_warp for the A/B in profiles/: with 32 threads per walk an SM
+// holds 32 times fewer walks in flight, and on every graph measured a step costs more lines than a rejection trial.
+constexpr int kCdfMax = 64;
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) node2vec_warp_walk_kernel(const WalkArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    if (i >= a.n_walks) return;  // the whole warp leaves together
+    const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
+    const uint64_t wid = global_walk_id(a, i);
+    const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
+    const uint32_t* table = (a.table != nullptr && *a.table_failed == 0) ? a.table : nullptr;
+    const bool symmetric = a.asymmetric != nullptr && *a.asymmetric == 0;
+    int64_t* row = a.out + i * a.out_row_stride;
+    const int L = a.walk_length;
+    int64_t t = __ldg(a.targets + i);
+    if (lane == 0) stg64_hint(row, t, pol_stream);
+    if (L == 0) return;
+    int64_t tb = 0, te = 0, vb = 0, ve = 0;
+    uint32_t ctx = kBloomAll;
+    load_row<true>(a, t, tb, te, pol_keep);
+    uint4 rnd = philox4x32_10(make_uint4(wlo, whi, 1u, 0u), a.key);
+    int64_t v = propose<true>(a, t, tb, te, rnd.x, rnd.z, pol_stream, vb, ve, ctx);
+    if (lane == 0) stg64_hint(row + 1, v, pol_stream);
+    const uint64_t thr_any = min(a.thr0, min(a.thr1, a.thr2)), thr_far = max(a.thr1, a.thr2);
+    for (int s = 2; s <= L; ++s) {
+        const int64_t dv = ve - vb;
+        int64_t x = v, xb = vb, xe = ve;
+        uint32_t xw = kBloomAll;
+        if (dv > 0 && dv <= kCdfMax) {
+            // exact CDF over the neighbourhood: two rounds of 32 lanes
+            rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, 0u), a.key);
+            const double u = (double)((((uint64_t)rnd.x << 32) | rnd.y) >> 11) * (1.0 / 9007199254740992.0);
+            double prefix[2] = {0.0, 0.0}, carry = 0.0;
+            uint4 rec[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int64_t j = (int64_t)r * 32 + lane;
+                const bool valid = j < dv;
+                rec[r] = valid ? ldg_u32x4_hint(a.records + vb + j, pol_stream) : make_uint4(0, 0, 0, 0);
+                double w = 0.0;
+                if (valid) {
+                    const int64_t xj = rec[r].y != 0 ? (int64_t)rec[r].x : (int64_t)(((uint64_t)rec[r].w << 32) | rec[r].x);
+                    const uint32_t wj = rec[r].y != 0 ? rec[r].w : kBloomAll;
+                    if (xj == t) w = a.w_back;
+                    else if (a.w_common == a.w_far) w = a.w_far;
+                    else w = (triangle_maybe(ctx, xj, symmetric, wj, bloom_bit(t)) &&
+                              is_member_filtered<true>(a, xj, t, tb, te, table, pol_stream, pol_keep)) ? a.w_common : a.w_far;
+                }
+                double incl = w;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                prefix[r] = carry + incl;
+                carry = __shfl_sync(0xFFFFFFFFu, prefix[r], 31);
+            }
+            const double target = u * carry;
+            // the first neighbour whose inclusive prefix exceeds the target (the last valid one if rounding leaves none)
+            const unsigned hit0 = __ballot_sync(0xFFFFFFFFu, lane < dv && prefix[0] > target);
+            const unsigned hit1 = __ballot_sync(0xFFFFFFFFu, (int64_t)32 + lane < dv && prefix[1] > target);
+            int round = 0, src = 0;
+            if (hit0) src = __ffs(hit0) - 1;
+            else if (hit1) { round = 1; src = __ffs(hit1) - 1; }
+            else { round = dv > 32 ? 1 : 0; src = (int)((dv - 1) & 31); }
+            const uint4 pick = make_uint4(__shfl_sync(0xFFFFFFFFu, round ? rec[1].x : rec[0].x, src),
+                                          __shfl_sync(0xFFFFFFFFu, round ? rec[1].y : rec[0].y, src),
+                                          __shfl_sync(0xFFFFFFFFu, round ? rec[1].z : rec[0].z, src),
+                                          __shfl_sync(0xFFFFFFFFu, round ? rec[1].w : rec[0].w, src));
+            xb = (int64_t)pick.z;
+            xe = xb + (int64_t)pick.y;
+            if (pick.y != 0) { x = (int64_t)pick.x; xw = pick.w; }
+            else x = (int64_t)(((uint64_t)pick.w << 32) | pick.x);
+        } else if (dv > 0) {
+            // rejection, every lane in lock step (rw_cuda.cu:146-179)
+            for (uint32_t trial = 0;; ++trial) {
+                rnd = philox4x32_10(make_uint4(wlo, whi, (uint32_t)s, trial), a.key);
+                x = propose<true>(a, v, vb, ve, rnd.x, rnd.z, pol_stream, xb, xe, xw);
+                const uint32_t u = rnd.y;
+                bool accept;
+                if (u < thr_any) accept = true;
+                else if (x == t) accept = u < a.thr0;
+                else if (u >= thr_far) accept = false;
+                else if (a.thr1 == a.thr2) accept = true;
+                else accept = u < ((triangle_maybe(ctx, x, symmetric, xw, bloom_bit(t)) &&
+                                    is_member_filtered<true>(a, x, t, tb, te, table, pol_stream, pol_keep)) ? a.thr1 : a.thr2);
+                if (accept) break;
+            }
+        }
+        t = v; tb = vb; te = ve;
+        v = x; vb = xb; ve = xe;
+        ctx = xw;
+        if (lane == 0) stg64_hint(row + s, v, pol_stream);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 // Shared memory and L1 share one 256 KB array per SM, and the L1 side is where the in-flight
 // gathers land.  Measured on the benchmark graph (profiles/r01_summary.md): the first-order kernel
@@ -541,6 +644,7 @@ int csr_walk_plan(CsrWalkPlan* plan, const CsrGraph& g, double p, double q, int 
         const double mx = fmax(fmax(1.0 / p, 1.0), 1.0 / q);  // rw_cuda.cu:119-123
         const double p0 = 1.0 / p / mx, p1 = 1.0 / mx, p2 = 1.0 / q / mx;
         a.thr0 = threshold(p0); a.thr1 = threshold(p1); a.thr2 = threshold(p2);
+        a.w_back = 1.0 / p; a.w_common = 1.0; a.w_far = 1.0 / q;
         // Fetch row_ptr[x] before the verdict only when most proposals are accepted anyway.
         plan->speculate = opt.n2v_speculate < 0 ? (fmin(p1, p2) >= 0.5) : (opt.n2v_speculate != 0);
         // Return-edge folding applies when 1/p is the strict maximum of the three weights and the
@@ -602,7 +706,11 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
         else set_row_window(st, a.row_ptr.base, (size_t)(a.n_nodes + 1) << a.row_ptr.shift, plan.device, true);
     }
     timing_begin(1, st);
-    if (plan.uniform) {
+    if (!plan.uniform && options().n2v_warp != 0 && rec && plan.table) {  // A/B: the warp-per-walk design (see node2vec_warp_walk_kernel)
+        constexpr int BLOCK = 256;
+        const int64_t blocks = (a.n_walks * 32 + BLOCK - 1) / BLOCK;
+        node2vec_warp_walk_kernel<BLOCK><<<(unsigned)blocks, BLOCK, 0, st>>>(a);
+    } else if (plan.uniform) {
         if (!stage) launch_uniform<false, false, false>(a, st);
         else if (rec) launch_uniform<true, true, true>(a, st);
         else if (row32) launch_uniform<true, true, false>(a, st);
