@@ -297,6 +297,14 @@ int trw_calib_gather(const int64_t* table, int64_t table_elems, int64_t n_thread
                      int loads_per_thread, int bytes_per_load, int64_t seed, int64_t* sink,
                      int device, void* stream);
 
+/* A/B of the fused walk -> window pipeline (measurement only): node2vec walks
+ * on a kept graph (plain-rejection laws) whose skip-gram windows of width 5 are written straight to
+ * window_target[n_walks*(L-3)] and window_pos[n_walks*(L-3), 4] -- bit-identical to trw_windows on the walks of
+ * trw_walk_csr_prepared -- without the walks ever being stored. */
+int trw_walk_csr_prepared_windows5(const trw_csr_graph* graph, const int64_t* targets, int64_t n_walks,
+                                   int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
+                                   int64_t* window_target, int64_t* window_pos, void* stream);
+
 /* With option "time_kernels" = 1 the CSR walk brackets its table build (memset + build kernel)
  * and its walk kernel with CUDA events on the launch stream; this waits for the last such call
  * and returns both durations in milliseconds (0 when that phase did not run). */

@@ -596,6 +596,25 @@ def test_warp_per_walk_exact_cdf_kernel_samples_the_same_law(native, orc, golden
         assert dof_s > 10_000 and chi2_pvalue(chi2_s, dof_s) > 0.01, (what, chi2_s, dof_s)
 
 
+def test_fused_walk_to_windows_prototype_equals_walk_then_to_windows(native, rw):
+    """The A/B kernel of SURVEY section 8 (f1): skip-gram targets and positive windows of width 5 written by the walk
+    kernel itself must be, bit for bit, what rw.to_windows makes of the walks of the same call."""
+    from torch_random_walk_b200 import rmat
+
+    rp, ci = rmat.rmat_csr(14, 16, device="cuda", seed=6)
+    n = rp.numel() - 1
+    nodes = torch.arange(n, device="cuda")[: n - 5]  # a ragged last CTA and warp
+    g = native.prepare_csr(rp, ci)
+    for L in (80, 7, 4):
+        for p_, q_ in ((1.0, 0.5), (2.0, 0.5)):
+            walks = g.walk(nodes, p_, q_, L, 3)
+            target, pos, _ = rw.to_windows(walks, 5, n, 1)
+            f_target, f_pos = g.walk_windows5(nodes, p_, q_, L, 3)
+            assert torch.equal(f_target, target) and torch.equal(f_pos, pos), (L, p_, q_)
+    with pytest.raises(RuntimeError):
+        g.walk_windows5(nodes, 0.5, 2.0, 80, 3)  # the mixture laws are not part of the prototype
+
+
 def _two_sample_class_chi2(counts_a, counts_b, row_ptr, col_idx, n, min_total=20):
     """Homogeneity of two sets of (t, v, x) counts on the acceptance classes (return / common neighbour / far) of
     every (t, v) context: sum of the 2 x 3 contingency chi-squares.  Returns (chi2, dof)."""

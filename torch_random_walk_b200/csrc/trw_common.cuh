@@ -337,6 +337,26 @@ struct LineStager {
             ring[tid * kPitch + slot] = v;
             pending = (slot == (uint32_t)(SLOTS - 1)) || last;
         }
+        flush(pending, s, slot);
+    }
+    // Four consecutive elements s4 .. s4+3 at once, for rows whose base and s4 are multiples of four elements (a group
+    // then never straddles a line): one collective per group instead of four.
+    __device__ __forceinline__ void put4(bool have, int s4, int64_t v0, int64_t v1, int64_t v2, int64_t v3, bool last) {
+        if (policy == 0) return;
+        bool pending = false;
+        uint32_t slot = 0;
+        if (have) {
+            slot = (phase + (uint32_t)s4) & (uint32_t)(SLOTS - 1);
+            int64_t* r = ring + tid * kPitch + slot;
+            r[0] = v0; r[1] = v1; r[2] = v2; r[3] = v3;
+            slot += 3u;
+            pending = (slot == (uint32_t)(SLOTS - 1)) || last;
+        }
+        flush(pending, s4 + 3, slot);
+    }
+    // Warp collective: the lanes whose piece is complete (`pending`; `s` = index of the element in `slot`, the last one
+    // filled) have it written by the warp, SLOTS lanes per piece.
+    __device__ __forceinline__ void flush(bool pending, int s, uint32_t slot) {
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, pending);
         if (mask == 0) return;
         __syncwarp();

@@ -116,6 +116,50 @@ struct RowOutSmem {
     static constexpr int kWords = STAGE ? BLOCK * LineStager<BLOCK, SLOTS>::kPitch : 1;
 };
 
+// A/B for SURVEY section 8 (f1), the fused walk -> window pipeline: the node2vec kernel emits the skip-gram windows of
+// width 5 (targets and positive windows, the two outputs of to_windows that depend on the walk) instead of the walk
+// rows, so the walks never make their round trip through HBM.  Element s of a walk is the target of window s-2 and
+// completes window s-4 = (w[s-4], w[s-3], w[s-1], w[s]); both streams are contiguous per walk and leave through line
+// stagers like the walk row does.  Measured, not shipped: profiles/r02_summary.md.
+template <int BLOCK>
+struct WindowOut {
+    static constexpr int kTargetSlots = 8, kPosSlots = 16;
+    static constexpr int kWords = BLOCK * (LineStager<BLOCK, kTargetSlots>::kPitch + LineStager<BLOCK, kPosSlots>::kPitch);
+    LineStager<BLOCK, kTargetSlots> tgt;
+    LineStager<BLOCK, kPosSlots> pos;
+    int64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;  // the last four elements of the walk
+    int L = 0;
+    __device__ __forceinline__ void init(int64_t* ring, const WalkArgs& a, int64_t i, int tid, uint64_t pol) {
+        L = a.walk_length;
+        const int64_t per_walk = (int64_t)L - 3;  // windows of width 5 in a row of L + 1 elements
+        tgt.init(ring, a.win_target + i * per_walk, tid, pol);
+        pos.init(ring + BLOCK * LineStager<BLOCK, kTargetSlots>::kPitch, a.win_pos + i * per_walk * 4, tid, pol);
+    }
+    __device__ __forceinline__ void put(bool have, int s, int64_t v, bool) {
+        tgt.put(have && s >= 2 && s <= L - 2, s - 2, v, s == L - 2);
+        pos.put4(have && s >= 4, 4 * (s - 4), h0, h1, h3, v, s == L);
+        if (have) { h0 = h1; h1 = h2; h2 = h3; h3 = v; }
+    }
+};
+template <int BLOCK, bool STAGE, int SLOTS>
+__device__ __forceinline__ void init_out(RowOut<BLOCK, STAGE, SLOTS>& o, int64_t* ring, const WalkArgs& a, int64_t i, int tid, uint64_t pol) {
+    o.init(ring, a.out + i * a.out_row_stride, tid, pol);
+}
+template <int BLOCK>
+__device__ __forceinline__ void init_out(WindowOut<BLOCK>& o, int64_t* ring, const WalkArgs& a, int64_t i, int tid, uint64_t pol) {
+    o.init(ring, a, i, tid, pol);
+}
+template <int BLOCK, bool STAGE, int SLOTS, bool WIN>
+struct OutSel {
+    using type = RowOut<BLOCK, STAGE, SLOTS>;
+    static constexpr int kWords = RowOutSmem<BLOCK, STAGE, SLOTS>::kWords;
+};
+template <int BLOCK, bool STAGE, int SLOTS>
+struct OutSel<BLOCK, STAGE, SLOTS, true> {
+    using type = WindowOut<BLOCK>;
+    static constexpr int kWords = WindowOut<BLOCK>::kWords;
+};
+
 // First-order walk: one thread per walk, two dependent gathers per step (row span from L2, then
 // the chosen col_idx entry from HBM), one Philox block per four steps.
 template <int BLOCK, bool STAGE, bool ROW32, bool REC>
@@ -169,15 +213,16 @@ constexpr int kN2vSlots = FOLD ? 16 : 8;
 // a point in bar x at height h is accepted iff h < min(w(x), M').  Every neighbour is therefore
 // still drawn with probability proportional to its node2vec weight (t: M' + e = 1/p).  This is
 // only exact when no edge is stored twice, which the prepare step verifies (strict_counts).
-template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32, bool FOLD, bool REC, int SLOTS = kN2vSlots<FOLD>>
+template <int BLOCK, int MIN_CTAS, bool STAGE, bool TABLE, bool SPECULATE, bool ROW32, bool FOLD, bool REC, int SLOTS = kN2vSlots<FOLD>,
+          bool WIN = false>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const WalkArgs a) {
-    __shared__ int64_t ring[RowOutSmem<BLOCK, STAGE, SLOTS>::kWords];
+    __shared__ int64_t ring[OutSel<BLOCK, STAGE, SLOTS, WIN>::kWords];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = i < a.n_walks;  // lanes past the end stay for the warp-collective stores
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     const uint64_t wid = global_walk_id(a, i);
-    RowOut<BLOCK, STAGE, SLOTS> o;
-    o.init(ring, a.out + (live ? i : 0) * a.out_row_stride, threadIdx.x, output_policy(a.store_mode));
+    typename OutSel<BLOCK, STAGE, SLOTS, WIN>::type o;
+    init_out(o, ring, a, live ? i : 0, threadIdx.x, output_policy(a.store_mode));
     const int L = a.walk_length;
     const uint32_t wlo = (uint32_t)wid, whi = (uint32_t)(wid >> 32);
     // a table whose build reported an overflowing segment is not trusted: scan instead
@@ -706,7 +751,11 @@ int csr_walk_launch(const CsrWalkPlan& plan, const int64_t* targets, int64_t n_w
         else set_row_window(st, a.row_ptr.base, (size_t)(a.n_nodes + 1) << a.row_ptr.shift, plan.device, true);
     }
     timing_begin(1, st);
-    if (!plan.uniform && options().n2v_warp != 0 && rec && plan.table) {  // A/B: the warp-per-walk design (see node2vec_warp_walk_kernel)
+    if (a.win_target != nullptr) {  // A/B: fused walk -> skip-gram windows (csr_walk_windows5 has checked the preconditions)
+        constexpr int BLOCK = 128;  // two stagers per thread: 26 KB per CTA, six CTAs (768 threads) per SM
+        const unsigned grid = (unsigned)((a.n_walks + BLOCK - 1) / BLOCK);
+        TRW_LAUNCH((node2vec_walk_kernel<BLOCK, 6, true, true, false, true, false, true, 16, true>), 0, grid, BLOCK, st, a);
+    } else if (!plan.uniform && options().n2v_warp != 0 && rec && plan.table) {  // A/B: the warp-per-walk design (see node2vec_warp_walk_kernel)
         constexpr int BLOCK = 256;
         const int64_t blocks = (a.n_walks * 32 + BLOCK - 1) / BLOCK;
         node2vec_warp_walk_kernel<BLOCK><<<(unsigned)blocks, BLOCK, 0, st>>>(a);
@@ -927,6 +976,30 @@ extern "C" int trw_csr_graph_add_blooms(trw_csr_graph* graph, const void* row_pt
     timing_end(0, (cudaStream_t)stream);
     (void)row_ptr;
     return rc;
+}
+
+// A/B entry of the fused walk -> window pipeline (WindowOut): node2vec walks of a kept graph whose skip-gram windows of
+// width 5 go straight to target[n_walks * (L-3)] and pos[n_walks * (L-3), 4]; the walks themselves are not written.
+extern "C" int trw_walk_csr_prepared_windows5(const trw_csr_graph* graph, const int64_t* targets, int64_t n_walks,
+                                              int64_t walk_id_offset, double p, double q, int walk_length, int64_t seed,
+                                              int64_t* window_target, int64_t* window_pos, void* stream) {
+    if (!graph || !targets || !window_target || !window_pos || n_walks < 0) { set_error("trw_walk_csr_prepared_windows5: bad argument"); return TRW_ERR_ARG; }
+    if (walk_length < 4) { set_error("trw_walk_csr_prepared_windows5: walk_length must be at least 4"); return TRW_ERR_ARG; }
+    if ((((uintptr_t)window_target) & 7) || (((uintptr_t)window_pos) & 31)) { set_error("trw_walk_csr_prepared_windows5: outputs must be 32-byte aligned"); return TRW_ERR_ARG; }
+    if (n_walks == 0) return TRW_OK;
+    DeviceGuard guard(graph->g.device);
+    if (!guard.ok) { set_error("trw_walk_csr_prepared_windows5: cudaSetDevice(%d) failed", graph->g.device); return TRW_ERR_DEVICE; }
+    CsrWalkPlan plan;
+    int rc = csr_walk_plan(&plan, graph->g, p, q, walk_length, seed);
+    if (rc) return rc;
+    if (plan.uniform || plan.fold || !plan.table || plan.a.records == nullptr || plan.a.row32 == nullptr) {
+        set_error("trw_walk_csr_prepared_windows5: needs a kept graph with records and a law that takes plain rejection (1/p <= max(1, 1/q), q <= 1 or p > q)");
+        return TRW_ERR_ARG;
+    }
+    plan.a.win_target = window_target;
+    plan.a.win_pos = window_pos;
+    // `out` is unused by this variant; a non-null aligned dummy keeps the launcher on its staged path
+    return csr_walk_launch(plan, targets, n_walks, walk_id_offset, window_target, (int64_t)walk_length + 1, (cudaStream_t)stream);
 }
 
 extern "C" void trw_csr_graph_destroy(trw_csr_graph* graph) { delete graph; }

@@ -27,6 +27,8 @@ struct WalkArgs {
     // return-edge folding (see node2vec_walk_kernel): envelope M', excess 1/p - M', thresholds 1/M', (1/q)/M'
     uint64_t fthr1, fthr2;
     double fold_env, fold_excess;
+    int64_t* win_target = nullptr;  // A/B of the fused walk -> window pipeline (WindowOut): skip-gram targets ...
+    int64_t* win_pos = nullptr;     // ... and positive windows of width 5 instead of the walk rows
     double w_back, w_common, w_far;  // the node2vec weights themselves, 1/p, 1, 1/q (exact-CDF A/B kernel)
     int mix;  // 1: two-sided mixture sampling (q > 1, p <= q); fold_env = 1/q, fold_excess = 1/p - 1/q
     const unsigned long long* strict_counts;  // [descents in col_idx, descents at row boundaries]; equal = rows strictly increasing

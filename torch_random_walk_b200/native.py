@@ -63,6 +63,7 @@ def _load():
                                          _c_i64, _c_ptr]
     lib.trw_walk_csr_prepared.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_i64,
                                           _c_ptr]
+    lib.trw_walk_csr_prepared_windows5.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_ptr, _c_ptr]
     lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
     lib.trw_csr_graph_destroy.restype = None
     lib.trw_csr_graph_info.argtypes = [_c_ptr, _c_ptr, ctypes.POINTER(_c_i64), _c_int]
@@ -249,6 +250,21 @@ class PreparedCsr:
         _check(_lib.trw_walk_csr_to_host(ctypes.byref(view), _ptr(target_nodes), n, int(walk_id_offset), id_block, id_stride,
                                          float(p), float(q), int(walk_length), int(seed), _ptr(out)))
         return out
+
+    def walk_windows5(self, target_nodes, p, q, walk_length, seed, walk_id_offset=0):
+        """A/B of the fused walk -> window pipeline (trw_walk_csr_prepared_windows5): (target_nodes[K], pos_windows[K, 4]) of
+        rw.to_windows(rw.walk(...), 5, ...) without the walks being written.  Measurement only."""
+        _require_cuda(target_nodes, "target_nodes")
+        target_nodes = target_nodes.contiguous()
+        n, per_walk = target_nodes.size(0), int(walk_length) - 3
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            self._order_after_preparation(stream)
+            tgt = torch.empty((n * per_walk,), dtype=torch.int64, device=self.device)
+            pos = torch.empty((n * per_walk, 4), dtype=torch.int64, device=self.device)
+            _check(_lib.trw_walk_csr_prepared_windows5(self._handle, _ptr(target_nodes), n, int(walk_id_offset), float(p), float(q),
+                                                       int(walk_length), int(seed), _ptr(tgt), _ptr(pos), _stream(self.device)))
+        return tgt, pos
 
     def info(self):
         """What the preparation built (trw_csr_graph_info; waits for the preparing stream)."""
