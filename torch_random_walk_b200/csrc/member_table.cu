@@ -567,7 +567,9 @@ __global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col
             }
 #pragma unroll
             for (int u = 0; u < kBloomUnroll; ++u)
-                if (maybe[u] && is_member<true>(w[u], (int64_t)bb[u], (int64_t)bb[u] + bd[u], col_idx, table, pol_stream))
+                // the table of the longer row is asked once per neighbour of every shorter row it owns, by the warps of all SMs at
+                // about the same time: worth keeping in L2 (evict_last), unlike the one-off sectors of a walk
+                if (maybe[u] && is_member<true>(w[u], (int64_t)bb[u], (int64_t)bb[u] + bd[u], col_idx, table, pol_keep))
                     atomicOr(&s_bloom[warp][j[u]], bloom_bit(w[u]));
         }
         __syncwarp();
