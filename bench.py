@@ -473,7 +473,7 @@ def main():
             torch.cuda.synchronize()
             st = native.graph_cache_state(dev) if cache_on else {"prepared": False, "blooms": False}
             warm.append({"ms": e0.elapsed_time(e1), "launches": native.launch_count(), "prepared": st["prepared"], "blooms": st["blooms"]})
-            settled = (not cache_on) or (st["prepared"] and (st["blooms"] or uniform) and warm[-1]["launches"] <= 2)
+            settled = (not cache_on) or (st["prepared"] and (st["blooms"] or uniform) and warm[-1]["launches"] <= 3)
             if w + 1 >= W and settled:
                 break
         native.reset_launch_count()

@@ -219,15 +219,16 @@ def test_prepared_graph_and_graph_cache(native, rw):
             states.append(native.graph_cache_state(rp.device))
         # call 1 one-shot (checksum + build + walk), call 2 prepares for keeps, the call after two hits adds the
         # triangle Blooms, every later call is checksum + walk kernel
-        assert launches[0] > 2 and launches[1] > launches[0]
+        assert launches[0] > 3 and launches[1] > launches[0]
         assert [st["prepared"] for st in states] == [False, True, True, True, True, True]
         assert [st["blooms"] for st in states] == [False, False, False, True, True, True]
-        assert launches[2] == 2 and launches[3] == 3 and launches[4] == 2 and launches[5] == 2
+        # (a cached call = two checksum launches, one per array, + the walk kernel)
+        assert launches[2] == 3 and launches[3] == 4 and launches[4] == 3 and launches[5] == 3
         assert torch.equal(rw.walk(rp, ci, nodes, 0.25, 4.0, 30, 11), base[3])  # same graph, other law: still cached
         # the cache goes by content: a re-created tensor with the same bytes hits ...
         native.reset_launch_count()
         assert torch.equal(rw.walk(rp.clone(), ci.clone(), nodes, 0.5, 2.0, 30, 11), base[2])
-        assert native.launch_count() == 2
+        assert native.launch_count() == 3
         # ... and any write is seen, whether torch counts it (in-place op) or not (.data, a view made earlier)
         ci2 = ci.clone()
         for _ in range(4):
@@ -847,16 +848,28 @@ def test_walk_host_keeps_the_replica_and_notices_changes(native):
     nodes = torch.arange(n)
     laws = ((1.0, 0.5), (0.5, 2.0), (1.0, 1.0))
     expect = {law: native.walk(rp.cuda(), ci.cuda(), nodes.cuda(), law[0], law[1], 20, 3, cache=False).cpu() for law in laws}
-    saved = {k: native.get_option(k) for k in ("host_threads", "host_compress", "host_chunk_walks")}
+    saved = {k: native.get_option(k) for k in ("host_threads", "host_compress", "host_chunk_walks", "host_check_dma")}
     try:
         native.lib().trw_release_cached_buffers()
         native.set_option("host_chunk_walks", 2048)
-        for threads, compress in ((2, 1), (12, 1), (12, 2)):
+        for threads, compress, dma in ((2, 1, 1), (12, 1, 1), (12, 2, 0), (12, 1, 0)):
             native.set_option("host_threads", threads)
             native.set_option("host_compress", compress)
+            native.set_option("host_check_dma", dma)
             for rounds in range(6):  # fresh, full preparation, ..., triangle Blooms, steady
                 for law in laws:
                     assert torch.equal(native.walk_host(rp, ci, nodes, law[0], law[1], 20, 3, device=0), expect[law]), (threads, compress, rounds, law)
+        # pageable arrays: kept as well, always summed by the host threads
+        rp_p, ci_p = rp.clone(), ci.clone()
+        assert not rp_p.is_pinned()
+        for rounds in range(4):
+            assert torch.equal(native.walk_host(rp_p, ci_p, nodes, 1.0, 0.5, 20, 3, device=0), expect[(1.0, 0.5)])
+        ci_p[int(rp[9])] = ci_p[int(rp[9]) + 1]
+        assert torch.equal(native.walk_host(rp_p, ci_p, nodes, 1.0, 0.5, 20, 3, device=0),
+                           native.walk(rp_p.cuda(), ci_p.cuda(), nodes.cuda(), 1.0, 0.5, 20, 3, cache=False).cpu())
+        native.set_option("host_check_dma", 1)
+        for rounds in range(3):
+            assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0), expect[(1.0, 0.5)])
         # change the graph under the same pointers
         lo, hi = int(rp[3]), int(rp[4])
         ci[lo:hi] = ci[lo]

@@ -18,29 +18,26 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z;
 }
 
-// sum over i of mix64(value[i] + golden * (i + salt)): order-independent to accumulate, position-sensitive in value
-__global__ void __launch_bounds__(256) csr_checksum_kernel(IdxPtr row_ptr, int64_t n_row, IdxPtr col_idx, int64_t nnz,
-                                                           unsigned long long* __restrict__ out) {
+// sum over i of mix64(value[i] + golden * (base + i + 1)): order-independent to accumulate, position-sensitive in value.
+// One launch covers elements [base, base + n) of an array and ADDS its sum to *out, so an array may be summed in pieces.
+__global__ void __launch_bounds__(256) checksum_part_kernel(IdxPtr arr, int64_t n, int64_t base, uint64_t golden,
+                                                            unsigned long long* __restrict__ out) {
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t acc = 0;
-    // two elements per 16-byte load where the alignment allows it
-    const bool vec = col_idx.wide() && (((uintptr_t)col_idx.base) & 15) == 0;
-    if (vec) {
-        const int64_t n2 = nnz >> 1;
-        const longlong2* c2 = reinterpret_cast<const longlong2*>(col_idx.base);
+    // two elements per 16-byte load where the width and the alignment allow it
+    if (arr.wide() && (((uintptr_t)arr.base) & 15) == 0) {
+        const int64_t n2 = n >> 1;
+        const longlong2* c2 = reinterpret_cast<const longlong2*>(arr.base);
         for (int64_t i = gtid; i < n2; i += gsz) {
             longlong2 v;
             asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(c2 + i));
-            acc += mix64((uint64_t)v.x + 0x9E3779B97F4A7C15ull * (uint64_t)(2 * i + 1));
-            acc += mix64((uint64_t)v.y + 0x9E3779B97F4A7C15ull * (uint64_t)(2 * i + 2));
+            acc += mix64((uint64_t)v.x + golden * (uint64_t)(base + 2 * i + 1));
+            acc += mix64((uint64_t)v.y + golden * (uint64_t)(base + 2 * i + 2));
         }
-        if (gtid == 0 && (nnz & 1)) acc += mix64((uint64_t)ldg64_stream(col_idx + (nnz - 1)) + 0x9E3779B97F4A7C15ull * (uint64_t)nnz);
+        if (gtid == 0 && (n & 1)) acc += mix64((uint64_t)ldg64_stream(arr + (n - 1)) + golden * (uint64_t)(base + n));
     } else {
-        for (int64_t i = gtid; i < nnz; i += gsz)
-            acc += mix64((uint64_t)ldg64_stream(col_idx + i) + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1));
+        for (int64_t i = gtid; i < n; i += gsz) acc += mix64((uint64_t)ldg64_stream(arr + i) + golden * (uint64_t)(base + i + 1));
     }
-    for (int64_t i = gtid; i < n_row; i += gsz)
-        acc += mix64((uint64_t)ldg64_stream(row_ptr + i) + 0xD6E8FEB86659FD93ull * (uint64_t)(i + 1));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
     __shared__ unsigned long long part[8];
@@ -51,6 +48,16 @@ __global__ void __launch_bounds__(256) csr_checksum_kernel(IdxPtr row_ptr, int64
         for (int w = 0; w < 8; ++w) s += part[w];
         atomicAdd(out, s);
     }
+}
+
+int csr_checksum_part(IdxPtr arr, int64_t n, int64_t base, bool is_col_idx, uint64_t* out_device, int device, cudaStream_t st) {
+    if (n <= 0) return TRW_OK;
+    const int64_t want = ((n >> 1) + 256) / 256;
+    const int64_t cap = (int64_t)sm_count(device) * 16;
+    checksum_part_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(arr, n, base, is_col_idx ? kChecksumColGolden : kChecksumRowGolden,
+                                                                          (unsigned long long*)out_device);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "csr_checksum launch");
 }
 
 }  // namespace trw
@@ -79,12 +86,7 @@ extern "C" int trw_csr_checksum_typed(const void* row_ptr, int row_ptr_bytes, co
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_cuda(cudaMemsetAsync(out_device, 0, sizeof(uint64_t), st), "checksum memset");
     if (rc) return rc;
-    const int64_t n_row = row_ptr ? n_nodes + 1 : 0;
-    const int64_t work = (nnz >> 1) + n_row + 1;
-    const int64_t want = (work + 255) / 256;
-    const unsigned grid = (unsigned)(want < (int64_t)sm_count(d) * 16 ? (want < 1 ? 1 : want) : (int64_t)sm_count(d) * 16);
-    csr_checksum_kernel<<<grid, 256, 0, st>>>(IdxPtr(row_ptr, row_ptr_bytes), n_row, IdxPtr(col_idx, col_idx_bytes), nnz,
-                                              (unsigned long long*)out_device);
-    count_launch(1);
-    return check_cuda(cudaGetLastError(), "csr_checksum launch");
+    rc = csr_checksum_part(IdxPtr(col_idx, col_idx_bytes), nnz, 0, true, out_device, d, st);
+    if (rc) return rc;
+    return csr_checksum_part(IdxPtr(row_ptr, row_ptr_bytes), row_ptr ? n_nodes + 1 : 0, 0, false, out_device, d, st);
 }

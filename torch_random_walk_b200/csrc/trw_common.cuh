@@ -251,6 +251,11 @@ __device__ __forceinline__ int64_t ldg64_keep(IdxPtr p, uint64_t pol) {
     return (int64_t)v;
 }
 
+// Content checksum of CSR arrays (csr_checksum.cu): adds the position-sensitive sum of elements [base, base + n) of
+// `arr` to *out_device; col_idx and row_ptr use different multipliers.  The host twin lives in walk_host.cu.
+constexpr uint64_t kChecksumColGolden = 0x9E3779B97F4A7C15ull, kChecksumRowGolden = 0xD6E8FEB86659FD93ull;
+int csr_checksum_part(IdxPtr arr, int64_t n, int64_t base, bool is_col_idx, uint64_t* out_device, int device, cudaStream_t st);
+
 // Coherent 16-byte load of memory other threads are updating with atomics.
 __device__ __forceinline__ uint4 ld_relaxed_u32x4(const uint32_t* p) {
     uint4 v;

@@ -31,6 +31,8 @@ struct Options {
     int64_t host_threads = 0;     // host threads of the wire compression (0: the machine's, divided by LOCAL_WORLD_SIZE)
     int64_t host_up_chunk = 1 << 25;  // col_idx entries per compressed upload chunk
     int64_t host_packed_share = -1; // of every 8 download chunks, how many travel as uint32 (-1: 8 with >= 12 host threads, else 0; host_compress = 2: 4)
+    int64_t host_check_dma = 1;   // 1: the kept replica's content check re-reads pinned host arrays with the copy engine and sums them on the
+                                  // device (pageable arrays are always summed by host threads); 0: host threads
     int64_t host_keep_graph = 1;  // 1: trw_walk_csr_host keeps the device replica of the graph between calls (same host arrays, content
                                   // checked by checksum on every call); needs host_cache_buffers
     int64_t host_cache_buffers = 1;  // 1: trw_walk_csr_host keeps its device buffers between calls
@@ -48,7 +50,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk) TRW_OPT(n2v_warp)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk) TRW_OPT(n2v_warp) TRW_OPT(host_check_dma)
 
 Options& options();
 void count_launch(int n);

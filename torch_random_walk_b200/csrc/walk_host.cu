@@ -40,14 +40,14 @@ namespace trw {
 // Device buffers, streams and events of the host path are kept between calls (per device,
 // grow-only): cudaMalloc/cudaFree of ~15 GB cost more than the walk itself.  Released by
 // trw_release_cached_buffers() or with option host_cache_buffers = 0.
-enum { kBufRowPtr = 0, kBufColIdx, kBufTargets, kBufWorkspace, kBufOut0, kBufOut1, kBufUp0, kBufUp1, kBufDown0, kBufDown1, kNumBufs };
+enum { kBufRowPtr = 0, kBufColIdx, kBufTargets, kBufWorkspace, kBufOut0, kBufOut1, kBufUp0, kBufUp1, kBufDown0, kBufDown1, kBufCheck, kNumBufs };
 enum { kPinUp0 = 0, kPinUp1, kPinDown0, kPinDown1, kNumPinned };
 struct HostWalkCache {
     void* ptr[kNumBufs] = {};
     size_t cap[kNumBufs] = {};
     void* pinned[kNumPinned] = {};  // host staging of the compressed transfers
     size_t pinned_cap[kNumPinned] = {};
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr, check = nullptr;
     cudaEvent_t walked[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}, uploaded[2] = {nullptr, nullptr};
     std::mutex mu;  // one host-path call at a time per device
     // the kept replica: which host arrays it mirrors, its device-side checksum, and what has been prepared on it
@@ -65,6 +65,7 @@ struct HostWalkCache {
         forget_replica();
         if (compute) cudaStreamSynchronize(compute);
         if (copy) cudaStreamSynchronize(copy);
+        if (check) cudaStreamSynchronize(check);
         for (int k = 0; k < kNumBufs; ++k) {
             if (ptr[k]) cudaFree(ptr[k]);
             ptr[k] = nullptr;
@@ -83,7 +84,8 @@ struct HostWalkCache {
         }
         if (compute) cudaStreamDestroy(compute);
         if (copy) cudaStreamDestroy(copy);
-        compute = copy = nullptr;
+        if (check) cudaStreamDestroy(check);
+        compute = copy = check = nullptr;
         cudaGetLastError();
     }
     int reserve(int slot, size_t bytes, const char* what) {
@@ -257,6 +259,40 @@ static uint64_t host_csr_checksum(const int64_t* row_ptr, const int64_t* col_idx
 
 constexpr int kRetryPlain = 1;  // host_pipeline: a walk entry did not fit the uint32 wire format
 
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / a pinned torch tensor)?  Only then can the copy
+// engine read it asynchronously.
+static bool host_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// Content check of pinned host arrays without the host's cores: the copy engine brings the arrays up once more, piece by
+// piece, through a side buffer on a stream of its own (the upload direction of PCIe is idle while walks come down), and
+// each piece is summed on the device as it lands.  The sum ends up in pinned cell `pinned[kPinUp0][1]`.
+constexpr int64_t kCheckPieceBytes = (int64_t)256 << 20;
+static int enqueue_dma_checksum(HostWalkCache& r, int d, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz) {
+    int rc = r.reserve(kBufCheck, (size_t)kCheckPieceBytes + 256, "cudaMalloc check buffer");
+    if (!rc) rc = r.reserve_pinned(kPinUp0, 256, "cudaHostAlloc checksum cell");
+    if (rc) return rc;
+    char* side = (char*)r.ptr[kBufCheck];
+    uint64_t* d_sum = (uint64_t*)(side + kCheckPieceBytes);
+    TRW_TRY(cudaMemsetAsync(d_sum, 0, sizeof(uint64_t), r.check), "check sum memset");
+    const int64_t piece = kCheckPieceBytes / 8;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int64_t* src = pass == 0 ? col_idx : row_ptr;
+        const int64_t n = pass == 0 ? nnz : n_nodes + 1;
+        for (int64_t done = 0; done < n; done += piece) {
+            const int64_t m = std::min(piece, n - done);
+            TRW_TRY(cudaMemcpyAsync(side, src + done, (size_t)m * 8, cudaMemcpyHostToDevice, r.check), "H2D check piece");
+            rc = csr_checksum_part(IdxPtr((const int64_t*)side), m, done, pass == 0, d_sum, d, r.check);
+            if (rc) return rc;
+        }
+    }
+    TRW_TRY(cudaMemcpyAsync((uint64_t*)r.pinned[kPinUp0] + 1, d_sum, sizeof(uint64_t), cudaMemcpyDeviceToHost, r.check), "D2H check sum");
+    return TRW_OK;
+}
+
 struct HostCallShape {
     int64_t n_walks, walk_id_offset, id_block, id_stride;
     int walk_length;
@@ -354,6 +390,7 @@ struct StreamDrain {
     ~StreamDrain() {
         if (c->compute) cudaStreamSynchronize(c->compute);
         if (c->copy) cudaStreamSynchronize(c->copy);
+        if (c->check) cudaStreamSynchronize(c->check);
         cudaGetLastError();
     }
 };
@@ -362,6 +399,7 @@ static int ensure_streams(HostWalkCache& r) {
     if (r.compute) return TRW_OK;
     TRW_TRY(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking), "stream create");
     TRW_TRY(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking), "stream create");
+    TRW_TRY(cudaStreamCreateWithFlags(&r.check, cudaStreamNonBlocking), "stream create");
     for (int k = 0; k < 2; ++k) {
         TRW_TRY(cudaEventCreateWithFlags(&r.walked[k], cudaEventDisableTiming), "event create");
         TRW_TRY(cudaEventCreateWithFlags(&r.copied[k], cudaEventDisableTiming), "event create");
@@ -461,21 +499,33 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         CsrWalkPlan plan;
         rc = csr_walk_plan(&plan, r.graph, p, q, walk_length, seed);
         if (rc) return rc;
-        // the content check runs on half of the host threads beside the pipeline (which widens with the other half)
-        const int check_threads = std::max(1, n_threads / 2);
+        // The content check runs beside the pipeline.  Pinned arrays: the copy engine re-reads them over the idle upload
+        // direction and the device sums them (no host core involved; option host_check_dma).  Pageable arrays: half of the
+        // host threads sum them while the other half widens.
+        const bool dma_check = options().host_check_dma != 0 && host_pinned(row_ptr) && host_pinned(col_idx);
+        const int check_threads = dma_check ? 0 : std::max(1, n_threads / 2);
         uint64_t host_sum = 0;
-        std::thread checker([&] { host_sum = host_csr_checksum(row_ptr, col_idx, n_nodes, nnz, check_threads); });
-        // plain copies here: the checksum already keeps the host's memory system busy, and widening packed chunks beside it
-        // measured slower than the 55 GB/s the copy engine moves on its own (profiles/r02_host_path.md); option
-        // host_packed_share overrides
-        const int mode = options().host_packed_share >= 0 ? download_mode(n_threads, n_nodes, wide_targets.load() == 0) : 0;
+        std::thread checker;
+        if (dma_check) {
+            rc = enqueue_dma_checksum(r, d, row_ptr, col_idx, n_nodes, nnz);
+            if (rc) return rc;
+        } else {
+            checker = std::thread([&] { host_sum = host_csr_checksum(row_ptr, col_idx, n_nodes, nnz, check_threads); });
+        }
+        // Download format: with the host's cores busy summing, plain copies measured fastest (profiles/r02_host_path.md);
+        // with the check on the copy engine the cores are free to widen packed chunks.  Option host_packed_share overrides.
+        const int mode = (dma_check || options().host_packed_share >= 0) ? download_mode(n_threads, n_nodes, wide_targets.load() == 0) : 0;
         rc = host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, mode, std::max(1, n_threads - check_threads));
-        checker.join();  // (the pipeline returns on every path; nothing above can throw)
+        if (checker.joinable()) checker.join();  // (the pipeline returns on every path; nothing above can throw)
         if (rc) return rc;
+        if (dma_check) {
+            TRW_TRY(cudaStreamSynchronize(r.check), "sync content check");
+            host_sum = ((const uint64_t*)r.pinned[kPinUp0])[1];
+        }
         if (host_sum == r.replica_checksum) {
             if (timing)
-                fprintf(stderr, "[trw_walk_csr_host] kept replica (level %d, hit %d), download mode %d, %d host threads | total %.1f ms\n",
-                        r.level, r.hits, mode, n_threads, ms_since(t_hit));
+                fprintf(stderr, "[trw_walk_csr_host] kept replica (level %d, hit %d), content check by %s, %d of 8 chunks packed, %d host threads | total %.1f ms\n",
+                        r.level, r.hits, dma_check ? "copy engine + device" : "host threads", mode, n_threads, ms_since(t_hit));
             return TRW_OK;
         }
         r.forget_replica();  // the arrays changed under the same pointers: upload afresh and walk again
