@@ -121,7 +121,9 @@ int trw_walk_csr_prepared_at(const trw_csr_graph* graph, const void* row_ptr, co
                              int64_t* out, int64_t out_row_stride, void* stream);
 /* Adds the triangle Blooms (a 32-bit Bloom of the common neighbours of every edge's endpoints,
  * kept in the edge records) to a graph prepared without them; one pass, quadratic in `cap`, the longest
- * "shorter row" it works out exactly (<= 0: the library default).  No-op when already present. */
+ * "shorter row" it works out exactly (<= 0: the library default).  No-op when already present.  It changes what the
+ * handle holds: do not call it while another thread launches walks through the same handle, and order walks on other
+ * streams after `stream`. */
 int trw_csr_graph_add_blooms(trw_csr_graph* graph, const void* row_ptr, const void* col_idx, int64_t cap, void* stream);
 /* 64-bit position-sensitive checksum of (row_ptr[n_nodes+1], col_idx[nnz]) into *out_device (device memory):
  * one streaming pass on `stream`.  Equal sizes and checksums identify the graph a kept preparation belongs

@@ -180,6 +180,9 @@ class PreparedCsr:
         self.n_nodes, self.nnz = max(row_ptr.numel() - 1, 0), column_idx.numel()
         self._handle = _c_ptr()
         self._destroy = _lib.trw_csr_graph_destroy  # bound now: module globals may be gone at interpreter exit
+        # add_blooms rewrites what the handle points to: launches through one handle are issued one at a time, so that a
+        # walk is always stream-ordered after the pass whose flags its plan reads
+        self._lock = threading.Lock()
         self.has_blooms = bool(blooms)
         with torch.cuda.device(self.device):
             need = _lib.trw_csr_graph_workspace_bytes(self.n_nodes, self.nnz)
@@ -202,14 +205,15 @@ class PreparedCsr:
         """Adds the triangle Blooms to a graph prepared without them (trw_csr_graph_add_blooms): one pass,
         ~0.3 s on a 0.5 G-entry R-MAT at the default cap, after which q != 1 walks probe memory far less."""
         ci = self.column_idx if column_idx is None else column_idx
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device)
             self._order_after_preparation(stream)
             _check(_lib.trw_csr_graph_add_blooms(self._handle, None, _ptr(ci) if ci is not None else None, int(cap),
                                                  ctypes.c_void_p(stream.cuda_stream)))
+            self._ready = torch.cuda.Event()
             self._ready.record(stream)
             self._stream_id = stream.cuda_stream
-        self.has_blooms = True
+            self.has_blooms = True
 
     def walk(self, target_nodes, p, q, walk_length, seed, walk_id_offset=0, out=None, csr=None, walk_id_blocks=None):
         """`csr=(row_ptr, column_idx)`: the arrays this walk reads (required when the graph does not hold its own).
@@ -227,7 +231,7 @@ class PreparedCsr:
         target_nodes = target_nodes.contiguous()
         n, wl = target_nodes.size(0), int(walk_length) + 1
         _check_out(out, n, wl, dev)
-        with torch.cuda.device(dev):
+        with self._lock, torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             self._order_after_preparation(stream)
             walks = torch.empty((n, wl), dtype=torch.int64, device=dev) if out is None else out
@@ -246,9 +250,10 @@ class PreparedCsr:
         n, wl = target_nodes.size(0), int(walk_length) + 1
         out = _host_out(out, n, wl)
         id_block, id_stride = (0, 0) if walk_id_blocks is None else (int(walk_id_blocks[0]), int(walk_id_blocks[1]))
-        view = _GraphView(self._handle, rp.data_ptr(), ci.data_ptr() if ci.numel() else None, self._stream_id)
-        _check(_lib.trw_walk_csr_to_host(ctypes.byref(view), _ptr(target_nodes), n, int(walk_id_offset), id_block, id_stride,
-                                         float(p), float(q), int(walk_length), int(seed), _ptr(out)))
+        with self._lock:
+            view = _GraphView(self._handle, rp.data_ptr(), ci.data_ptr() if ci.numel() else None, self._stream_id)
+            _check(_lib.trw_walk_csr_to_host(ctypes.byref(view), _ptr(target_nodes), n, int(walk_id_offset), id_block, id_stride,
+                                             float(p), float(q), int(walk_length), int(seed), _ptr(out)))
         return out
 
     def walk_windows5(self, target_nodes, p, q, walk_length, seed, walk_id_offset=0):
@@ -257,7 +262,7 @@ class PreparedCsr:
         _require_cuda(target_nodes, "target_nodes")
         target_nodes = target_nodes.contiguous()
         n, per_walk = target_nodes.size(0), int(walk_length) - 3
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device)
             self._order_after_preparation(stream)
             tgt = torch.empty((n * per_walk,), dtype=torch.int64, device=self.device)
