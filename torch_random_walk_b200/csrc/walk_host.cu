@@ -57,7 +57,6 @@ struct HostWalkCache {
     uint64_t replica_checksum = 0;
     bool have_replica = false;
     int level = -1;       // -1 nothing prepared, 0 what one call's (p, q) needed, 1 the full kept preparation, 2 with triangle Blooms
-    int needs_sig = 0;    // level 0: the needs it was prepared for
     int hits = 0;
     CsrGraph graph;
     void forget_replica() { have_replica = false; level = -1; hits = 0; key_row_ptr = key_col_idx = nullptr; key_n_nodes = key_nnz = -1; }
@@ -464,7 +463,6 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     const HostCallShape shape{n_walks, walk_id_offset, 0, 0, walk_length};
     bool uniform, want_table, want_strict, want_records;
     csr_one_shot_needs(p, q, nnz, n_walks, walk_length, &uniform, &want_table, &want_strict, &want_records);
-    const int needs_sig = (uniform ? 1 : 0) | (want_table ? 2 : 0) | (want_strict ? 4 : 0) | (want_records ? 8 : 0);
 
     rc = r.reserve(kBufTargets, (size_t)n_walks * 8, "cudaMalloc targets");
     if (rc) return rc;
@@ -613,7 +611,6 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         r.key_row_ptr = row_ptr; r.key_col_idx = col_idx; r.key_n_nodes = n_nodes; r.key_nnz = nnz;
         r.have_replica = true;
         r.level = 0;
-        r.needs_sig = needs_sig;
         r.hits = 0;
     }
     if (timing) {
