@@ -317,7 +317,8 @@ int trw_last_kernel_ms(float* build_ms, float* walk_ms);
 int trw_device_info(int device, int64_t* out, int n_out);
 
 /* Tuning knobs for experiments ("name" -> integer); returns TRW_ERR_ARG for unknown names.
- * Defaults are the shipped configuration; bench.py records any override it applies. */
+ * Defaults are the shipped configuration; bench.py records any override it applies.  A knob belongs to the thread
+ * that sets it: other threads keep the defaults, and concurrent callers do not see each other's settings. */
 int trw_set_option(const char* name, int64_t value);
 int64_t trw_get_option(const char* name);
 

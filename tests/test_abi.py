@@ -116,3 +116,31 @@ def test_argument_validation_precedes_device_use():
     assert lib.trw_csr_graph_prepare(buf, buf, 1, 1, None, 0, 0, None, None) == -1  # null out_graph
     assert lib.trw_walk_csr_prepared(None, buf, 1, 0, 1.0, 1.0, 2, 1, buf, 3, None) == -1  # null graph
     lib.trw_csr_graph_destroy(None)
+
+
+def test_options_belong_to_the_calling_thread():
+    """trw_set_option changes the knobs of the calling thread only: another thread keeps the shipped defaults."""
+    import ctypes
+    import threading
+
+    from torch_random_walk_b200 import native
+
+    lib = native.lib()
+    default = native.get_option("edge_bloom_cap")
+    seen = {}
+
+    def other():
+        seen["before"] = native.get_option("edge_bloom_cap")
+        native.set_option("edge_bloom_cap", default + 7)
+        seen["own"] = native.get_option("edge_bloom_cap")
+
+    native.set_option("edge_bloom_cap", default + 1)
+    try:
+        t = threading.Thread(target=other)
+        t.start()
+        t.join()
+        assert seen == {"before": default, "own": default + 7}
+        assert native.get_option("edge_bloom_cap") == default + 1
+    finally:
+        native.set_option("edge_bloom_cap", default)
+    assert lib.trw_set_option(b"no_such_option", ctypes.c_int64(1)) != 0

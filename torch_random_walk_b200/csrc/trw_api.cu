@@ -39,8 +39,10 @@ int sm_count(int device) {
     return cached[device];
 }
 
+// The knobs belong to the calling thread: a thread that never sets one runs on the shipped defaults whatever other
+// threads experiment with, and concurrent callers cannot change each other's kernels mid-call.
 Options& options() {
-    static Options o;
+    thread_local Options o;
     return o;
 }
 

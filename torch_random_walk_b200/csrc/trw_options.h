@@ -1,4 +1,4 @@
-// Process-wide tuning knobs (trw_set_option / trw_get_option).  Defaults = shipped configuration.
+// Tuning knobs of the calling thread (trw_set_option / trw_get_option; thread_local).  Defaults = shipped configuration.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
