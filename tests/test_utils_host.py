@@ -138,3 +138,36 @@ def test_csr_from_edge_index_equals_to_csr(golden, name, graph, symmetric):
     assert np.array_equal(col_idx.numpy(), golden[f"utils/{name}/col_idx"])
     with pytest.raises(IndexError):
         utils.csr_from_edge_index(torch.tensor([[0, len(nodes)]]), len(nodes))
+
+
+def test_csr_files_round_trip_and_compact(tmp_path):
+    """f4 of SURVEY section 8: a CSR graph kept on disk ('.npz' / '.pt'), int32 where the values allow it, and an
+    edge-list file turned into the same CSR that utils.csr_from_edge_index gives."""
+    rng = np.random.default_rng(5)
+    edges = torch.from_numpy(rng.integers(0, 500, (4000, 2)))
+    row_ptr, col_idx = utils.csr_from_edge_index(edges, 500, symmetric=True)
+    for ext in (".npz", ".pt"):
+        path = str(tmp_path / ("graph" + ext))
+        utils.save_csr(path, row_ptr, col_idx)
+        rp, ci = utils.load_csr(path)
+        assert rp.dtype == torch.int32 and ci.dtype == torch.int32  # compact by default
+        assert torch.equal(rp.long(), row_ptr) and torch.equal(ci.long(), col_idx)
+        rp64, ci64 = utils.load_csr(path, dtype=torch.int64)
+        assert rp64.dtype == torch.int64 and torch.equal(rp64, row_ptr) and torch.equal(ci64, col_idx)
+        utils.save_csr(path, row_ptr, col_idx, compact=False)
+        assert utils.load_csr(path)[1].dtype == torch.int64
+    big = col_idx.clone()
+    big[3] = 2 ** 31 + 5
+    assert utils.compact_csr(row_ptr, big)[1].dtype == torch.int64 and utils.compact_csr(row_ptr, big)[0].dtype == torch.int32
+    np.save(str(tmp_path / "edges.npy"), edges.numpy())
+    torch.save({"edge_index": edges.t().contiguous()}, str(tmp_path / "edges.pt"))
+    for name in ("edges.npy", "edges.pt"):
+        rp, ci = utils.load_edge_index(str(tmp_path / name), num_nodes=500, symmetric=True)
+        assert torch.equal(rp, row_ptr) and torch.equal(ci, col_idx)
+    bad = str(tmp_path / "bad.npz")
+    np.savez(bad, row_ptr=np.array([0, 3]), col_idx=np.array([1]))
+    try:
+        utils.load_csr(bad)
+        raise AssertionError("a malformed file must be refused")
+    except ValueError:
+        pass

@@ -163,3 +163,74 @@ def csr_from_edge_index(edge_index, num_nodes, symmetric=False):
     row_ptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=col_idx.device)
     torch.cumsum(torch.bincount(rows, minlength=num_nodes), 0, out=row_ptr[1:])
     return row_ptr.contiguous(), col_idx
+
+
+# ---------------------------------------------------------------------------------------------
+# Interchange formats (the reference has none: its only inputs are networkx
+# objects).  A graph prepared once can be kept on disk as two arrays and handed to rw.walk as they
+# are -- int32 arrays included, which halve the file, the PCIe transfer and the graph in HBM.
+# ---------------------------------------------------------------------------------------------
+def compact_csr(row_ptr, col_idx):
+    """(row_ptr, col_idx) in the narrowest integer type rw.walk takes: int32 where every value fits
+    (node ids < 2^31 for col_idx, nnz < 2^31 for row_ptr), int64 otherwise.  Values are unchanged."""
+    def narrow(t):
+        t = torch.as_tensor(t)
+        if t.numel() == 0 or (int(t.max()) < 2 ** 31 and int(t.min()) >= -(2 ** 31)):
+            return t.to(torch.int32).contiguous()
+        return t.to(torch.int64).contiguous()
+
+    return narrow(row_ptr), narrow(col_idx)
+
+
+def save_csr(path, row_ptr, col_idx, compact=True):
+    """Writes a CSR graph to `path`: '.npz' (numpy, arrays `row_ptr` / `col_idx`) or '.pt' (torch.save of
+    a dict with the same keys).  compact=True stores int32 where the values allow it."""
+    if compact:
+        row_ptr, col_idx = compact_csr(row_ptr, col_idx)
+    row_ptr, col_idx = torch.as_tensor(row_ptr).cpu().contiguous(), torch.as_tensor(col_idx).cpu().contiguous()
+    if str(path).endswith(".npz"):
+        np.savez(path, row_ptr=row_ptr.numpy(), col_idx=col_idx.numpy())
+    elif str(path).endswith(".pt"):
+        torch.save({"row_ptr": row_ptr, "col_idx": col_idx}, path)
+    else:
+        raise ValueError("save_csr writes '.npz' or '.pt'")
+
+
+def load_csr(path, device=None, dtype=None):
+    """Reads what save_csr wrote -> (row_ptr, col_idx) on `device` (default CPU).  dtype=None keeps the
+    stored integer types (rw.walk takes int32 and int64); torch.int64 gives the reference's dtype."""
+    if str(path).endswith(".npz"):
+        with np.load(path) as z:
+            row_ptr, col_idx = torch.from_numpy(z["row_ptr"]), torch.from_numpy(z["col_idx"])
+    elif str(path).endswith(".pt"):
+        d = torch.load(path, map_location="cpu")
+        row_ptr, col_idx = d["row_ptr"], d["col_idx"]
+    else:
+        raise ValueError("load_csr reads '.npz' or '.pt'")
+    if row_ptr.dim() != 1 or col_idx.dim() != 1 or row_ptr.numel() == 0 or int(row_ptr[-1]) != col_idx.numel():
+        raise ValueError("not a CSR graph: row_ptr[-1] must equal len(col_idx)")
+    if dtype is not None:
+        row_ptr, col_idx = row_ptr.to(dtype), col_idx.to(dtype)
+    if device is not None:
+        row_ptr, col_idx = row_ptr.to(device), col_idx.to(device)
+    return row_ptr.contiguous(), col_idx.contiguous()
+
+
+def load_edge_index(path, num_nodes=None, symmetric=False, device=None):
+    """Edge list file -> CSR: '.npy' (an integer array [E,2] or [2,E]) or '.pt' (a tensor of that shape,
+    or a dict with key 'edge_index').  num_nodes defaults to max id + 1.  Rows sorted, duplicates
+    merged (csr_from_edge_index); symmetric=True adds the reversed edges."""
+    if str(path).endswith(".npy"):
+        e = torch.from_numpy(np.load(path))
+    elif str(path).endswith(".pt"):
+        e = torch.load(path, map_location="cpu")
+        if isinstance(e, dict):
+            e = e["edge_index"]
+    else:
+        raise ValueError("load_edge_index reads '.npy' or '.pt'")
+    e = torch.as_tensor(e).to(torch.int64)
+    if device is not None:
+        e = e.to(device)
+    if num_nodes is None:
+        num_nodes = int(e.max()) + 1 if e.numel() else 0
+    return csr_from_edge_index(e, num_nodes, symmetric=symmetric)
