@@ -289,6 +289,22 @@ int trw_windows_triples_cbow(const int64_t* walks, int64_t n_walks, int64_t walk
                              int64_t* pos_triples, int64_t* neg_triples, int64_t* pos_windows,
                              int device, void* stream);
 
+/* The triple-window calls with a workspace (trw_windows_triples_workspace_bytes(n_triples) bytes of 256-byte aligned
+ * device memory, contents undefined before and after): the negative rows are then gathered from a 16-byte uint32
+ * copy of `triples` made inside the call (one 128-bit load per row instead of three 64-bit ones) whenever every id
+ * fits 32 bits; identical outputs. */
+size_t trw_windows_triples_workspace_bytes(int64_t n_triples);
+int trw_windows_triples_ws(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                           int64_t num_nodes, int64_t padding_idx,
+                           const int64_t* triples, int64_t n_triples, int64_t seed,
+                           int64_t* target, int64_t* pos, int64_t* neg,
+                           void* workspace, size_t workspace_bytes, int device, void* stream);
+int trw_windows_triples_cbow_ws(const int64_t* walks, int64_t n_walks, int64_t walk_cols,
+                                int window_size, int64_t num_nodes, int64_t padding_idx,
+                                const int64_t* triples, int64_t n_triples, int64_t seed,
+                                int64_t* pos_triples, int64_t* neg_triples, int64_t* pos_windows,
+                                void* workspace, size_t workspace_bytes, int device, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py / profiles only; not part of the reference's surface).
  * trw_calib_gather: every thread performs `loads_per_thread` dependent random loads of

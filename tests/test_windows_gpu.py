@@ -170,6 +170,28 @@ def test_bulk_store_path_of_the_triple_windows_equals_plain_stores(rw):
             assert torch.equal(a, b), (n, wl, W)
 
 
+def test_compact_triple_table_gives_the_same_negatives(rw):
+    """The negative rows come from a 16-byte uint32 copy of `triples` made inside the call; with it switched off
+    (option win_table16), and for a table with an id that does not fit 32 bits, the outputs must be the same."""
+    from torch_random_walk_b200 import native
+
+    walks = torch.randint(0, 5000, (777, 41), device="cuda")
+    for triples in (torch.randint(0, 5000, (30011, 3), device="cuda"),
+                    torch.cat((torch.randint(0, 5000, (999, 3), device="cuda"), torch.tensor([[1, (1 << 33) + 2, 3]], device="cuda")))):
+        packed = rw.to_windows_triples(walks, 5, 5000, 4999, triples, 3) + rw.to_windows_triples_cbow(walks, 5, 5000, 4999, triples, 3)
+        native.set_option("win_table16", 0)
+        try:
+            plain = rw.to_windows_triples(walks, 5, 5000, 4999, triples, 3) + rw.to_windows_triples_cbow(walks, 5, 5000, 4999, triples, 3)
+        finally:
+            native.set_option("win_table16", 1)
+        for a, b in zip(packed, plain):
+            assert torch.equal(a, b)
+        # every negative row is a row of `triples`
+        neg = packed[2].reshape(-1, 3)[:5000]
+        keys = set(map(tuple, triples.tolist()))
+        assert all(tuple(r) in keys for r in neg.tolist())
+
+
 def test_window_outputs_stay_inside_their_tensors(rw):
     """Guard bands around every output of the four window kernels (see the walk test of the same name)."""
     import ctypes

@@ -1,0 +1,11 @@
+import sys, torch
+sys.path.insert(0, "/root/repo")
+from torch_random_walk_b200 import native, rmat
+triples = rmat.kg_triples(14541, 237, 310116, device="cuda")
+_, ts = rmat.relation_tail_index(triples, 14541)
+tw = torch.randint(0, 14541, (500000, 81), dtype=torch.int64, device="cuda")
+for _ in range(2):
+    out = native.to_windows_triples(tw, 5, 14541, 14778, ts, 1)
+    del out
+torch.cuda.synchronize()
+print("ok")

@@ -120,21 +120,25 @@ static std::tuple<at::Tensor, at::Tensor, at::Tensor> triple_windows(Fn fn, cons
   auto other = cbow ? torch::empty({k, 3}, like(*walks)) : torch::empty({k, 2 * window_size, 3}, like(*walks));
   auto& o1 = cbow ? other : win;
   auto& o2 = cbow ? win : other;
+  // workspace for the 16-byte copy of `triples` the negative rows are gathered from
+  const size_t need = trw_windows_triples_workspace_bytes(tr.size(0));
+  auto ws = torch::empty({(int64_t)need}, like(*walks).dtype(torch::kUInt8));
   TRW_CHECK(fn(ptr(*walks), n, wl, window_size, num_nodes, padding_idx, ptr(tr), tr.size(0), seed, first.data_ptr<int64_t>(),
-               o1.data_ptr<int64_t>(), o2.data_ptr<int64_t>(), walks->device().index(), stream()));
+               o1.data_ptr<int64_t>(), o2.data_ptr<int64_t>(), need ? ws.data_ptr() : nullptr, need, walks->device().index(),
+               stream()));
   return std::make_tuple(first, o1, o2);
 }
 
 std::tuple<at::Tensor, at::Tensor, at::Tensor> to_windows_triples(const torch::Tensor* walks, const int window_size,
                                                                   const int64_t num_nodes, const int64_t padding_idx,
                                                                   const torch::Tensor* triples, const int seed) {
-  return triple_windows(trw_windows_triples, walks, window_size, num_nodes, padding_idx, triples, seed, false);
+  return triple_windows(trw_windows_triples_ws, walks, window_size, num_nodes, padding_idx, triples, seed, false);
 }
 
 std::tuple<at::Tensor, at::Tensor, at::Tensor> to_windows_triples_cbow(const torch::Tensor* walks, const int window_size,
                                                                        const int64_t num_nodes, const int64_t padding_idx,
                                                                        const torch::Tensor* triples, const int seed) {
-  return triple_windows(trw_windows_triples_cbow, walks, window_size, num_nodes, padding_idx, triples, seed, true);
+  return triple_windows(trw_windows_triples_cbow_ws, walks, window_size, num_nodes, padding_idx, triples, seed, true);
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {

@@ -13,6 +13,8 @@
 // rows produced whole into per-warp stages (triple_tile()).  Positives and targets are bit-exact
 // with the reference; negatives are Philox draws indexed by the output element (one block per
 // aligned quad of draws), so they do not depend on the launch shape or on which path wrote them.
+#include <algorithm>
+
 #include "trw_common.cuh"
 #include "trw_options.h"
 
@@ -42,6 +44,8 @@ struct WinArgs {
     int64_t num_nodes, pad;
     const int64_t* triples;
     int64_t n_triples;
+    const uint4* triples16;   // optional 16-byte copy of `triples` (x, y, z = head, relation, tail as uint32), see compact_triples_kernel
+    const int* triples16_bad; // device flag: some value did not fit, the copy must not be used
     uint2 key;
     int64_t* out[3];       // outputs in the API's order
     uint32_t epw[3];       // elements of out[k] per walk
@@ -119,13 +123,20 @@ __device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint
                  ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
 }
 
-template <int BLOCK, bool BULK, class RowFn>
+struct NoPre {
+    __device__ __forceinline__ void operator()(uint32_t, uint32_t) const {}
+};
+// pre(first, cnt) is called by every lane before the rows of a round are produced (and followed by a __syncwarp):
+// per-round work that the rows share, such as drawing the round's random row indices.
+template <int BLOCK, bool BULK, class RowFn, class Pre = NoPre>
 __device__ __forceinline__ void emit_rows(int64_t* __restrict__ dst, uint32_t n_rows, int64_t* __restrict__ stage, uint32_t& round,
-                                          RowFn row_fn) {
+                                          RowFn row_fn, Pre pre = Pre()) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool vec = (((uintptr_t)dst) & 15) == 0;
     for (uint32_t first = warp * kWarpRows; first < n_rows; first += (BLOCK / 32) * kWarpRows) {
         const uint32_t cnt = min((uint32_t)kWarpRows, n_rows - first);
+        pre(first, cnt);
+        __syncwarp();
         int64_t* wstage = stage + (warp * (BULK ? 2 : 1) + (BULK ? (round & 1u) : 0u)) * (kWarpRows * 3);
         if (BULK) {  // this stage was handed to the copy engine two rounds ago
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -171,7 +182,9 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
         const int64_t* w = tile + (size_t)i * a.wl + 2u * ti;
         o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
     });
-    // positive windows: row (i, ti, h), the three slots of triple_window_value() at once
+    // positive windows: row (i, ti, h), the three slots at once, through the per-warp stage.  (Storing them element by element from
+    // the tile instead -- a (walk, target) block per warp round, one lane per element -- measured 2.7 vs 2.1 ms: 30 of 32 lanes
+    // busy and one division per 30 elements cost more than the stage's shared-memory traffic.)
     if (R > 0) {
         emit_rows<BLOCK, BULK>(a.out[pos_out] + (uint64_t)i0 * K * R * 3u, (uint32_t)tw * K * R, stage, round, [&](uint32_t row, int64_t* o) {
             uint32_t k, h, i, ti;
@@ -192,7 +205,43 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
             }
         });
     }
-    if (MODE == kTriples) {
+    // The negatives gather rows of `triples`.  As int64 a row is three 8-byte loads that straddle sectors; the caller may
+    // pass a 16-byte uint32 copy (one LDG.128 per row, a third of the instructions), valid when every id fits 32 bits.
+    const bool small_table = (uint64_t)a.n_triples <= 0xFFFFFFFFull;
+    const uint4* t16 = (a.triples16 != nullptr && small_table && *a.triples16_bad == 0) ? a.triples16 : nullptr;
+    if (MODE == kTriples && t16 != nullptr) {
+        // neg_windows from the 16-byte copy.  ncu: the kernel is bound by L1/shared-memory wavefronts (92 %), not by HBM or
+        // issue slots, so rows do not go through a stage here: a warp draws the row indices of 64 rows (four per Philox
+        // block; same blocks and word order as the int64 path below) and then stores element by element, coalesced --
+        // the three lanes of a row read one sector of the table between them.
+        __shared__ uint32_t drawn[BLOCK / 32][kWarpRows];
+        const uint64_t row0 = (uint64_t)i0 * K * R;
+        const uint32_t n_rows = (uint32_t)tw * K * R;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t* mine = drawn[warp];
+        int64_t* dst = a.out[neg_out] + row0 * 3u;
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(t16);
+        const uint32_t nt = (uint32_t)a.n_triples;
+        for (uint32_t first = warp * kWarpRows; first < n_rows; first += (BLOCK / 32) * kWarpRows) {
+            const uint32_t cnt = min((uint32_t)kWarpRows, n_rows - first);
+            if (lane * 4u < cnt) {
+                const uint64_t gq = (row0 + first) / 4u + lane;
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), 3u, 0x51554144u), a.key);
+                mine[lane * 4 + 0] = __umulhi(r.x, nt); mine[lane * 4 + 1] = __umulhi(r.y, nt);
+                mine[lane * 4 + 2] = __umulhi(r.z, nt); mine[lane * 4 + 3] = __umulhi(r.w, nt);
+            }
+            __syncwarp();
+            int64_t* out = dst + (uint64_t)first * 3u;
+            const uint32_t n = cnt * 3u;
+#pragma unroll 2
+            for (uint32_t e = lane; e < n; e += 32) {
+                const uint32_t row = (e * 0xAAABu) >> 17;  // e / 3 for e < 2^15
+                const uint32_t c = e - row * 3u;
+                out[e] = (int64_t)__ldg(words + 4u * mine[row] + c);
+            }
+            __syncwarp();
+        }
+    } else if (MODE == kTriples) {
         // neg_windows: every row a uniformly drawn row of `triples` (windows_cuda.cu:353-365).  The row
         // indices of a chunk are drawn first, four per Philox block (the tile's first row is a multiple
         // of four), then the rows are gathered element by element straight into the coalesced stores
@@ -203,7 +252,7 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
         const uint64_t row0 = (uint64_t)i0 * K * R;
         const uint32_t n_rows = (uint32_t)tw * K * R;
         int64_t* dst = a.out[neg_out] + row0 * 3u;
-        const bool small = (uint64_t)a.n_triples <= 0xFFFFFFFFull;
+        const bool small = small_table;
         for (uint32_t base = 0; base < n_rows; base += kNegChunkRows) {
             const uint32_t rows = min((uint32_t)kNegChunkRows, n_rows - base);
             for (uint32_t q = tid; q * 4u < rows; q += BLOCK) {
@@ -238,8 +287,14 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
             int64_t nh = 0, nr = 0, nt = 0;
             for (uint32_t attempt = 0; attempt <= 101u; ++attempt) {
                 const uint2 r = draw64(a.key, grow, 4u, attempt);
-                const int64_t* t = a.triples + bounded(r.x, r.y, a.n_triples) * 3;
-                nh = __ldg(t); nr = __ldg(t + 1); nt = __ldg(t + 2);
+                const int64_t pick = bounded(r.x, r.y, a.n_triples);
+                if (t16 != nullptr) {
+                    const uint4 t = __ldg(t16 + pick);
+                    nh = (int64_t)t.x; nr = (int64_t)t.y; nt = (int64_t)t.z;
+                } else {
+                    const int64_t* t = a.triples + pick * 3;
+                    nh = __ldg(t); nr = __ldg(t + 1); nt = __ldg(t + 2);
+                }
                 if (nh != ph || nr != pr || nt != pt) break;
             }
             o[0] = nh; o[1] = nr; o[2] = nt;
@@ -319,10 +374,27 @@ __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
     }
 }
 
+// 16-byte copy of the triple table for the negative gathers: (head, relation, tail, 0) as uint32.  *bad is raised when a
+// value does not fit (negative or >= 2^32); the window kernel then reads the int64 table as before.
+__global__ void __launch_bounds__(256) compact_triples_kernel(const int64_t* __restrict__ triples, int64_t n, uint4* __restrict__ out,
+                                                              int* __restrict__ bad) {
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    bool wide = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gsz) {
+        const int64_t h = __ldg(triples + 3 * i), r = __ldg(triples + 3 * i + 1), t = __ldg(triples + 3 * i + 2);
+        wide |= ((uint64_t)h | (uint64_t)r | (uint64_t)t) > 0xFFFFFFFFull;
+        out[i] = make_uint4((uint32_t)h, (uint32_t)r, (uint32_t)t, 0u);
+    }
+    if (wide) *bad = 1;
+}
+
+static size_t triples_workspace_bytes(int64_t n_triples) { return n_triples > 0 ? (((size_t)n_triples * 16 + 255) & ~(size_t)255) + 256 : 0; }
+
 template <int MODE>
 static int launch_windows(const char* name, const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
                           int64_t num_nodes, int64_t pad, const int64_t* triples, int64_t n_triples, int64_t seed,
-                          int64_t* o0, int64_t* o1, int64_t* o2, int device, void* stream) {
+                          int64_t* o0, int64_t* o1, int64_t* o2, int device, void* stream, void* workspace = nullptr,
+                          size_t workspace_bytes = 0) {
     constexpr bool kTripleMode = (MODE == kTriples || MODE == kTriplesCbow);
     if (n_walks < 0 || walk_cols < 0 || window_size < 0) { set_error("%s: negative size", name); return TRW_ERR_ARG; }
     if (walk_cols > (1 << 24) || window_size > (1 << 15)) {
@@ -359,6 +431,21 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     WinArgs a;
     a.walks = walks; a.n_walks = n_walks; a.wl = (int)walk_cols; a.W = W; a.mid = W / 2; a.per_walk = (int)per_walk;
     a.num_nodes = num_nodes; a.pad = pad; a.triples = triples; a.n_triples = n_triples;
+    a.triples16 = nullptr; a.triples16_bad = nullptr;
+    if (kTripleMode && workspace != nullptr && options().win_table16 != 0) {
+        if (workspace_bytes < triples_workspace_bytes(n_triples) || ((uintptr_t)workspace & 255)) {
+            set_error("%s: workspace needs %zu bytes at 256-byte alignment", name, triples_workspace_bytes(n_triples));
+            return TRW_ERR_WORKSPACE;
+        }
+        uint4* t16 = reinterpret_cast<uint4*>(workspace);
+        int* bad = reinterpret_cast<int*>((char*)workspace + triples_workspace_bytes(n_triples) - 256);
+        int rc = check_cuda(cudaMemsetAsync(bad, 0, sizeof(int), (cudaStream_t)stream), "triples flag memset");
+        if (rc) return rc;
+        const int64_t blocks = std::min<int64_t>((n_triples + 255) / 256, (int64_t)sm_count(d) * 8);
+        compact_triples_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(triples, n_triples, t16, bad);
+        count_launch(1);
+        a.triples16 = t16; a.triples16_bad = bad;
+    }
     a.key = philox_key(seed, kTagWindows);
     a.out[0] = o0; a.out[1] = o1; a.out[2] = o2;
     for (int k = 0; k < 3; ++k) a.epw[k] = epw[k];
@@ -423,6 +510,24 @@ extern "C" int trw_windows_triples(const int64_t* walks, int64_t n_walks, int64_
                                    int64_t seed, int64_t* target, int64_t* pos, int64_t* neg, int device, void* stream) {
     return launch_windows<kTriples>("trw_windows_triples", walks, n_walks, walk_cols, window_size, num_nodes, padding_idx,
                                     triples, n_triples, seed, target, pos, neg, device, stream);
+}
+
+extern "C" size_t trw_windows_triples_workspace_bytes(int64_t n_triples) { return triples_workspace_bytes(n_triples); }
+
+extern "C" int trw_windows_triples_ws(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size, int64_t num_nodes,
+                                      int64_t padding_idx, const int64_t* triples, int64_t n_triples, int64_t seed, int64_t* target,
+                                      int64_t* pos, int64_t* neg, void* workspace, size_t workspace_bytes, int device, void* stream) {
+    return launch_windows<kTriples>("trw_windows_triples", walks, n_walks, walk_cols, window_size, num_nodes, padding_idx, triples,
+                                    n_triples, seed, target, pos, neg, device, stream, workspace, workspace_bytes);
+}
+
+extern "C" int trw_windows_triples_cbow_ws(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                                           int64_t num_nodes, int64_t padding_idx, const int64_t* triples, int64_t n_triples,
+                                           int64_t seed, int64_t* pos_triples, int64_t* neg_triples, int64_t* pos_windows,
+                                           void* workspace, size_t workspace_bytes, int device, void* stream) {
+    return launch_windows<kTriplesCbow>("trw_windows_triples_cbow", walks, n_walks, walk_cols, window_size, num_nodes, padding_idx,
+                                        triples, n_triples, seed, pos_triples, neg_triples, pos_windows, device, stream, workspace,
+                                        workspace_bytes);
 }
 
 extern "C" int trw_windows_triples_cbow(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,

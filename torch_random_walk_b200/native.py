@@ -85,6 +85,11 @@ def _load():
     wint = [_c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
     lib.trw_windows_triples.argtypes = wint
     lib.trw_windows_triples_cbow.argtypes = wint
+    wint_ws = wint[:-2] + [_c_ptr, _c_size] + wint[-2:]
+    lib.trw_windows_triples_ws.argtypes = wint_ws
+    lib.trw_windows_triples_cbow_ws.argtypes = wint_ws
+    lib.trw_windows_triples_workspace_bytes.restype = _c_size
+    lib.trw_windows_triples_workspace_bytes.argtypes = [_c_i64]
     lib.trw_calib_gather.argtypes = [_c_ptr, _c_i64, _c_i64, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_ptr]
     lib.trw_device_check.argtypes = [_c_int]
     if lib.trw_abi_version() != 3:
@@ -518,19 +523,21 @@ def _triple_windows(fn, walks, window_size, num_nodes, padding_idx, triples, see
         win_a = torch.empty((k, 2 * w, 3), dtype=torch.int64, device=dev)
         other = torch.empty((k, 3) if cbow else (k, 2 * w, 3), dtype=torch.int64, device=dev)
         outs = (first, other, win_a) if cbow else (first, win_a, other)
+        need = _lib.trw_windows_triples_workspace_bytes(triples.size(0))
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
         _check(fn(_ptr(walks), n, wl, w, int(num_nodes), int(padding_idx), _ptr(triples), triples.size(0), int(seed),
-                  _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), dev.index, _stream(dev)))
+                  _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(ws) if ws is not None else None, need, dev.index, _stream(dev)))
     return outs
 
 
 def to_windows_triples(walks, window_size, num_nodes, padding_idx, triples, seed):
     """csrc/rw_init.cpp:103-116 -> (target_triples[K,3], pos_windows[K,2W,3], neg_windows[K,2W,3])."""
-    return _triple_windows(_lib.trw_windows_triples, walks, window_size, num_nodes, padding_idx, triples, seed, False)
+    return _triple_windows(_lib.trw_windows_triples_ws, walks, window_size, num_nodes, padding_idx, triples, seed, False)
 
 
 def to_windows_triples_cbow(walks, window_size, num_nodes, padding_idx, triples, seed):
     """csrc/rw_init.cpp:118-131 -> (pos_triples[K,3], neg_triples[K,3], pos_windows[K,2W,3])."""
-    return _triple_windows(_lib.trw_windows_triples_cbow, walks, window_size, num_nodes, padding_idx, triples, seed, True)
+    return _triple_windows(_lib.trw_windows_triples_cbow_ws, walks, window_size, num_nodes, padding_idx, triples, seed, True)
 
 
 def _host_int64(t, name):
