@@ -75,6 +75,13 @@ def _worker(rank, world, port, ret):
         gid = torch.arange(offset, offset + local.numel())
         fake = torch.stack((local, gid * 7 + 1, gid * gid), 1)
         full = trw_dist.gather_walks(fake, targets.numel())
+        # the same through a block-cyclic split (blocks of two walks dealt round-robin)
+        local_bc, (off, blk, stride) = trw_dist.shard_targets_block_cyclic(targets, block=2)
+        i = torch.arange(local_bc.numel())
+        gid_bc = off + (i // blk) * stride + i % blk
+        fake_bc = torch.stack((local_bc, gid_bc * 7 + 1, gid_bc * gid_bc), 1)
+        full_bc = trw_dist.gather_walks_block_cyclic(fake_bc, targets.numel(), block=2)
+        assert torch.equal(full_bc, full)
         ret[rank] = (row_ptr.tolist(), col_idx.tolist(), offset, full.tolist())
     finally:
         dist.destroy_process_group()

@@ -105,6 +105,24 @@ def gather_walks(local_walks: torch.Tensor, n_total: int, group=None):
     return torch.cat([out[r * pad: r * pad + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
 
 
+def gather_walks_block_cyclic(local_walks: torch.Tensor, n_total: int, block: int = DEFAULT_BLOCK, group=None):
+    """All-gather the shards of a block-cyclic split (shard_targets_block_cyclic) back into the caller's order:
+    [n_total, row_len] on every rank."""
+    world = dist.get_world_size(group)
+    row_len = local_walks.size(1)
+    counts = [block_cyclic_count(n_total, r, world, block) for r in range(world)]
+    pad = max(counts) if counts else 0
+    buf = local_walks
+    if buf.size(0) != pad:  # equalise shard sizes for all_gather_into_tensor
+        buf = torch.cat((buf, buf.new_zeros((pad - buf.size(0), row_len))))
+    flat = torch.empty((world * pad, row_len), dtype=local_walks.dtype, device=local_walks.device)
+    dist.all_gather_into_tensor(flat, buf.contiguous(), group=group)
+    out = torch.empty((n_total, row_len), dtype=local_walks.dtype, device=local_walks.device)
+    for r in range(world):
+        out[block_cyclic_indices(n_total, r, world, block, device=local_walks.device)] = flat[r * pad: r * pad + counts[r]]
+    return out
+
+
 def walk_sharded(row_ptr, col_idx, target_nodes, p, q, walk_length, seed, gather=False):
     """rw.walk over all ranks: every rank holds the (replicated) CSR and the full target list,
     walks its contiguous shard with global walk ids, and optionally gathers the result."""
@@ -147,6 +165,12 @@ class ReplicatedCsr:
         """Walks this rank's shard of `target_nodes` (the full list, identical on every rank)."""
         local, off, blocks, _ = self.shard(target_nodes, layout, block)
         return self.graph.walk(local, p, q, walk_length, seed, walk_id_offset=off, walk_id_blocks=blocks, out=out)
+
+    def gather(self, local_walks, n_total, layout="block_cyclic", block=DEFAULT_BLOCK):
+        """The ranks' shards of one `walk` call back in the caller's order, on every rank."""
+        if layout == "contiguous":
+            return gather_walks(local_walks, n_total, group=self.group)
+        return gather_walks_block_cyclic(local_walks, n_total, block, group=self.group)
 
     def walk_local_to_host(self, local_targets_host, p, q, walk_length, seed, walk_id_offset, walk_id_blocks=None, out=None):
         """The rank's shard for start nodes and walks in HOST memory (native.PreparedCsr.walk_to_host)."""
