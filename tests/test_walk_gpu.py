@@ -325,7 +325,7 @@ def _clustered_csr(seed, n, communities, avg_deg):
     return torch.from_numpy(np.cumsum(row_ptr)), torch.from_numpy(dst.astype(np.int64))
 
 
-@pytest.mark.parametrize("kind", ["rmat", "clustered", "directed", "duplicates", "out_of_graph_ids"])
+@pytest.mark.parametrize("kind", ["rmat", "clustered", "directed", "duplicates", "out_of_graph_ids", "self_loops"])
 def test_triangle_blooms_and_edge_filter_do_not_change_a_walk(native, kind):
     """A kept graph carries triangle Blooms in its edge records and an L2-resident edge filter
     (member_table.cuh).  Both are one-sided short cuts in front of the membership table: whatever the
@@ -346,6 +346,17 @@ def test_triangle_blooms_and_edge_filter_do_not_change_a_walk(native, kind):
             if rp_np[v + 1] - rp_np[v] >= 2:
                 ci_np[rp_np[v] + 1] = ci_np[rp_np[v]]
         rp, ci = cuda(rp, T(ci_np))
+    elif kind == "self_loops":
+        # a symmetric graph in which every third node also lists itself (a self-loop is its own mirror entry)
+        n_ = 5000
+        rng = np.random.default_rng(8)
+        src, dst = rng.integers(0, n_, 60000), rng.integers(0, n_, 60000)
+        loops = np.arange(0, n_, 3)
+        src, dst = np.r_[src, dst, loops], np.r_[dst, src, loops]
+        key = np.unique(src.astype(np.int64) * n_ + dst)
+        rp_np = np.zeros(n_ + 1, dtype=np.int64)
+        np.add.at(rp_np, key // n_ + 1, 1)
+        rp, ci = cuda(T(np.cumsum(rp_np)), T(key % n_))
     else:
         rp, ci = rmat.rmat_csr(14, 16, device="cuda", seed=4)
         ci = ci.clone()
@@ -364,7 +375,7 @@ def test_triangle_blooms_and_edge_filter_do_not_change_a_walk(native, kind):
             for (p_, q_), b in zip(laws, base):
                 assert torch.equal(g.walk(nodes, p_, q_, 40, 3), b), (kind, cap, filter_mb, p_, q_)
             if cap == 256 and filter_mb == 64:
-                assert g.symmetric == (kind in ("rmat", "clustered"))
+                assert g.symmetric == (kind in ("rmat", "clustered", "self_loops"))
             del g
     finally:
         native.set_option("edge_bloom_cap", 256)
