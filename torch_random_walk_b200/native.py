@@ -306,6 +306,11 @@ def csr_checksum(row_ptr, column_idx):
     """64-bit content checksum of a CSR graph on its device (trw_csr_checksum; one streaming pass, then a
     host wait for 8 bytes).  Equal sizes and checksums identify the graph a kept preparation belongs to."""
     dev = row_ptr.device
+    with _checksum_lock:  # the result cells are shared by the callers of a device: one checksum at a time
+        return _csr_checksum_locked(row_ptr, column_idx, dev)
+
+
+def _csr_checksum_locked(row_ptr, column_idx, dev):
     bufs = _checksum_bufs.get(dev.index)
     if bufs is None:
         bufs = (torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64).pin_memory(), torch.cuda.Event())
@@ -340,6 +345,7 @@ _graph_cache = {}   # device index -> dict(key=(n_nodes, nnz, checksum), graph=P
 _seen_once = {}     # device index -> key of the last one-shot graph (a second call with it prepares the graph for keeps)
 _no_room = {}       # device index -> key whose preparation ran out of memory (not retried)
 _checksum_bufs = {}
+_checksum_lock = threading.Lock()
 _cache_lock = threading.RLock()
 _graph_cache_on = os.environ.get("TRW_GRAPH_CACHE", "1") != "0"
 _BLOOM_AFTER_HITS = int(os.environ.get("TRW_BLOOM_AFTER_HITS", "2"))
