@@ -834,6 +834,66 @@ def test_guard_bands_around_outputs_and_workspace(native):
             native.set_option("records", -1)
 
 
+def test_guard_bands_around_a_kept_graph(native):
+    """The same for a kept graph called through the C ABI: the workspace of trw_csr_graph_prepare_ex (table, edge
+    records with their triangle Blooms, edge filter, work lists, flag cells), the walk output in contiguous and
+    block-cyclic numbering, the fused window outputs and the checksum cell sit between sentinel bands."""
+    import ctypes
+
+    from torch_random_walk_b200 import rmat
+
+    lib = native.lib()
+    rp, ci = rmat.rmat_csr(14, 16, device="cuda", seed=10)
+    n, nnz = rp.numel() - 1, ci.numel()
+    nodes = torch.arange(n - 3, device="cuda")
+    nw, L, guard = nodes.numel(), 23, 4096
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sentinel = -0x0123456789ABCDEF
+
+    def banded(words):
+        t = torch.full((guard + words + guard,), sentinel, dtype=torch.int64, device="cuda")
+        return t, t.data_ptr() + guard * 8
+
+    def intact(*tensors):
+        torch.cuda.synchronize()
+        return all(bool((t[:guard] == sentinel).all()) and bool((t[-guard:] == sentinel).all()) for t in tensors)
+
+    try:
+        for filter_mb in (0, 1):
+            native.set_option("edge_filter_mb", filter_mb)
+            need = lib.trw_csr_graph_workspace_bytes(n, nnz)
+            ws, ws_ptr = banded((need + 7) // 8)
+            assert ws_ptr % 256 == 0
+            handle = ctypes.c_void_p()
+            rc = lib.trw_csr_graph_prepare_ex(ctypes.c_void_p(rp.data_ptr()), ctypes.c_void_p(ci.data_ptr()), n, nnz,
+                                              ctypes.c_void_p(ws_ptr), need, 0, st, 8, ctypes.byref(handle))
+            assert rc == 0, lib.trw_last_error()
+            assert lib.trw_csr_graph_add_blooms(handle, None, None, 64, st) == 0  # already there at cap 8: a no-op
+            for p_, q_ in ((1.0, 0.5), (0.5, 2.0), (0.25, 0.5), (1.0, 1.0)):
+                out, out_ptr = banded(nw * (L + 1))
+                for ids in ((0, 0, 0), (128, 128, 512)):
+                    rc = lib.trw_walk_csr_prepared_at(handle, ctypes.c_void_p(rp.data_ptr()), ctypes.c_void_p(ci.data_ptr()),
+                                                      ctypes.c_void_p(nodes.data_ptr()), nw, ids[0], ids[1], ids[2], p_, q_, L, 5,
+                                                      ctypes.c_void_p(out_ptr), L + 1, st)
+                    assert rc == 0, lib.trw_last_error()
+                    assert intact(ws, out), (filter_mb, p_, q_, ids)
+                    if ids == (0, 0, 0):
+                        walks = out[guard:guard + nw * (L + 1)].view(nw, L + 1)
+                        assert torch.equal(walks, native.walk(rp, ci, nodes, p_, q_, L, 5, cache=False))
+            tgt, tgt_ptr = banded(nw * (L - 3))
+            pos, pos_ptr = banded(nw * (L - 3) * 4)
+            rc = lib.trw_walk_csr_prepared_windows5(handle, ctypes.c_void_p(nodes.data_ptr()), nw, 0, 1.0, 0.5, L, 5,
+                                                    ctypes.c_void_p(tgt_ptr), ctypes.c_void_p(pos_ptr), st)
+            assert rc == 0, lib.trw_last_error()
+            assert intact(ws, tgt, pos)
+            cell, cell_ptr = banded(1)
+            assert lib.trw_csr_checksum(ctypes.c_void_p(rp.data_ptr()), ctypes.c_void_p(ci.data_ptr()), n, nnz, ctypes.c_void_p(cell_ptr), 0, st) == 0
+            assert intact(cell) and int(cell[guard]) == native.csr_checksum(rp, ci) - (1 << 64 if native.csr_checksum(rp, ci) >= 1 << 63 else 0)
+            lib.trw_csr_graph_destroy(handle)
+    finally:
+        native.set_option("edge_filter_mb", 0)
+
+
 def test_walk_host_matches_device_path(native):
     rp, ci = random_csr(8, 3000, 20)
     nodes = torch.randint(0, 3000, (10000,))

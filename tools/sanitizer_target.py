@@ -30,9 +30,31 @@ def main():
     big = torch.empty((nodes.numel(), 100), dtype=torch.int64, device="cuda")
     for p, q in laws[:3]:
         native.walk(rp, ci, nodes, p, q, 80, 3, out=big[:, 7:88])  # rows that start off any line boundary
-    g = native.prepare_csr(rp, ci)
+    g = native.prepare_csr(rp, ci)  # edge records + triangle Blooms
     for p, q in laws:
         g.walk(nodes[:1000], p, q, 33, 9, walk_id_offset=12345)
+        g.walk(nodes[:1000], p, q, 33, 9, walk_id_offset=64, walk_id_blocks=(64, 256))  # block-cyclic walk ids
+    g.walk_windows5(nodes[:777], 1.0, 0.5, 17, 9)                      # fused walk -> window prototype
+    g.walk_to_host(nodes[:999].cpu(), 1.0, 0.5, 17, 9)                 # download pipeline
+    native.set_option("n2v_warp", 1)                                   # warp-per-walk A/B kernel
+    g.walk(nodes[:500], 0.5, 2.0, 12, 9)
+    native.set_option("n2v_warp", 0)
+    for cap, mb in ((8, 0), (1 << 20, 1)):                             # Bloom caps, edge filter
+        native.set_option("edge_bloom_cap", cap)
+        native.set_option("edge_filter_mb", mb)
+        g2 = native.prepare_csr(rp, ci)
+        g2.walk(nodes[:1000], 1.0, 0.5, 20, 9)
+        del g2
+    native.set_option("edge_bloom_cap", 256)
+    native.set_option("edge_filter_mb", 0)
+    g32 = native.prepare_csr(rp.int(), ci.int())                       # int32 CSR
+    g32.walk(nodes[:1000], 0.5, 2.0, 20, 9)
+    native.walk(rp.int(), ci.int(), nodes[:1000], 1.0, 0.5, 20, 9)
+    native.csr_checksum(rp, ci[1:])                                    # checksum, unaligned start
+    native.csr_checksum(rp.int(), ci.int())
+    rp_h, ci_h = rp.cpu().pin_memory(), ci.cpu().pin_memory()
+    for _ in range(5):                                                 # host path: fresh upload, kept replica, copy-engine check
+        native.walk_host(rp_h, ci_h, nodes[:3000].cpu(), 1.0, 0.5, 11, 3, device=0)
     # a star: one hub row of 5000 neighbours (hub-segment builder), leaves of degree 1
     m = 5001
     hub_rp = torch.cat((torch.tensor([0, m - 1]), m - 1 + torch.arange(1, m))).cuda()
@@ -62,6 +84,10 @@ def main():
     for W in (1, 3, 5):
         rw.to_windows_triples(tw, W, 200, 207, ts, 1)
         rw.to_windows_triples_cbow(tw, W, 200, 207, ts, 1)
+    native.set_option("win_bulk", 1)                                   # bulk-store stages
+    rw.to_windows_triples(tw, 5, 200, 207, ts, 1)
+    rw.to_windows_triples_cbow(tw, 5, 200, 207, ts, 1)
+    native.set_option("win_bulk", 0)
     # edge-list walks
     el = torch.stack((torch.repeat_interleave(torch.arange(n, device="cuda"), rp[1:] - rp[:-1]), ci), 1).contiguous()
     nei, el = utils.build_node_edge_index(el, torch.arange(n))
