@@ -1,5 +1,10 @@
+"""Two to_windows_triples calls at 0.5 M walks for ncu (profiles/r02_ncu_extract.txt):
+
+    ncu --set full --clock-control none -k regex:windows_kernel -c 1 -o gpurun_out/r2_prof_win python tools/windows_profile_target.py
+"""
 import sys, torch
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torch_random_walk_b200 import native, rmat
 triples = rmat.kg_triples(14541, 237, 310116, device="cuda")
 _, ts = rmat.relation_tail_index(triples, 14541)
