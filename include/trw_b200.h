@@ -130,6 +130,11 @@ int trw_csr_graph_add_blooms(trw_csr_graph* graph, const void* row_ptr, const vo
  * to; the reference, being stateless (csrc/cuda/rw_cuda.cu:186-248), needs no such thing. */
 int trw_csr_checksum(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                      uint64_t* out_device, int device, void* stream);
+/* The same sum over arrays in HOST memory, on n_threads host threads (<= 0: as many as the host path uses); simd = 0
+ * keeps to the scalar loop, otherwise AVX-512 where the CPU has it (same value).  A host caller can compare it with
+ * trw_csr_checksum of a device replica -- what trw_walk_csr_host does on every call to its kept replica. */
+int trw_csr_checksum_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
+                          int n_threads, int simd, uint64_t* out);
 void trw_csr_graph_destroy(trw_csr_graph* graph);
 
 /* ---------------------------------------------------------------------------------------
@@ -162,8 +167,9 @@ int trw_csr_graph_info(const trw_csr_graph* graph, void* stream, int64_t* out, i
  * next ones run.  Allocates its own device memory (kept between calls, grow-only, until
  * trw_release_cached_buffers) and returns after `out` is complete.  This is the end-to-end
  * path a caller holding CPU tensors uses.  A caller that comes back with the same host arrays finds
- * the device replica of the graph kept: the walk starts on it at once while the host threads verify,
- * by checksum, that the arrays still hold what was uploaded (a mismatch uploads afresh and walks again). */
+ * the device replica of the graph kept: the walk starts on it at once while the copy engine (re-reading pinned
+ * arrays) and the host threads verify, by checksum, that the arrays still hold what was uploaded (a mismatch uploads
+ * afresh and walks again). */
 int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz,
                       const int64_t* targets, int64_t n_walks, int64_t walk_id_offset,
                       double p, double q, int walk_length, int64_t seed,
@@ -182,6 +188,12 @@ typedef struct trw_csr_graph_view {
 int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_t* targets, int64_t n_walks,
                          int64_t walk_id_offset, int64_t walk_id_block, int64_t walk_id_stride,
                          double p, double q, int walk_length, int64_t seed, int64_t* out);
+
+/* The replica trw_walk_csr_host keeps on `device`: out[0] one is held, out[1] its preparation level (-1 none, 0 one
+ * call's needs, 1 the full kept preparation, 2 with triangle Blooms), out[2] validated hits so far, out[3] how the last
+ * call got its graph (0 no call yet, 1 kept replica validated, 2 fresh upload, 3 kept replica found changed and
+ * uploaded afresh).  n_out >= 4. */
+int trw_host_replica_info(int device, int64_t* out, int n_out);
 
 /* Frees the device buffers, streams and events trw_walk_csr_host keeps between calls. */
 void trw_release_cached_buffers(void);

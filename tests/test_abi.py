@@ -144,3 +144,42 @@ def test_options_belong_to_the_calling_thread():
     finally:
         native.set_option("edge_bloom_cap", default)
     assert lib.trw_set_option(b"no_such_option", ctypes.c_int64(1)) != 0
+
+
+def test_host_checksum_forms_agree():
+    """trw_csr_checksum_host (what the host path compares with its kept device replica): the AVX-512 loop, the scalar
+    loop and a numpy restatement of the definition give one value, for every length around the vector width and any
+    thread count.  Pure host code: no device is touched."""
+    import numpy as np
+
+    from torch_random_walk_b200 import native
+
+    def mix(z):
+        z = z ^ (z >> np.uint64(30))
+        z = z * np.uint64(0xBF58476D1CE4E5B9)
+        z = z ^ (z >> np.uint64(27))
+        z = z * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+    def restated(rp, ci):
+        total = np.uint64(0)
+        with np.errstate(over="ignore"):
+            for arr, golden in ((ci, 0x9E3779B97F4A7C15), (rp, 0xD6E8FEB86659FD93)):
+                pos = np.arange(1, arr.size + 1, dtype=np.uint64) * np.uint64(golden)
+                total = total + mix(arr.astype(np.uint64) + pos).sum(dtype=np.uint64)
+        v = int(total)
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    gen = torch.Generator().manual_seed(5)
+    for nnz in (0, 1, 7, 8, 15, 16, 17, 31, 33, 100, 4099):
+        ci = torch.randint(-5, 1 << 40, (nnz,), generator=gen, dtype=torch.int64)
+        rp = torch.randint(0, 1 << 33, (nnz % 13 + 1,), generator=gen, dtype=torch.int64)
+        want = restated(rp.numpy(), ci.numpy())
+        for threads in (1, 3, 16):
+            assert native.csr_checksum_host(rp, ci, threads=threads, simd=True) == want, (nnz, threads)
+            assert native.csr_checksum_host(rp, ci, threads=threads, simd=False) == want, (nnz, threads)
+    ci = torch.arange(100, dtype=torch.int64)
+    rp = torch.tensor([0, 100])
+    a = native.csr_checksum_host(rp, ci)
+    ci[50], ci[51] = ci[51].item(), ci[50].item()  # position-sensitive: a swap is seen
+    assert native.csr_checksum_host(rp, ci) != a

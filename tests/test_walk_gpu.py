@@ -923,22 +923,27 @@ def test_walk_host_keeps_the_replica_and_notices_changes(native):
     try:
         native.lib().trw_release_cached_buffers()
         native.set_option("host_chunk_walks", 2048)
-        for threads, compress, dma in ((2, 1, 1), (12, 1, 1), (12, 2, 0), (12, 1, 0)):
+        for threads, compress, dma in ((2, 1, 8), (12, 1, 8), (12, 2, 0), (12, 1, 3), (5, 2, 5)):  # dma: eighths summed by the copy engine
             native.set_option("host_threads", threads)
             native.set_option("host_compress", compress)
             native.set_option("host_check_dma", dma)
             for rounds in range(6):  # fresh, full preparation, ..., triangle Blooms, steady
                 for law in laws:
                     assert torch.equal(native.walk_host(rp, ci, nodes, law[0], law[1], 20, 3, device=0), expect[law]), (threads, compress, rounds, law)
+            info = native.host_replica_info(0)  # a content check that failed would show as a fresh upload on every call
+            assert info["held"] and info["level"] == 2 and info["last_call"] == "kept replica validated", (threads, compress, dma, info)
+        assert native.csr_checksum_host(rp, ci) == native.csr_checksum(rp.cuda(), ci.cuda())
         # pageable arrays: kept as well, always summed by the host threads
         rp_p, ci_p = rp.clone(), ci.clone()
         assert not rp_p.is_pinned()
         for rounds in range(4):
             assert torch.equal(native.walk_host(rp_p, ci_p, nodes, 1.0, 0.5, 20, 3, device=0), expect[(1.0, 0.5)])
         ci_p[int(rp[9])] = ci_p[int(rp[9]) + 1]
+        assert native.host_replica_info(0)["last_call"] == "kept replica validated"
         assert torch.equal(native.walk_host(rp_p, ci_p, nodes, 1.0, 0.5, 20, 3, device=0),
                            native.walk(rp_p.cuda(), ci_p.cuda(), nodes.cuda(), 1.0, 0.5, 20, 3, cache=False).cpu())
-        native.set_option("host_check_dma", 1)
+        assert native.host_replica_info(0)["last_call"] == "kept replica found changed"
+        native.set_option("host_check_dma", 4)
         for rounds in range(3):
             assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0), expect[(1.0, 0.5)])
         # change the graph under the same pointers
@@ -947,9 +952,12 @@ def test_walk_host_keeps_the_replica_and_notices_changes(native):
         changed = native.walk(rp.cuda(), ci.cuda(), nodes.cuda(), 1.0, 0.5, 20, 3, cache=False).cpu()
         assert not torch.equal(changed, expect[(1.0, 0.5)])
         assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0), changed)
+        assert native.host_replica_info(0)["last_call"] == "kept replica found changed"
         assert torch.equal(native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0), changed)
+        assert native.host_replica_info(0)["last_call"] == "kept replica validated"
         rp2 = rp.clone().pin_memory()  # same content at another address: a fresh upload, same walks
         assert torch.equal(native.walk_host(rp2, ci, nodes, 1.0, 0.5, 20, 3, device=0), changed)
+        assert native.host_replica_info(0)["last_call"] == "fresh upload"
         with pytest.raises(RuntimeError):
             native.walk_host(rp, ci, nodes, 1.0, 0.5, 20, 3, device=0, out=torch.empty((n, 20), dtype=torch.int64))
     finally:

@@ -30,9 +30,9 @@ struct Options {
                                   // 2 the same with every other chunk of walks copied as plain int64 (copy engine and host cores share the output), 0 plain
     int64_t host_threads = 0;     // host threads of the wire compression (0: the machine's, divided by LOCAL_WORLD_SIZE)
     int64_t host_up_chunk = 1 << 25;  // col_idx entries per compressed upload chunk
-    int64_t host_packed_share = -1; // of every 8 download chunks, how many travel as uint32 (-1: 8 with >= 12 host threads, else 0; host_compress = 2: 4)
-    int64_t host_check_dma = 1;   // 1: the kept replica's content check re-reads pinned host arrays with the copy engine and sums them on the
-                                  // device (pageable arrays are always summed by host threads); 0: host threads
+    int64_t host_packed_share = -1; // of every 8 download chunks, how many travel as uint32 (-1: with >= 12 host threads 8, or 6 while a content check runs, else 0; host_compress = 2: 4)
+    int64_t host_check_dma = 3;   // of the kept replica's content check, how many eighths of col_idx the copy engine re-reads from pinned host
+                                  // arrays and the device sums (0: the host threads sum everything, 8: the copy engine re-reads everything)
     int64_t host_keep_graph = 1;  // 1: trw_walk_csr_host keeps the device replica of the graph between calls (same host arrays, content
                                   // checked by checksum on every call); needs host_cache_buffers
     int64_t host_cache_buffers = 1;  // 1: trw_walk_csr_host keeps its device buffers between calls

@@ -13,10 +13,11 @@
 //     not fit falls back to plain copies;
 //   * the graph does not cross PCIe again when the caller comes back with the same arrays: the device
 //     replica and its preparation are kept per device, keyed by the host pointers and sizes and
-//     VALIDATED BY CONTENT on every call -- the host threads checksum row_ptr and col_idx (the same
-//     64-bit position-sensitive sum the device computed over the replica when it was uploaded,
-//     csr_checksum.cu) while the walk already runs on the kept replica; a mismatch throws that work
-//     away, uploads afresh and walks again.  Like the device-side graph cache the preparation grows
+//     VALIDATED BY CONTENT on every call -- row_ptr and col_idx are summed again (the same 64-bit
+//     position-sensitive sum the device computed over the replica when it was uploaded,
+//     csr_checksum.cu; part by the copy engine re-reading pinned arrays, part by the host threads)
+//     while the walk already runs on the kept replica; a mismatch throws that work away, uploads
+//     afresh and walks again.  Like the device-side graph cache the preparation grows
 //     with use (per-call needs, then the full kept preparation, then the triangle Blooms).
 #include <algorithm>
 #include <atomic>
@@ -40,8 +41,10 @@ namespace trw {
 // Device buffers, streams and events of the host path are kept between calls (per device,
 // grow-only): cudaMalloc/cudaFree of ~15 GB cost more than the walk itself.  Released by
 // trw_release_cached_buffers() or with option host_cache_buffers = 0.
-enum { kBufRowPtr = 0, kBufColIdx, kBufTargets, kBufWorkspace, kBufOut0, kBufOut1, kBufUp0, kBufUp1, kBufDown0, kBufDown1, kBufCheck, kNumBufs };
-enum { kPinUp0 = 0, kPinUp1, kPinDown0, kPinDown1, kNumPinned };
+constexpr int kRing = 3;  // chunks in flight on the way down (walk buffers, packed staging)
+enum { kBufRowPtr = 0, kBufColIdx, kBufTargets, kBufWorkspace, kBufOut0, kBufOut1, kBufOut2, kBufUp0, kBufUp1, kBufDown0, kBufDown1, kBufDown2,
+       kBufCheck, kNumBufs };
+enum { kPinUp0 = 0, kPinUp1, kPinDown0, kPinDown1, kPinDown2, kNumPinned };
 struct HostWalkCache {
     void* ptr[kNumBufs] = {};
     size_t cap[kNumBufs] = {};
@@ -49,6 +52,7 @@ struct HostWalkCache {
     size_t pinned_cap[kNumPinned] = {};
     cudaStream_t compute = nullptr, copy = nullptr, check = nullptr;
     cudaEvent_t walked[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}, uploaded[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> landed;  // download pipeline: one event per chunk (the host waits on them in its own order)
     std::mutex mu;  // one host-path call at a time per device
     // the kept replica: which host arrays it mirrors, its device-side checksum, and what has been prepared on it
     const void* key_row_ptr = nullptr;
@@ -56,6 +60,8 @@ struct HostWalkCache {
     int64_t key_n_nodes = -1, key_nnz = -1;
     uint64_t replica_checksum = 0;
     bool have_replica = false;
+    int last_call = 0;    // how the last call through this cache got its graph: 1 kept replica validated, 2 fresh upload, 3 kept replica
+                          // found changed (then uploaded afresh)
     int level = -1;       // -1 nothing prepared, 0 what one call's (p, q) needed, 1 the full kept preparation, 2 with triangle Blooms
     int hits = 0;
     CsrGraph graph;
@@ -81,6 +87,8 @@ struct HostWalkCache {
             if (uploaded[k]) cudaEventDestroy(uploaded[k]);
             walked[k] = copied[k] = uploaded[k] = nullptr;
         }
+        for (cudaEvent_t e : landed) cudaEventDestroy(e);
+        landed.clear();
         if (compute) cudaStreamDestroy(compute);
         if (copy) cudaStreamDestroy(copy);
         if (check) cudaStreamDestroy(check);
@@ -231,7 +239,7 @@ static inline uint64_t mix64_host(uint64_t z) {
     z ^= z >> 31;
     return z;
 }
-static uint64_t checksum_range(const int64_t* v, int64_t lo, int64_t hi, uint64_t golden) {
+static uint64_t checksum_range_scalar(const int64_t* v, int64_t lo, int64_t hi, uint64_t golden) {
     uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // four independent chains keep the multipliers busy
     int64_t i = lo;
     for (; i + 4 <= hi; i += 4) {
@@ -243,17 +251,37 @@ static uint64_t checksum_range(const int64_t* v, int64_t lo, int64_t hi, uint64_
     for (; i < hi; ++i) a0 += mix64_host((uint64_t)v[i] + golden * (uint64_t)(i + 1));
     return a0 + a1 + a2 + a3;
 }
-static uint64_t host_csr_checksum(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, int n_threads) {
-    std::vector<uint64_t> part((size_t)std::max(n_threads, 1), 0);
-    parallel_for(std::max(n_threads, 1), [&](int tid, int nt) {
-        uint64_t acc = checksum_range(col_idx, nnz * tid / nt, nnz * (tid + 1) / nt, 0x9E3779B97F4A7C15ull);
-        const int64_t n_row = n_nodes + 1;
-        acc += checksum_range(row_ptr, n_row * tid / nt, n_row * (tid + 1) / nt, 0xD6E8FEB86659FD93ull);
-        part[(size_t)tid] = acc;
-    });
-    uint64_t total = 0;
-    for (uint64_t x : part) total += x;
-    return total;
+#if defined(__x86_64__)
+// The scalar loop is bound by its two 64-bit multiplies per entry (6.4 GB/s per core measured on the GPU box, a sixth of
+// what a core streams); AVX-512DQ has the 64-bit low multiply, eight entries at a time.  Same sum: all arithmetic is mod 2^64.
+__attribute__((target("avx512f,avx512dq"))) static uint64_t checksum_range_avx512(const int64_t* v, int64_t lo, int64_t hi, uint64_t golden) {
+    const __m512i c1 = _mm512_set1_epi64((long long)0xBF58476D1CE4E5B9ull), c2 = _mm512_set1_epi64((long long)0x94D049BB133111EBull);
+    const __m512i g = _mm512_set1_epi64((long long)golden), step = _mm512_set1_epi64((long long)(golden * 16u));
+    __m512i pos0 = _mm512_mullo_epi64(_mm512_add_epi64(_mm512_set1_epi64(lo + 1), _mm512_setr_epi64(0, 1, 2, 3, 4, 5, 6, 7)), g);  // golden * (i + 1 + lane)
+    __m512i pos1 = _mm512_add_epi64(pos0, _mm512_set1_epi64((long long)(golden * 8u)));
+    __m512i a0 = _mm512_setzero_si512(), a1 = _mm512_setzero_si512();
+    int64_t i = lo;
+    for (; i + 16 <= hi; i += 16) {
+        __m512i z0 = _mm512_add_epi64(_mm512_loadu_si512(v + i), pos0);
+        __m512i z1 = _mm512_add_epi64(_mm512_loadu_si512(v + i + 8), pos1);
+        z0 = _mm512_mullo_epi64(_mm512_xor_si512(z0, _mm512_srli_epi64(z0, 30)), c1);
+        z1 = _mm512_mullo_epi64(_mm512_xor_si512(z1, _mm512_srli_epi64(z1, 30)), c1);
+        z0 = _mm512_mullo_epi64(_mm512_xor_si512(z0, _mm512_srli_epi64(z0, 27)), c2);
+        z1 = _mm512_mullo_epi64(_mm512_xor_si512(z1, _mm512_srli_epi64(z1, 27)), c2);
+        a0 = _mm512_add_epi64(a0, _mm512_xor_si512(z0, _mm512_srli_epi64(z0, 31)));
+        a1 = _mm512_add_epi64(a1, _mm512_xor_si512(z1, _mm512_srli_epi64(z1, 31)));
+        pos0 = _mm512_add_epi64(pos0, step);
+        pos1 = _mm512_add_epi64(pos1, step);
+    }
+    return (uint64_t)_mm512_reduce_add_epi64(_mm512_add_epi64(a0, a1)) + checksum_range_scalar(v, i, hi, golden);
+}
+#endif
+static uint64_t checksum_range(const int64_t* v, int64_t lo, int64_t hi, uint64_t golden, bool simd = true) {
+#if defined(__x86_64__)
+    static const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq");
+    if (simd && avx512) return checksum_range_avx512(v, lo, hi, golden);
+#endif
+    return checksum_range_scalar(v, lo, hi, golden);
 }
 
 constexpr int kRetryPlain = 1;  // host_pipeline: a walk entry did not fit the uint32 wire format
@@ -270,7 +298,8 @@ static bool host_pinned(const void* p) {
 // piece, through a side buffer on a stream of its own (the upload direction of PCIe is idle while walks come down), and
 // each piece is summed on the device as it lands.  The sum ends up in pinned cell `pinned[kPinUp0][1]`.
 constexpr int64_t kCheckPieceBytes = (int64_t)256 << 20;
-static int enqueue_dma_checksum(HostWalkCache& r, int d, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz) {
+static int enqueue_dma_checksum(HostWalkCache& r, int d, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t col_hi,
+                                bool with_row_ptr) {
     int rc = r.reserve(kBufCheck, (size_t)kCheckPieceBytes + 256, "cudaMalloc check buffer");
     if (!rc) rc = r.reserve_pinned(kPinUp0, 256, "cudaHostAlloc checksum cell");
     if (rc) return rc;
@@ -278,9 +307,9 @@ static int enqueue_dma_checksum(HostWalkCache& r, int d, const int64_t* row_ptr,
     uint64_t* d_sum = (uint64_t*)(side + kCheckPieceBytes);
     TRW_TRY(cudaMemsetAsync(d_sum, 0, sizeof(uint64_t), r.check), "check sum memset");
     const int64_t piece = kCheckPieceBytes / 8;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < (with_row_ptr ? 2 : 1); ++pass) {  // col_idx[0, col_hi), then row_ptr
         const int64_t* src = pass == 0 ? col_idx : row_ptr;
-        const int64_t n = pass == 0 ? nnz : n_nodes + 1;
+        const int64_t n = pass == 0 ? col_hi : n_nodes + 1;
         for (int64_t done = 0; done < n; done += piece) {
             const int64_t m = std::min(piece, n - done);
             TRW_TRY(cudaMemcpyAsync(side, src + done, (size_t)m * 8, cudaMemcpyHostToDevice, r.check), "H2D check piece");
@@ -297,88 +326,236 @@ struct HostCallShape {
     int walk_length;
 };
 
-// Walks `shape.n_walks` start nodes (already on the device) in chunks and streams the chunks into host memory.
-// `mode` of every 8 chunks are narrowed on the device, copied as uint32 and widened by `n_threads` host threads while the
-// next chunk is in flight; the others are int64 rows copied straight into `out` -- 0: plain copies, 8: everything packed,
-// in between the copy engine and the host cores each carry part of the output.  Waits for everything before it returns.
+// ---- the host's share of one call ----------------------------------------------------------------------------------
+// Two kinds of work want the host's cores while the chunks of a call are in flight: widening packed chunks that have
+// landed (urgent: their staging is wanted again) and summing the part of the host CSR that the copy engine does not
+// re-read for the content check.  One team of threads serves both, widening first, so neither kind waits for threads the
+// other kind holds idle.  The calling thread runs the pipeline and lends a hand with widening whenever it has to wait.
+constexpr int64_t kWidenPiece = (int64_t)1 << 18;  // elements per piece: 1 MB of staging in, 2 MB out
+constexpr int64_t kSumPiece = (int64_t)1 << 22;    // entries per piece: 32 MB
+
+struct HostSum {  // entries [lo, hi) of an array of the host CSR, summed as csr_checksum_part sums its replica
+    const int64_t* v;
+    int64_t lo, hi;
+    uint64_t golden;
+};
+struct WidenJob {
+    const uint32_t* src = nullptr;
+    int64_t* dst = nullptr;
+    int64_t n = 0, pieces = 0;
+    std::atomic<int64_t> next{0}, done{0};
+    bool finished() const { return done.load(std::memory_order_acquire) >= pieces; }
+};
+
+class HostTeam {
+  public:
+    HostTeam(int n_threads, int n_jobs, const HostSum* sums, int n_sums) : jobs_((size_t)std::max(n_jobs, 0)) {
+        for (int k = 0; k < n_sums; ++k)
+            for (int64_t lo = sums[k].lo; lo < sums[k].hi; lo += kSumPiece)
+                sum_pieces_.push_back(HostSum{sums[k].v, lo, std::min(lo + kSumPiece, sums[k].hi), sums[k].golden});
+        if (jobs_.empty() && sum_pieces_.empty()) return;
+        try {
+            for (int t = 0; t < n_threads; ++t) workers_.emplace_back([this] { run(); });
+        } catch (...) {
+            // the system refused a thread: the calling thread works through what the others leave (drain())
+        }
+    }
+    ~HostTeam() {
+        abort_.store(true, std::memory_order_release);
+        join();
+    }
+    WidenJob& job(int j) { return jobs_[(size_t)j]; }
+    int n_jobs() const { return (int)jobs_.size(); }
+    // jobs [0, n) have landed in their staging (set up before the call; published in order)
+    void publish(int n) { published_.store(n, std::memory_order_release); }
+    // One piece of widening on the calling thread, if any is to be had.
+    bool help_widen() { return widen_once(caller_first_); }
+    // Everything published is finished and every sum piece taken and summed; returns the sum.  The caller works along.
+    uint64_t drain() {
+        publish(n_jobs());
+        for (;;) {
+            if (widen_once(caller_first_) || sum_once(total_caller_)) continue;
+            bool all = sums_done_.load(std::memory_order_acquire) >= (int64_t)sum_pieces_.size();
+            for (size_t j = 0; all && j < jobs_.size(); ++j) all = jobs_[j].finished();
+            if (all) break;
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        join();
+        return total_.load(std::memory_order_acquire) + total_caller_;
+    }
+
+  private:
+    bool widen_once(int& first) {
+        const int pub = published_.load(std::memory_order_acquire);
+        for (int j = first; j < pub; ++j) {
+            WidenJob& w = jobs_[(size_t)j];
+            const int64_t pc = w.next.load(std::memory_order_relaxed) < w.pieces ? w.next.fetch_add(1, std::memory_order_relaxed) : w.pieces;
+            if (pc >= w.pieces) {
+                if (j == first) ++first;
+                continue;
+            }
+            const int64_t lo = pc * kWidenPiece;
+            widen_to_i64(w.src + lo, w.dst + lo, std::min(kWidenPiece, w.n - lo));
+            w.done.fetch_add(1, std::memory_order_release);
+            return true;
+        }
+        return false;
+    }
+    bool sum_once(uint64_t& acc) {
+        const int64_t n = (int64_t)sum_pieces_.size();
+        if (sum_next_.load(std::memory_order_relaxed) >= n) return false;
+        const int64_t pc = sum_next_.fetch_add(1, std::memory_order_relaxed);
+        if (pc >= n) return false;
+        const HostSum& s = sum_pieces_[(size_t)pc];
+        acc += checksum_range(s.v, s.lo, s.hi, s.golden);
+        sums_done_.fetch_add(1, std::memory_order_release);
+        return true;
+    }
+    void run() {
+        uint64_t acc = 0;
+        int first = 0;
+        while (!abort_.load(std::memory_order_acquire)) {
+            if (widen_once(first) || sum_once(acc)) continue;
+            if (first >= n_jobs() && sum_next_.load(std::memory_order_relaxed) >= (int64_t)sum_pieces_.size()) break;  // nothing left to take
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        total_.fetch_add(acc, std::memory_order_acq_rel);
+    }
+    void join() {
+        for (auto& w : workers_)
+            if (w.joinable()) w.join();
+    }
+    std::vector<WidenJob> jobs_;
+    std::vector<HostSum> sum_pieces_;
+    std::vector<std::thread> workers_;
+    std::atomic<int> published_{0};
+    std::atomic<int64_t> sum_next_{0}, sums_done_{0};
+    std::atomic<uint64_t> total_{0};
+    std::atomic<bool> abort_{false};
+    uint64_t total_caller_ = 0;
+    int caller_first_ = 0;
+};
+
+// Walks `shape.n_walks` start nodes (already on the device) in chunks and streams the chunks into host memory, up to
+// kRing of them in flight.  `mode` of every 8 chunks are narrowed on the device, copied as uint32 into pinned staging and
+// widened into `out` by the host team; the others are int64 rows copied straight into `out` -- 0: plain copies, 8:
+// everything packed, in between the copy engine and the host cores each carry part of the output.  The team also sums
+// `sums` (parts of the host CSR, for the kept replica's content check) into *host_sum.  Waits for everything before it
+// returns.
 static int host_pipeline(HostWalkCache& r, int d, const CsrWalkPlan& plan, const int64_t* d_targets, const HostCallShape& sh,
-                         int64_t* out, int mode, int n_threads) {
+                         int64_t* out, int mode, int n_threads, const HostSum* sums = nullptr, int n_sums = 0,
+                         uint64_t* host_sum = nullptr) {
     const int64_t row_len = (int64_t)sh.walk_length + 1;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(options().host_chunk_walks, sh.n_walks));
     if (sh.id_block > 0 && chunk % sh.id_block != 0 && sh.n_walks > chunk) {
         set_error("host walk: host_chunk_walks must be a multiple of the walk-id block (%lld)", (long long)sh.id_block);
         return TRW_ERR_ARG;
     }
-    const int n_buf = sh.n_walks > chunk ? 2 : 1;
+    const int n_chunks = (int)((sh.n_walks + chunk - 1) / chunk);
+    const int n_buf = std::min(n_chunks, kRing);
+    auto is_packed = [mode](int c) { return ((c + 1) * mode) / 8 != (c * mode) / 8; };  // `mode` of every 8 chunks, evenly spread
+    std::vector<int> job_of_chunk((size_t)n_chunks, -1), chunk_of_job;
+    for (int c = 0; c < n_chunks; ++c)
+        if (is_packed(c)) { job_of_chunk[(size_t)c] = (int)chunk_of_job.size(); chunk_of_job.push_back(c); }
+    const int n_jobs = (int)chunk_of_job.size();
     int rc = TRW_OK;
     for (int k = 0; k < n_buf && !rc; ++k) rc = r.reserve(kBufOut0 + k, (size_t)chunk * row_len * 8, "cudaMalloc walks");
-    if (mode != 0) {
-        const size_t down_bytes = (size_t)chunk * row_len * 4;
-        for (int k = 0; k < n_buf && !rc; ++k) {
-            rc = r.reserve(kBufDown0 + k, down_bytes + 256, "cudaMalloc download staging");
-            if (!rc) rc = r.reserve_pinned(kPinDown0 + k, down_bytes, "cudaHostAlloc download staging");
-        }
+    const size_t down_bytes = (size_t)chunk * row_len * 4;
+    for (int k = 0; k < std::min(n_jobs, kRing) && !rc; ++k) {
+        rc = r.reserve(kBufDown0 + k, down_bytes + 256, "cudaMalloc download staging");
+        if (!rc) rc = r.reserve_pinned(kPinDown0 + k, down_bytes, "cudaHostAlloc download staging");
     }
     if (rc) return rc;
-    void* const d_out[2] = {r.ptr[kBufOut0], r.ptr[kBufOut1]};
-    int* d_overflow = mode != 0 ? (int*)((char*)r.ptr[kBufDown0] + (size_t)chunk * row_len * 4) : nullptr;  // the 256 spare bytes
-    if (mode != 0) TRW_TRY(cudaMemsetAsync(d_overflow, 0, sizeof(int), r.compute), "overflow flag memset");
-    // widen a chunk that has landed in pinned staging into the caller's buffer with the host threads
-    auto widen_to_caller = [&](int b, int64_t first_walk, int64_t m) {
-        const uint32_t* stage = (const uint32_t*)r.pinned[kPinDown0 + b];
-        int64_t* dst = out + first_walk * row_len;
-        const int64_t n_el = m * row_len;
-        parallel_for(n_threads, [&](int tid, int nt) {
-            const int64_t lo = n_el * tid / nt, hi = n_el * (tid + 1) / nt;
-            widen_to_i64(stage + lo, dst + lo, hi - lo);
-        });
-    };
-    int64_t done = 0, prev_first = 0, prev_m = 0;
-    int prev_b = -1;  // a compressed chunk whose widening is still owed
-    for (int c = 0; done < sh.n_walks; ++c) {
-        const int b = c & 1;
-        const int64_t m = std::min(chunk, sh.n_walks - done);
-        const bool packed = ((c + 1) * mode) / 8 != (c * mode) / 8;  // `mode` of every 8 chunks, evenly spread
-        if (c >= 2) TRW_TRY(cudaStreamWaitEvent(r.compute, r.copied[b], 0), "wait copied");
+    while ((int)r.landed.size() < n_chunks) {
+        cudaEvent_t e;
+        TRW_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create");
+        r.landed.push_back(e);
+    }
+    int* d_overflow = n_jobs ? (int*)((char*)r.ptr[kBufDown0] + down_bytes) : nullptr;  // the 256 spare bytes
+    if (n_jobs) TRW_TRY(cudaMemsetAsync(d_overflow, 0, sizeof(int), r.compute), "overflow flag memset");
+
+    HostTeam team(n_threads, n_jobs, sums, n_sums);
+    for (int j = 0; j < n_jobs; ++j) {
+        const int64_t first = (int64_t)chunk_of_job[(size_t)j] * chunk, m = std::min(chunk, sh.n_walks - first);
+        WidenJob& w = team.job(j);
+        w.src = (const uint32_t*)r.pinned[kPinDown0 + j % kRing];
+        w.dst = out + first * row_len;
+        w.n = m * row_len;
+        w.pieces = (w.n + kWidenPiece - 1) / kWidenPiece;
+    }
+    auto enqueue = [&](int c) -> int {
+        const int b = c % kRing;
+        const int64_t done = (int64_t)c * chunk, m = std::min(chunk, sh.n_walks - done);
+        const int j = job_of_chunk[(size_t)c];
+        if (c >= kRing) TRW_TRY(cudaStreamWaitEvent(r.compute, r.landed[(size_t)(c - kRing)], 0), "wait landed");  // its walk buffer is free
         // ids of this chunk: contiguous shards advance the offset; block-cyclic ones advance it by whole strides
         const int64_t off = sh.id_block > 0 ? sh.walk_id_offset + (done / sh.id_block) * sh.id_stride : sh.walk_id_offset + done;
-        rc = csr_walk_launch(plan, d_targets + done, m, off, (int64_t*)d_out[b], row_len, r.compute, sh.id_block, sh.id_stride);
-        if (rc) return rc;
-        if (packed) {
-            narrow_i64_kernel<<<sm_count(d) * 8, 256, 0, r.compute>>>((const int64_t*)d_out[b], (uint32_t*)r.ptr[kBufDown0 + b],
+        int rc2 = csr_walk_launch(plan, d_targets + done, m, off, (int64_t*)r.ptr[kBufOut0 + b], row_len, r.compute, sh.id_block, sh.id_stride);
+        if (rc2) return rc2;
+        if (j >= 0) {  // (its device staging is free: the job that used it last has been widened, so its copy is long done)
+            narrow_i64_kernel<<<sm_count(d) * 8, 256, 0, r.compute>>>((const int64_t*)r.ptr[kBufOut0 + b], (uint32_t*)r.ptr[kBufDown0 + j % kRing],
                                                                      m * row_len, d_overflow);
             count_launch(1);
         }
-        TRW_TRY(cudaEventRecord(r.walked[b], r.compute), "record walked");
-        TRW_TRY(cudaStreamWaitEvent(r.copy, r.walked[b], 0), "wait walked");
-        if (packed)
-            TRW_TRY(cudaMemcpyAsync(r.pinned[kPinDown0 + b], r.ptr[kBufDown0 + b], (size_t)m * row_len * 4, cudaMemcpyDeviceToHost,
+        TRW_TRY(cudaEventRecord(r.walked[c & 1], r.compute), "record walked");
+        TRW_TRY(cudaStreamWaitEvent(r.copy, r.walked[c & 1], 0), "wait walked");
+        if (j >= 0)
+            TRW_TRY(cudaMemcpyAsync(r.pinned[kPinDown0 + j % kRing], r.ptr[kBufDown0 + j % kRing], (size_t)m * row_len * 4, cudaMemcpyDeviceToHost,
                                     r.copy), "D2H walks (uint32)");
         else
-            TRW_TRY(cudaMemcpyAsync(out + done * row_len, d_out[b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy),
-                    "D2H walks");
-        TRW_TRY(cudaEventRecord(r.copied[b], r.copy), "record copied");
-        if (prev_b >= 0) {  // the previous packed chunk has landed (or lands now): widen it while this one walks and copies
-            TRW_TRY(cudaEventSynchronize(r.copied[prev_b]), "wait previous chunk");
-            widen_to_caller(prev_b, prev_first, prev_m);
-            prev_b = -1;
+            TRW_TRY(cudaMemcpyAsync(out + done * row_len, r.ptr[kBufOut0 + b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy), "D2H walks");
+        TRW_TRY(cudaEventRecord(r.landed[(size_t)c], r.copy), "record landed");
+        return TRW_OK;
+    };
+    // The calling thread keeps the device fed: it enqueues a chunk as soon as its staging is free, and otherwise announces
+    // packed chunks to the team as they land.  It never blocks inside the driver: while it waits it widens.
+    int enq = 0, pub = 0, jobs_enqueued = 0;
+    const bool timing = getenv("TRW_HOST_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    double t_enqueued = 0, t_landed = 0;
+    while (enq < n_chunks || pub < n_jobs) {
+        if (enq < n_chunks) {
+            const int j = job_of_chunk[(size_t)enq];
+            if (j < kRing || team.job(j - kRing).finished()) {
+                rc = enqueue(enq);
+                if (rc) return rc;
+                if (j >= 0) jobs_enqueued = j + 1;
+                if (++enq == n_chunks) t_enqueued = ms_now();
+                continue;
+            }
         }
-        if (packed) { prev_b = b; prev_first = done; prev_m = m; }
-        done += m;
+        if (pub < jobs_enqueued) {
+            const cudaError_t st = cudaEventQuery(r.landed[(size_t)chunk_of_job[(size_t)pub]]);
+            if (st == cudaSuccess) {
+                team.publish(++pub);
+                if (pub == n_jobs) t_landed = ms_now();
+                continue;
+            }
+            if (st != cudaErrorNotReady) return check_cuda(st, "query landed");
+        }
+        if (!team.help_widen()) std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
+    const uint64_t sum = team.drain();  // (every job is published by now)
+    if (host_sum) *host_sum = sum;
+    const double t_drained = ms_now();
     TRW_TRY(cudaStreamSynchronize(r.compute), "sync compute");
     TRW_TRY(cudaStreamSynchronize(r.copy), "sync copy");
-    if (prev_b >= 0) widen_to_caller(prev_b, prev_first, prev_m);
-    if (mode != 0) {
+    if (timing)
+        fprintf(stderr, "[host_pipeline] %d chunks (%d packed), %d host threads, %d sum parts | last chunk enqueued %.1f ms, last packed chunk landed %.1f, "
+                "host work done %.1f, copies done %.1f\n", n_chunks, n_jobs, n_threads, n_sums, t_enqueued, t_landed, t_drained, ms_now());
+    if (n_jobs) {
         int overflow = 0;
         TRW_TRY(cudaMemcpy(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost), "read overflow flag");
         if (overflow) return kRetryPlain;  // an id beyond 32 bits came out of the graph: the caller walks again with plain copies
     }
     return TRW_OK;
 }
+// *host_sum is complete after the first pass whatever its outcome, so a retry carries no sums.
 static int host_pipeline_any(HostWalkCache& r, int d, const CsrWalkPlan& plan, const int64_t* d_targets, const HostCallShape& sh,
-                             int64_t* out, int mode, int n_threads) {
-    int rc = host_pipeline(r, d, plan, d_targets, sh, out, mode, n_threads);
+                             int64_t* out, int mode, int n_threads, const HostSum* sums = nullptr, int n_sums = 0,
+                             uint64_t* host_sum = nullptr) {
+    int rc = host_pipeline(r, d, plan, d_targets, sh, out, mode, n_threads, sums, n_sums, host_sum);
     if (rc == kRetryPlain) rc = host_pipeline(r, d, plan, d_targets, sh, out, 0, n_threads);
     return rc;
 }
@@ -407,13 +584,17 @@ static int ensure_streams(HostWalkCache& r) {
     return TRW_OK;
 }
 
-// Download mode for this call: option host_compress 0 plain, 1 packed (needs the threads), 2 alternating; ids must fit.
-static int download_mode(int n_threads, int64_t n_nodes, bool ids_fit) {
+// Download mode for this call (how many of every 8 chunks travel packed): option host_compress 0 plain, 1 packed (needs
+// the threads), 2 half and half; ids must fit.  `checking`: the kept replica's content check runs beside the download and
+// takes its share of the host's memory bandwidth, which is what bounds the call then -- measured on c3 with 16 threads
+// (profiles/r02_host_path.md): 6 of 8 packed with 3 eighths of the check on the copy engine, 84 ms; all packed 97 ms;
+// plain copies 114-122 ms.
+static int download_mode(int n_threads, int64_t n_nodes, bool ids_fit, bool checking = false) {
     const int64_t want = options().host_compress;
     if (want == 0 || !ids_fit || (uint64_t)n_nodes >= 0xFFFFFFFFull) return 0;
     const int share = (int)options().host_packed_share;  // of 8 chunks, how many travel packed (-1: by thread count)
     if (share >= 0) return share > 8 ? 8 : share;
-    if (n_threads >= kMinCompressThreads) return want == 2 ? 4 : 8;
+    if (n_threads >= kMinCompressThreads) return want == 2 ? 4 : (checking ? 6 : 8);
     return n_threads >= 4 && want == 2 ? 2 : 0;
 }
 
@@ -497,36 +678,39 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         CsrWalkPlan plan;
         rc = csr_walk_plan(&plan, r.graph, p, q, walk_length, seed);
         if (rc) return rc;
-        // The content check runs beside the pipeline.  Pinned arrays: the copy engine re-reads them over the idle upload
-        // direction and the device sums them (no host core involved; option host_check_dma).  Pageable arrays: half of the
-        // host threads sum them while the other half widens.
-        const bool dma_check = options().host_check_dma != 0 && host_pinned(row_ptr) && host_pinned(col_idx);
-        const int check_threads = dma_check ? 0 : std::max(1, n_threads / 2);
-        uint64_t host_sum = 0;
-        std::thread checker;
-        if (dma_check) {
-            rc = enqueue_dma_checksum(r, d, row_ptr, col_idx, n_nodes, nnz);
+        // The content check runs beside the pipeline, shared between the copy engine and the host's cores.  Pinned arrays:
+        // the copy engine re-reads `host_check_dma` eighths of col_idx over the upload direction and the device sums them;
+        // the host team sums the rest between its widening jobs.  Pageable arrays are summed by the team alone.
+        const bool dma_ok = host_pinned(row_ptr) && host_pinned(col_idx);
+        const int64_t dma_share = dma_ok ? std::min<int64_t>(std::max<int64_t>(options().host_check_dma, 0), 8) : 0;
+        const int64_t col_hi = dma_share >= 8 ? nnz : (nnz / 8) * dma_share;  // col_idx[0, col_hi) by the copy engine
+        if (dma_share > 0) {
+            rc = enqueue_dma_checksum(r, d, row_ptr, col_idx, n_nodes, col_hi, dma_share >= 8);
             if (rc) return rc;
-        } else {
-            checker = std::thread([&] { host_sum = host_csr_checksum(row_ptr, col_idx, n_nodes, nnz, check_threads); });
         }
-        // Download format: with the host's cores busy summing, plain copies measured fastest (profiles/r02_host_path.md);
-        // with the check on the copy engine the cores are free to widen packed chunks.  Option host_packed_share overrides.
-        const int mode = (dma_check || options().host_packed_share >= 0) ? download_mode(n_threads, n_nodes, wide_targets.load() == 0) : 0;
-        rc = host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, mode, std::max(1, n_threads - check_threads));
-        if (checker.joinable()) checker.join();  // (the pipeline returns on every path; nothing above can throw)
+        HostSum sums[2];
+        int n_sums = 0;
+        if (col_hi < nnz) sums[n_sums++] = HostSum{col_idx, col_hi, nnz, kChecksumColGolden};
+        if (dma_share < 8) sums[n_sums++] = HostSum{row_ptr, 0, n_nodes + 1, kChecksumRowGolden};
+        const int mode = download_mode(n_threads, n_nodes, wide_targets.load() == 0, /*checking=*/true);
+        uint64_t host_sum = 0;
+        rc = host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, mode, n_threads, sums, n_sums, &host_sum);
         if (rc) return rc;
-        if (dma_check) {
+        if (dma_share > 0) {
             TRW_TRY(cudaStreamSynchronize(r.check), "sync content check");
-            host_sum = ((const uint64_t*)r.pinned[kPinUp0])[1];
+            host_sum += ((const uint64_t*)r.pinned[kPinUp0])[1];
         }
         if (host_sum == r.replica_checksum) {
             if (timing)
                 fprintf(stderr, "[trw_walk_csr_host] kept replica (level %d, hit %d), content check by %s, %d of 8 chunks packed, %d host threads | total %.1f ms\n",
-                        r.level, r.hits, dma_check ? "copy engine + device" : "host threads", mode, n_threads, ms_since(t_hit));
+                        r.level, r.hits, dma_share >= 8 ? "copy engine + device" : dma_share > 0 ? "copy engine and host threads" : "host threads", mode, n_threads, ms_since(t_hit));
+            r.last_call = 1;
             return TRW_OK;
         }
         r.forget_replica();  // the arrays changed under the same pointers: upload afresh and walk again
+        r.last_call = 3;
+    } else {
+        r.last_call = 2;
     }
 
     // ---- fresh upload
@@ -690,4 +874,43 @@ extern "C" void trw_release_cached_buffers(void) {
     }
     if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();
+}
+
+// Host twin of trw_csr_checksum: the same 64-bit sum over arrays in host memory, on `n_threads` threads (<= 0: the
+// host path's thread count).  `simd` = 0 keeps to the scalar loop (what the tests compare the AVX-512 form against).
+extern "C" int trw_csr_checksum_host(const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t nnz, int n_threads, int simd,
+                                     uint64_t* out) {
+    if (n_nodes < 0 || nnz < 0 || !out || (!row_ptr && n_nodes + 1 > 0) || (nnz > 0 && !col_idx)) {
+        set_error("trw_csr_checksum_host: bad argument");
+        return TRW_ERR_ARG;
+    }
+    const int nt = std::max(1, n_threads > 0 ? n_threads : host_thread_count());
+    std::vector<uint64_t> part((size_t)nt, 0);
+    parallel_for(nt, [&](int tid, int n) {
+        const int64_t n_row = n_nodes + 1;
+        part[(size_t)tid] = checksum_range(col_idx, nnz * tid / n, nnz * (tid + 1) / n, kChecksumColGolden, simd != 0) +
+                            checksum_range(row_ptr, n_row * tid / n, n_row * (tid + 1) / n, kChecksumRowGolden, simd != 0);
+    });
+    uint64_t total = 0;
+    for (uint64_t x : part) total += x;
+    *out = total;
+    return TRW_OK;
+}
+
+// The kept replica of trw_walk_csr_host on `device`: out[0] a replica is held, out[1] its preparation level (-1 none, 0
+// one call's needs, 1 the full kept preparation, 2 with triangle Blooms), out[2] validated hits so far, out[3] how the
+// last call got its graph (0 no call yet, 1 kept replica validated, 2 fresh upload, 3 kept replica found changed).
+extern "C" int trw_host_replica_info(int device, int64_t* out, int n_out) {
+    const int d = resolve_device(device);
+    if (d < 0 || d >= 64 || !out || n_out < 4) {
+        set_error("trw_host_replica_info: bad argument");
+        return TRW_ERR_ARG;
+    }
+    HostWalkCache& c = g_host_cache[d];
+    std::lock_guard<std::mutex> lock(c.mu);
+    out[0] = c.have_replica ? 1 : 0;
+    out[1] = c.level;
+    out[2] = c.hits;
+    out[3] = c.last_call;
+    return TRW_OK;
 }

@@ -64,6 +64,8 @@ def _load():
     lib.trw_walk_csr_prepared.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_i64,
                                           _c_ptr]
     lib.trw_walk_csr_prepared_windows5.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int, _c_i64, _c_ptr, _c_ptr, _c_ptr]
+    lib.trw_csr_checksum_host.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_int, _c_int, ctypes.POINTER(ctypes.c_uint64)]
+    lib.trw_host_replica_info.argtypes = [_c_int, ctypes.POINTER(_c_i64), _c_int]
     lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
     lib.trw_csr_graph_destroy.restype = None
     lib.trw_csr_graph_info.argtypes = [_c_ptr, _c_ptr, ctypes.POINTER(_c_i64), _c_int]
@@ -561,6 +563,25 @@ def _host_out(out, n, wl):
             out.size(0) == n and out.size(1) == wl and out.is_contiguous()):
         raise RuntimeError(f"out must be a contiguous int64 CPU tensor of shape ({n}, {wl})")
     return out
+
+
+def csr_checksum_host(row_ptr, column_idx, threads=0, simd=True):
+    """The checksum of csr_checksum for int64 CSR arrays in host memory (trw_csr_checksum_host): what the host path compares
+    with its kept device replica.  `simd=False` keeps to the scalar loop (same value)."""
+    row_ptr, column_idx = _host_int64(row_ptr, "row_ptr"), _host_int64(column_idx, "column_idx")
+    out = ctypes.c_uint64(0)
+    _check(_lib.trw_csr_checksum_host(_ptr(row_ptr), _ptr(column_idx), max(row_ptr.numel() - 1, 0), column_idx.numel(), int(threads),
+                                      1 if simd else 0, ctypes.byref(out)))
+    v = int(out.value)
+    return v - (1 << 64) if v >= (1 << 63) else v  # as csr_checksum reports it (an int64 cell)
+
+
+def host_replica_info(device=0):
+    """What trw_walk_csr_host keeps on `device` (trw_host_replica_info)."""
+    out = (ctypes.c_int64 * 4)()
+    _check(_lib.trw_host_replica_info(int(device), out, 4))
+    return {"held": bool(out[0]), "level": int(out[1]), "hits": int(out[2]),
+            "last_call": {0: "none", 1: "kept replica validated", 2: "fresh upload", 3: "kept replica found changed"}[int(out[3])]}
 
 
 def walk_host(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, device=0, walk_id_offset=0, out=None):
