@@ -919,19 +919,22 @@ def test_walk_host_keeps_the_replica_and_notices_changes(native):
     nodes = torch.arange(n)
     laws = ((1.0, 0.5), (0.5, 2.0), (1.0, 1.0))
     expect = {law: native.walk(rp.cuda(), ci.cuda(), nodes.cuda(), law[0], law[1], 20, 3, cache=False).cpu() for law in laws}
-    saved = {k: native.get_option(k) for k in ("host_threads", "host_compress", "host_chunk_walks", "host_check_dma")}
+    saved = {k: native.get_option(k) for k in ("host_threads", "host_compress", "host_chunk_walks", "host_check_dma", "host_packed_share", "host_sum_piece")}
     try:
         native.lib().trw_release_cached_buffers()
-        native.set_option("host_chunk_walks", 2048)
-        for threads, compress, dma in ((2, 1, 8), (12, 1, 8), (12, 2, 0), (12, 1, 3), (5, 2, 5)):  # dma: eighths summed by the copy engine
+        native.set_option("host_sum_piece", 10007)  # ~25 pieces for the copy engine and the host threads to share
+        native.set_option("host_chunk_walks", 1024)  # eight chunks: the ring of three buffers goes round
+        # dma: eighths of the content check the copy engine may take; share: chunks of 8 that travel packed (-1: adaptive)
+        for threads, compress, dma, share in ((2, 1, 8, -1), (12, 1, 8, -1), (12, 2, 0, -1), (12, 1, 3, 5), (5, 1, 5, 8), (1, 1, 4, -1), (3, 0, 4, -1)):
             native.set_option("host_threads", threads)
             native.set_option("host_compress", compress)
             native.set_option("host_check_dma", dma)
+            native.set_option("host_packed_share", share)
             for rounds in range(6):  # fresh, full preparation, ..., triangle Blooms, steady
                 for law in laws:
                     assert torch.equal(native.walk_host(rp, ci, nodes, law[0], law[1], 20, 3, device=0), expect[law]), (threads, compress, rounds, law)
             info = native.host_replica_info(0)  # a content check that failed would show as a fresh upload on every call
-            assert info["held"] and info["level"] == 2 and info["last_call"] == "kept replica validated", (threads, compress, dma, info)
+            assert info["held"] and info["level"] == 2 and info["last_call"] == "kept replica validated", (threads, compress, dma, share, info)
         assert native.csr_checksum_host(rp, ci) == native.csr_checksum(rp.cuda(), ci.cuda())
         # pageable arrays: kept as well, always summed by the host threads
         rp_p, ci_p = rp.clone(), ci.clone()

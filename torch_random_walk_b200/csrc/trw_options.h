@@ -26,13 +26,14 @@ struct Options {
     int64_t persist_row_ptr = 0;  // 1: L2 access-policy window (persisting) over row_ptr during walk kernels
     int64_t persist_l2_mb = 64;   // persisting-L2 carve-out requested when persist_row_ptr is on
     int64_t host_chunk_walks = 1 << 20;  // walks per pipelined chunk in trw_walk_csr_host
-    int64_t host_compress = 1;    // trw_walk_csr_host wire format when ids fit and >= 12 host threads are free: 1 col_idx up and walks back as uint32,
-                                  // 2 the same with every other chunk of walks copied as plain int64 (copy engine and host cores share the output), 0 plain
+    int64_t host_compress = 1;    // wire format of the host path when ids fit 32 bits: 1 col_idx goes up as uint32 (>= 12 host threads) and walks come back
+                                  // as uint32 for as many chunks as the host threads keep up with (host_packed_share), 2 every other chunk packed, 0 plain int64 copies
     int64_t host_threads = 0;     // host threads of the wire compression (0: the machine's, divided by LOCAL_WORLD_SIZE)
     int64_t host_up_chunk = 1 << 25;  // col_idx entries per compressed upload chunk
-    int64_t host_packed_share = -1; // of every 8 download chunks, how many travel as uint32 (-1: with >= 12 host threads 8, or 6 while a content check runs, else 0; host_compress = 2: 4)
-    int64_t host_check_dma = 3;   // of the kept replica's content check, how many eighths of col_idx the copy engine re-reads from pinned host
-                                  // arrays and the device sums (0: the host threads sum everything, 8: the copy engine re-reads everything)
+    int64_t host_packed_share = -1; // of every 8 download chunks, how many travel as uint32 (-1: decided chunk by chunk by how the host threads keep up)
+    int64_t host_check_dma = 4;   // of the kept replica's content check, up to how many eighths the copy engine may re-read from pinned host arrays
+                                  // (summed on the device; it takes pieces from the front of the list, the host threads from the back; 0: host threads only)
+    int64_t host_sum_piece = 1 << 22;  // entries per piece of the content check's work list (32 MB; tests shrink it to exercise the list on small graphs)
     int64_t host_keep_graph = 1;  // 1: trw_walk_csr_host keeps the device replica of the graph between calls (same host arrays, content
                                   // checked by checksum on every call); needs host_cache_buffers
     int64_t host_cache_buffers = 1;  // 1: trw_walk_csr_host keeps its device buffers between calls
@@ -52,7 +53,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk) TRW_OPT(n2v_warp) TRW_OPT(win_table16) TRW_OPT(host_check_dma)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk) TRW_OPT(n2v_warp) TRW_OPT(win_table16) TRW_OPT(host_check_dma) TRW_OPT(host_sum_piece)
 
 Options& options();
 void count_launch(int n);

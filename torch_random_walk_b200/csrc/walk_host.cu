@@ -294,33 +294,6 @@ static bool host_pinned(const void* p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
-// Content check of pinned host arrays without the host's cores: the copy engine brings the arrays up once more, piece by
-// piece, through a side buffer on a stream of its own (the upload direction of PCIe is idle while walks come down), and
-// each piece is summed on the device as it lands.  The sum ends up in pinned cell `pinned[kPinUp0][1]`.
-constexpr int64_t kCheckPieceBytes = (int64_t)256 << 20;
-static int enqueue_dma_checksum(HostWalkCache& r, int d, const int64_t* row_ptr, const int64_t* col_idx, int64_t n_nodes, int64_t col_hi,
-                                bool with_row_ptr) {
-    int rc = r.reserve(kBufCheck, (size_t)kCheckPieceBytes + 256, "cudaMalloc check buffer");
-    if (!rc) rc = r.reserve_pinned(kPinUp0, 256, "cudaHostAlloc checksum cell");
-    if (rc) return rc;
-    char* side = (char*)r.ptr[kBufCheck];
-    uint64_t* d_sum = (uint64_t*)(side + kCheckPieceBytes);
-    TRW_TRY(cudaMemsetAsync(d_sum, 0, sizeof(uint64_t), r.check), "check sum memset");
-    const int64_t piece = kCheckPieceBytes / 8;
-    for (int pass = 0; pass < (with_row_ptr ? 2 : 1); ++pass) {  // col_idx[0, col_hi), then row_ptr
-        const int64_t* src = pass == 0 ? col_idx : row_ptr;
-        const int64_t n = pass == 0 ? col_hi : n_nodes + 1;
-        for (int64_t done = 0; done < n; done += piece) {
-            const int64_t m = std::min(piece, n - done);
-            TRW_TRY(cudaMemcpyAsync(side, src + done, (size_t)m * 8, cudaMemcpyHostToDevice, r.check), "H2D check piece");
-            rc = csr_checksum_part(IdxPtr((const int64_t*)side), m, done, pass == 0, d_sum, d, r.check);
-            if (rc) return rc;
-        }
-    }
-    TRW_TRY(cudaMemcpyAsync((uint64_t*)r.pinned[kPinUp0] + 1, d_sum, sizeof(uint64_t), cudaMemcpyDeviceToHost, r.check), "D2H check sum");
-    return TRW_OK;
-}
-
 struct HostCallShape {
     int64_t n_walks, walk_id_offset, id_block, id_stride;
     int walk_length;
@@ -328,11 +301,16 @@ struct HostCallShape {
 
 // ---- the host's share of one call ----------------------------------------------------------------------------------
 // Two kinds of work want the host's cores while the chunks of a call are in flight: widening packed chunks that have
-// landed (urgent: their staging is wanted again) and summing the part of the host CSR that the copy engine does not
-// re-read for the content check.  One team of threads serves both, widening first, so neither kind waits for threads the
-// other kind holds idle.  The calling thread runs the pipeline and lends a hand with widening whenever it has to wait.
+// landed and summing the host CSR for the kept replica's content check.  One team of threads serves both.  Neither
+// split is fixed in advance, because what the host can carry differs from box to box and from minute to minute (its
+// memory bandwidth is shared with the DMA traffic and with whatever else runs on the machine):
+//   * the pieces of the checksum sit in one list that the copy engine eats from the front (re-reading pinned arrays over
+//     the upload direction, summed on the device) and the team from the back, until they meet;
+//   * a worker sums before it widens whenever the checksum lags behind the chunks (so the sums end with the download,
+//     not after it), and the pipeline sends a chunk packed only while the team keeps up with the widening (below).
+// The calling thread runs the pipeline and lends a hand with widening whenever it has to wait.
 constexpr int64_t kWidenPiece = (int64_t)1 << 18;  // elements per piece: 1 MB of staging in, 2 MB out
-constexpr int64_t kSumPiece = (int64_t)1 << 22;    // entries per piece: 32 MB
+constexpr int64_t kMaxSumPiece = (int64_t)1 << 22;  // entries per piece of the checksum list: at most 32 MB (option host_sum_piece)
 
 struct HostSum {  // entries [lo, hi) of an array of the host CSR, summed as csr_checksum_part sums its replica
     const int64_t* v;
@@ -349,10 +327,11 @@ struct WidenJob {
 
 class HostTeam {
   public:
-    HostTeam(int n_threads, int n_jobs, const HostSum* sums, int n_sums) : jobs_((size_t)std::max(n_jobs, 0)) {
+    HostTeam(int n_threads, int max_jobs, const HostSum* sums, int n_sums, int64_t sum_piece) : jobs_((size_t)std::max(max_jobs, 0)) {
         for (int k = 0; k < n_sums; ++k)
-            for (int64_t lo = sums[k].lo; lo < sums[k].hi; lo += kSumPiece)
-                sum_pieces_.push_back(HostSum{sums[k].v, lo, std::min(lo + kSumPiece, sums[k].hi), sums[k].golden});
+            for (int64_t lo = sums[k].lo; lo < sums[k].hi; lo += sum_piece)
+                sum_pieces_.push_back(HostSum{sums[k].v, lo, std::min(lo + sum_piece, sums[k].hi), sums[k].golden});
+        back_ = (int64_t)sum_pieces_.size();
         if (jobs_.empty() && sum_pieces_.empty()) return;
         try {
             for (int t = 0; t < n_threads; ++t) workers_.emplace_back([this] { run(); });
@@ -364,19 +343,43 @@ class HostTeam {
         abort_.store(true, std::memory_order_release);
         join();
     }
-    WidenJob& job(int j) { return jobs_[(size_t)j]; }
-    int n_jobs() const { return (int)jobs_.size(); }
-    // jobs [0, n) have landed in their staging (set up before the call; published in order)
-    void publish(int n) { published_.store(n, std::memory_order_release); }
-    // One piece of widening on the calling thread, if any is to be had.
-    bool help_widen() { return widen_once(caller_first_); }
-    // Everything published is finished and every sum piece taken and summed; returns the sum.  The caller works along.
+    // A packed chunk is on its way into `src`: job j = jobs added so far.  Widened once publish() has passed it.
+    int add_job(const uint32_t* src, int64_t* dst, int64_t n) {
+        WidenJob& w = jobs_[(size_t)added_];
+        w.src = src; w.dst = dst; w.n = n;
+        w.pieces = (n + kWidenPiece - 1) / kWidenPiece;
+        return added_++;
+    }
+    int jobs_added() const { return added_; }
+    bool job_finished(int j) const { return j < 0 || jobs_[(size_t)j].finished(); }
+    void publish(int n) { published_.store(n, std::memory_order_release); }  // jobs [0, n) have landed in their staging
+    // landed jobs the team has not finished widening: how far the host is behind
+    int backlog() {
+        const int pub = published_.load(std::memory_order_relaxed);
+        while (caller_done_ < pub && jobs_[(size_t)caller_done_].finished()) ++caller_done_;
+        int n = 0;
+        for (int j = caller_done_; j < pub; ++j) n += jobs_[(size_t)j].finished() ? 0 : 1;
+        return n;
+    }
+    // How far the download has come, in 1/1024: the sums are kept level with it.
+    void set_progress(int64_t done, int64_t total) { progress_.store(total > 0 ? done * 1024 / total : 1024, std::memory_order_relaxed); }
+    // The copy engine's side of the checksum list: the next piece from the front, while it may take one.
+    bool claim_front(HostSum* out, int64_t max_front) {
+        std::lock_guard<std::mutex> lock(mu_);
+        if (front_ >= back_ || front_ >= max_front) return false;
+        *out = sum_pieces_[(size_t)front_++];
+        return true;
+    }
+    bool help_widen() { return widen_once(caller_first_); }  // one piece of widening on the calling thread, if there is any
+    // No more jobs will be added: everything added is widened and every sum piece summed on return (the caller works
+    // along; the copy engine's pieces are the caller's to wait for).  Returns the team's sum.
     uint64_t drain() {
-        publish(n_jobs());
+        final_jobs_.store(added_, std::memory_order_release);
+        publish(added_);
         for (;;) {
             if (widen_once(caller_first_) || sum_once(total_caller_)) continue;
-            bool all = sums_done_.load(std::memory_order_acquire) >= (int64_t)sum_pieces_.size();
-            for (size_t j = 0; all && j < jobs_.size(); ++j) all = jobs_[j].finished();
+            bool all = sums_taken_.load(std::memory_order_acquire) == sums_done_.load(std::memory_order_acquire) && !sums_left();
+            for (int j = 0; all && j < added_; ++j) all = jobs_[(size_t)j].finished();
             if (all) break;
             std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
@@ -385,6 +388,10 @@ class HostTeam {
     }
 
   private:
+    bool sums_left() {
+        std::lock_guard<std::mutex> lock(mu_);
+        return front_ < back_;
+    }
     bool widen_once(int& first) {
         const int pub = published_.load(std::memory_order_acquire);
         for (int j = first; j < pub; ++j) {
@@ -402,21 +409,30 @@ class HostTeam {
         return false;
     }
     bool sum_once(uint64_t& acc) {
-        const int64_t n = (int64_t)sum_pieces_.size();
-        if (sum_next_.load(std::memory_order_relaxed) >= n) return false;
-        const int64_t pc = sum_next_.fetch_add(1, std::memory_order_relaxed);
-        if (pc >= n) return false;
-        const HostSum& s = sum_pieces_[(size_t)pc];
+        HostSum s;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            if (front_ >= back_) return false;
+            s = sum_pieces_[(size_t)--back_];
+            sums_taken_.fetch_add(1, std::memory_order_relaxed);
+        }
         acc += checksum_range(s.v, s.lo, s.hi, s.golden);
         sums_done_.fetch_add(1, std::memory_order_release);
         return true;
+    }
+    bool sums_lag() {  // fewer pieces are gone (either way) than the download's progress asks for
+        if (sum_pieces_.empty()) return false;
+        std::lock_guard<std::mutex> lock(mu_);
+        const int64_t n = (int64_t)sum_pieces_.size(), gone = front_ + (n - back_);
+        return front_ < back_ && gone * 1024 < progress_.load(std::memory_order_relaxed) * n;
     }
     void run() {
         uint64_t acc = 0;
         int first = 0;
         while (!abort_.load(std::memory_order_acquire)) {
+            if (sums_lag() && sum_once(acc)) continue;
             if (widen_once(first) || sum_once(acc)) continue;
-            if (first >= n_jobs() && sum_next_.load(std::memory_order_relaxed) >= (int64_t)sum_pieces_.size()) break;  // nothing left to take
+            if (first >= final_jobs_.load(std::memory_order_acquire)) break;  // every job widened or taken, no sum piece left
             std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
         total_.fetch_add(acc, std::memory_order_acq_rel);
@@ -428,23 +444,33 @@ class HostTeam {
     std::vector<WidenJob> jobs_;
     std::vector<HostSum> sum_pieces_;
     std::vector<std::thread> workers_;
-    std::atomic<int> published_{0};
-    std::atomic<int64_t> sum_next_{0}, sums_done_{0};
+    std::mutex mu_;            // the two ends of the checksum list
+    int64_t front_ = 0, back_ = 0;
+    std::atomic<int> published_{0}, final_jobs_{1 << 30};
+    std::atomic<int64_t> sums_taken_{0}, sums_done_{0}, progress_{0};
     std::atomic<uint64_t> total_{0};
     std::atomic<bool> abort_{false};
     uint64_t total_caller_ = 0;
-    int caller_first_ = 0;
+    int added_ = 0, caller_first_ = 0, caller_done_ = 0;
 };
 
-// Walks `shape.n_walks` start nodes (already on the device) in chunks and streams the chunks into host memory, up to
-// kRing of them in flight.  `mode` of every 8 chunks are narrowed on the device, copied as uint32 into pinned staging and
-// widened into `out` by the host team; the others are int64 rows copied straight into `out` -- 0: plain copies, 8:
-// everything packed, in between the copy engine and the host cores each carry part of the output.  The team also sums
-// `sums` (parts of the host CSR, for the kept replica's content check) into *host_sum.  Waits for everything before it
-// returns.
+// What the kept replica's content check asks of a pipeline run: the arrays to sum and who may sum them.
+struct ContentCheck {
+    HostSum sums[2];
+    int n_sums = 0;
+    int dma_eighths = 0;  // the copy engine may take up to this many eighths of the pieces (0: the arrays are pageable, or option host_check_dma = 0)
+    uint64_t sum = 0;     // out: the checksum of the host arrays
+};
+
+// Walks `shape.n_walks` start nodes (already on the device) in chunks and streams the chunks into host memory, two
+// copies queued at a time.  A packed chunk is narrowed on the device, copied as uint32 into pinned staging and widened into
+// `out` by the host team; a plain chunk is int64 rows copied straight into `out`.  `mode` 0..8: that many of every 8
+// chunks packed (0 plain copies, 8 everything packed).  `mode` < 0: decided chunk by chunk -- packed while the team keeps
+// up (at most one landed chunk still being widened), plain otherwise, so the copy engine and the host's cores each carry
+// what they can.  With `check`, the team and the copy engine also sum the host CSR (ContentCheck).  Waits for everything
+// before it returns.
 static int host_pipeline(HostWalkCache& r, int d, const CsrWalkPlan& plan, const int64_t* d_targets, const HostCallShape& sh,
-                         int64_t* out, int mode, int n_threads, const HostSum* sums = nullptr, int n_sums = 0,
-                         uint64_t* host_sum = nullptr) {
+                         int64_t* out, int mode, int n_threads, ContentCheck* check = nullptr) {
     const int64_t row_len = (int64_t)sh.walk_length + 1;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(options().host_chunk_walks, sh.n_walks));
     if (sh.id_block > 0 && chunk % sh.id_block != 0 && sh.n_walks > chunk) {
@@ -453,53 +479,78 @@ static int host_pipeline(HostWalkCache& r, int d, const CsrWalkPlan& plan, const
     }
     const int n_chunks = (int)((sh.n_walks + chunk - 1) / chunk);
     const int n_buf = std::min(n_chunks, kRing);
-    auto is_packed = [mode](int c) { return ((c + 1) * mode) / 8 != (c * mode) / 8; };  // `mode` of every 8 chunks, evenly spread
-    std::vector<int> job_of_chunk((size_t)n_chunks, -1), chunk_of_job;
-    for (int c = 0; c < n_chunks; ++c)
-        if (is_packed(c)) { job_of_chunk[(size_t)c] = (int)chunk_of_job.size(); chunk_of_job.push_back(c); }
-    const int n_jobs = (int)chunk_of_job.size();
+    const bool adaptive = mode < 0;
+    auto packed_by_pattern = [mode](int c) { return ((c + 1) * mode) / 8 != (c * mode) / 8; };  // `mode` of every 8 chunks, evenly spread
     int rc = TRW_OK;
     for (int k = 0; k < n_buf && !rc; ++k) rc = r.reserve(kBufOut0 + k, (size_t)chunk * row_len * 8, "cudaMalloc walks");
     const size_t down_bytes = (size_t)chunk * row_len * 4;
-    for (int k = 0; k < std::min(n_jobs, kRing) && !rc; ++k) {
+    for (int k = 0; k < n_buf && mode != 0 && !rc; ++k) {
         rc = r.reserve(kBufDown0 + k, down_bytes + 256, "cudaMalloc download staging");
         if (!rc) rc = r.reserve_pinned(kPinDown0 + k, down_bytes, "cudaHostAlloc download staging");
     }
+    const int dma_eighths = check ? check->dma_eighths : 0;
+    const int64_t sum_piece = std::min(std::max<int64_t>(options().host_sum_piece, 16), kMaxSumPiece);
+    if (!rc && dma_eighths > 0) rc = r.reserve(kBufCheck, 2 * (size_t)kMaxSumPiece * 8 + 256, "cudaMalloc check buffer");
+    if (!rc && dma_eighths > 0) rc = r.reserve_pinned(kPinUp0, 256, "cudaHostAlloc checksum cell");
     if (rc) return rc;
-    while ((int)r.landed.size() < n_chunks) {
+    while ((int)r.landed.size() < n_chunks + 2) {
         cudaEvent_t e;
         TRW_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create");
         r.landed.push_back(e);
     }
-    int* d_overflow = n_jobs ? (int*)((char*)r.ptr[kBufDown0] + down_bytes) : nullptr;  // the 256 spare bytes
-    if (n_jobs) TRW_TRY(cudaMemsetAsync(d_overflow, 0, sizeof(int), r.compute), "overflow flag memset");
+    cudaEvent_t* const summed = r.landed.data() + n_chunks;  // the two side buffers of the copy engine's checksum pieces
+    int* d_overflow = mode != 0 ? (int*)((char*)r.ptr[kBufDown0] + down_bytes) : nullptr;  // the 256 spare bytes
+    if (mode != 0) TRW_TRY(cudaMemsetAsync(d_overflow, 0, sizeof(int), r.compute), "overflow flag memset");
+    uint64_t* d_sum = dma_eighths > 0 ? (uint64_t*)((char*)r.ptr[kBufCheck] + 2 * (size_t)kMaxSumPiece * 8) : nullptr;
+    if (d_sum) TRW_TRY(cudaMemsetAsync(d_sum, 0, sizeof(uint64_t), r.check), "check sum memset");
 
-    HostTeam team(n_threads, n_jobs, sums, n_sums);
-    for (int j = 0; j < n_jobs; ++j) {
-        const int64_t first = (int64_t)chunk_of_job[(size_t)j] * chunk, m = std::min(chunk, sh.n_walks - first);
-        WidenJob& w = team.job(j);
-        w.src = (const uint32_t*)r.pinned[kPinDown0 + j % kRing];
-        w.dst = out + first * row_len;
-        w.n = m * row_len;
-        w.pieces = (w.n + kWidenPiece - 1) / kWidenPiece;
-    }
-    auto enqueue = [&](int c) -> int {
+    HostTeam team(n_threads, mode != 0 ? n_chunks : 0, check ? check->sums : nullptr, check ? check->n_sums : 0, sum_piece);
+    std::vector<int> job_of_chunk((size_t)n_chunks, -1), chunk_of_job;
+    int64_t n_sum_pieces = 0;
+    if (check)
+        for (int k = 0; k < check->n_sums; ++k) n_sum_pieces += (check->sums[k].hi - check->sums[k].lo + sum_piece - 1) / sum_piece;
+    const int64_t dma_max = n_sum_pieces * dma_eighths / 8;
+    int dma_issued = 0;
+    // the copy engine's share of the checksum: keep its two side buffers busy
+    auto feed_check = [&]() -> int {
+        while (dma_issued < dma_max) {
+            const int slot = dma_issued & 1;
+            if (dma_issued >= 2) {
+                const cudaError_t st = cudaEventQuery(summed[slot]);
+                if (st == cudaErrorNotReady) return TRW_OK;
+                if (st != cudaSuccess) return check_cuda(st, "query check piece");
+            }
+            HostSum pc;
+            if (!team.claim_front(&pc, dma_max)) { dma_issued = (int)dma_max; return TRW_OK; }
+            int64_t* side = (int64_t*)r.ptr[kBufCheck] + (size_t)slot * kMaxSumPiece;
+            TRW_TRY(cudaMemcpyAsync(side, pc.v + pc.lo, (size_t)(pc.hi - pc.lo) * 8, cudaMemcpyHostToDevice, r.check), "H2D check piece");
+            const int rc2 = csr_checksum_part(IdxPtr((const int64_t*)side), pc.hi - pc.lo, pc.lo, pc.golden == kChecksumColGolden, d_sum, d, r.check);
+            if (rc2) return rc2;
+            TRW_TRY(cudaEventRecord(summed[slot], r.check), "record check piece");
+            ++dma_issued;
+        }
+        return TRW_OK;
+    };
+    auto enqueue = [&](int c, bool packed) -> int {
         const int b = c % kRing;
         const int64_t done = (int64_t)c * chunk, m = std::min(chunk, sh.n_walks - done);
-        const int j = job_of_chunk[(size_t)c];
         if (c >= kRing) TRW_TRY(cudaStreamWaitEvent(r.compute, r.landed[(size_t)(c - kRing)], 0), "wait landed");  // its walk buffer is free
         // ids of this chunk: contiguous shards advance the offset; block-cyclic ones advance it by whole strides
         const int64_t off = sh.id_block > 0 ? sh.walk_id_offset + (done / sh.id_block) * sh.id_stride : sh.walk_id_offset + done;
         int rc2 = csr_walk_launch(plan, d_targets + done, m, off, (int64_t*)r.ptr[kBufOut0 + b], row_len, r.compute, sh.id_block, sh.id_stride);
         if (rc2) return rc2;
-        if (j >= 0) {  // (its device staging is free: the job that used it last has been widened, so its copy is long done)
+        int j = -1;
+        if (packed) {  // (its staging is free: the job that used it last has been widened, so its copy is long done)
+            j = team.add_job((const uint32_t*)r.pinned[kPinDown0 + team.jobs_added() % kRing], out + done * row_len, m * row_len);
+            job_of_chunk[(size_t)c] = j;
+            chunk_of_job.push_back(c);
             narrow_i64_kernel<<<sm_count(d) * 8, 256, 0, r.compute>>>((const int64_t*)r.ptr[kBufOut0 + b], (uint32_t*)r.ptr[kBufDown0 + j % kRing],
                                                                      m * row_len, d_overflow);
             count_launch(1);
         }
         TRW_TRY(cudaEventRecord(r.walked[c & 1], r.compute), "record walked");
         TRW_TRY(cudaStreamWaitEvent(r.copy, r.walked[c & 1], 0), "wait walked");
-        if (j >= 0)
+        if (packed)
             TRW_TRY(cudaMemcpyAsync(r.pinned[kPinDown0 + j % kRing], r.ptr[kBufDown0 + j % kRing], (size_t)m * row_len * 4, cudaMemcpyDeviceToHost,
                                     r.copy), "D2H walks (uint32)");
         else
@@ -507,55 +558,77 @@ static int host_pipeline(HostWalkCache& r, int d, const CsrWalkPlan& plan, const
         TRW_TRY(cudaEventRecord(r.landed[(size_t)c], r.copy), "record landed");
         return TRW_OK;
     };
-    // The calling thread keeps the device fed: it enqueues a chunk as soon as its staging is free, and otherwise announces
-    // packed chunks to the team as they land.  It never blocks inside the driver: while it waits it widens.
-    int enq = 0, pub = 0, jobs_enqueued = 0;
+    // The calling thread keeps two copies queued (a chunk's format is decided as late as that allows), announces packed
+    // chunks to the team as they land and feeds the copy engine's checksum pieces.  It never blocks inside the driver:
+    // while it waits it widens.
+    int enq = 0, pub = 0, landed_upto = 0, n_packed = 0;
     const bool timing = getenv("TRW_HOST_TIMING") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     double t_enqueued = 0, t_landed = 0;
-    while (enq < n_chunks || pub < n_jobs) {
-        if (enq < n_chunks) {
-            const int j = job_of_chunk[(size_t)enq];
-            if (j < kRing || team.job(j - kRing).finished()) {
-                rc = enqueue(enq);
+    while (enq < n_chunks || pub < team.jobs_added()) {
+        bool moved = false;
+        rc = feed_check();
+        if (rc) return rc;
+        while (landed_upto < enq) {  // chunks land in order
+            const cudaError_t st = cudaEventQuery(r.landed[(size_t)landed_upto]);
+            if (st == cudaErrorNotReady) break;
+            if (st != cudaSuccess) return check_cuda(st, "query landed");
+            if (job_of_chunk[(size_t)landed_upto] >= 0) team.publish(++pub);
+            if (++landed_upto == n_chunks) t_landed = ms_now();
+            team.set_progress(landed_upto, n_chunks);
+            moved = true;
+        }
+        if (enq < n_chunks && enq - landed_upto < 2) {
+            const int j_next = team.jobs_added();
+            const bool staging_free = team.job_finished(j_next - kRing);
+            bool packed = false, can = true;
+            if (adaptive) packed = staging_free && team.backlog() <= 1;
+            else if (packed_by_pattern(enq)) { packed = true; can = staging_free; }
+            if (can) {
+                rc = enqueue(enq, packed);
                 if (rc) return rc;
-                if (j >= 0) jobs_enqueued = j + 1;
+                n_packed += packed ? 1 : 0;
                 if (++enq == n_chunks) t_enqueued = ms_now();
-                continue;
+                moved = true;
             }
         }
-        if (pub < jobs_enqueued) {
-            const cudaError_t st = cudaEventQuery(r.landed[(size_t)chunk_of_job[(size_t)pub]]);
-            if (st == cudaSuccess) {
-                team.publish(++pub);
-                if (pub == n_jobs) t_landed = ms_now();
-                continue;
-            }
-            if (st != cudaErrorNotReady) return check_cuda(st, "query landed");
-        }
-        if (!team.help_widen()) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        if (!moved && !team.help_widen()) std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
-    const uint64_t sum = team.drain();  // (every job is published by now)
-    if (host_sum) *host_sum = sum;
+    team.set_progress(1, 1);
+    while (dma_issued < dma_max) {  // (only if the download ended first: the engine's pieces run on, the team takes the rest)
+        rc = feed_check();
+        if (rc) return rc;
+        if (dma_issued < dma_max && !team.help_widen()) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    const uint64_t sum = team.drain();
     const double t_drained = ms_now();
     TRW_TRY(cudaStreamSynchronize(r.compute), "sync compute");
     TRW_TRY(cudaStreamSynchronize(r.copy), "sync copy");
+    if (check) {
+        check->sum = sum;
+        if (d_sum) {
+            uint64_t* cell = (uint64_t*)r.pinned[kPinUp0] + 1;
+            TRW_TRY(cudaMemcpyAsync(cell, d_sum, sizeof(uint64_t), cudaMemcpyDeviceToHost, r.check), "D2H check sum");
+            TRW_TRY(cudaStreamSynchronize(r.check), "sync content check");
+            check->sum += *cell;
+        }
+    }
     if (timing)
-        fprintf(stderr, "[host_pipeline] %d chunks (%d packed), %d host threads, %d sum parts | last chunk enqueued %.1f ms, last packed chunk landed %.1f, "
-                "host work done %.1f, copies done %.1f\n", n_chunks, n_jobs, n_threads, n_sums, t_enqueued, t_landed, t_drained, ms_now());
-    if (n_jobs) {
+        fprintf(stderr, "[host_pipeline] %d chunks (%d packed%s), %d host threads, %lld sum pieces (%d by the copy engine) | last chunk enqueued %.1f ms, "
+                "landed %.1f, host work done %.1f, all done %.1f\n", n_chunks, n_packed, adaptive ? ", adaptive" : "", n_threads,
+                (long long)n_sum_pieces, dma_issued, t_enqueued, t_landed, t_drained, ms_now());
+    if (n_packed) {
         int overflow = 0;
         TRW_TRY(cudaMemcpy(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost), "read overflow flag");
         if (overflow) return kRetryPlain;  // an id beyond 32 bits came out of the graph: the caller walks again with plain copies
     }
     return TRW_OK;
 }
-// *host_sum is complete after the first pass whatever its outcome, so a retry carries no sums.
+// The content check is complete after the first pass whatever its outcome, so a retry carries none.
 static int host_pipeline_any(HostWalkCache& r, int d, const CsrWalkPlan& plan, const int64_t* d_targets, const HostCallShape& sh,
-                             int64_t* out, int mode, int n_threads, const HostSum* sums = nullptr, int n_sums = 0,
-                             uint64_t* host_sum = nullptr) {
-    int rc = host_pipeline(r, d, plan, d_targets, sh, out, mode, n_threads, sums, n_sums, host_sum);
+                             int64_t* out, int mode, int n_threads, ContentCheck* check = nullptr) {
+    int rc = host_pipeline(r, d, plan, d_targets, sh, out, mode, n_threads, check);
     if (rc == kRetryPlain) rc = host_pipeline(r, d, plan, d_targets, sh, out, 0, n_threads);
     return rc;
 }
@@ -584,18 +657,19 @@ static int ensure_streams(HostWalkCache& r) {
     return TRW_OK;
 }
 
-// Download mode for this call (how many of every 8 chunks travel packed): option host_compress 0 plain, 1 packed (needs
-// the threads), 2 half and half; ids must fit.  `checking`: the kept replica's content check runs beside the download and
-// takes its share of the host's memory bandwidth, which is what bounds the call then -- measured on c3 with 16 threads
-// (profiles/r02_host_path.md): 6 of 8 packed with 3 eighths of the check on the copy engine, 84 ms; all packed 97 ms;
-// plain copies 114-122 ms.
+// Download mode for this call: how many of every 8 chunks travel packed, or -1 for "decided chunk by chunk by how the
+// host keeps up" (host_pipeline).  Option host_compress 0: plain copies; ids must fit 32 bits.  Option host_packed_share
+// fixes the share (measurements, tests); the default is the adaptive mode whenever the host path has threads to widen
+// with.  (c3, 16 host threads, kept replica with its content check, profiles/r02_host_path.md: fixed shares measured
+// between 84 and 122 ms per call depending on share AND box; no fixed share is best on every box.)
 static int download_mode(int n_threads, int64_t n_nodes, bool ids_fit, bool checking = false) {
+    (void)checking;
     const int64_t want = options().host_compress;
     if (want == 0 || !ids_fit || (uint64_t)n_nodes >= 0xFFFFFFFFull) return 0;
-    const int share = (int)options().host_packed_share;  // of 8 chunks, how many travel packed (-1: by thread count)
+    const int share = (int)options().host_packed_share;  // of 8 chunks, how many travel packed (-1: adaptive)
     if (share >= 0) return share > 8 ? 8 : share;
-    if (n_threads >= kMinCompressThreads) return want == 2 ? 4 : (checking ? 6 : 8);
-    return n_threads >= 4 && want == 2 ? 2 : 0;
+    if (want == 2) return n_threads >= 4 ? 4 : 0;
+    return n_threads >= 2 ? -1 : 0;
 }
 
 }  // namespace trw
@@ -649,7 +723,7 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     if (rc) return rc;
     TRW_TRY(cudaMemcpyAsync(r.ptr[kBufTargets], targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
     std::atomic<int> wide_targets{0};  // start nodes travel as int64, but their values come back inside the walks
-    if (options().host_compress != 0 && n_threads >= kMinCompressThreads)
+    if (options().host_compress != 0 && n_threads >= 2)  // (a wide id that slips through is caught on the device: kRetryPlain)
         parallel_for(n_threads, [&](int tid, int nt) {
             bool bad = false;
             for (int64_t i = n_walks * tid / nt, e = n_walks * (tid + 1) / nt; i < e; ++i) bad |= (uint64_t)targets[i] > 0xFFFFFFFFull;
@@ -678,32 +752,20 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         CsrWalkPlan plan;
         rc = csr_walk_plan(&plan, r.graph, p, q, walk_length, seed);
         if (rc) return rc;
-        // The content check runs beside the pipeline, shared between the copy engine and the host's cores.  Pinned arrays:
-        // the copy engine re-reads `host_check_dma` eighths of col_idx over the upload direction and the device sums them;
-        // the host team sums the rest between its widening jobs.  Pageable arrays are summed by the team alone.
-        const bool dma_ok = host_pinned(row_ptr) && host_pinned(col_idx);
-        const int64_t dma_share = dma_ok ? std::min<int64_t>(std::max<int64_t>(options().host_check_dma, 0), 8) : 0;
-        const int64_t col_hi = dma_share >= 8 ? nnz : (nnz / 8) * dma_share;  // col_idx[0, col_hi) by the copy engine
-        if (dma_share > 0) {
-            rc = enqueue_dma_checksum(r, d, row_ptr, col_idx, n_nodes, col_hi, dma_share >= 8);
-            if (rc) return rc;
-        }
-        HostSum sums[2];
-        int n_sums = 0;
-        if (col_hi < nnz) sums[n_sums++] = HostSum{col_idx, col_hi, nnz, kChecksumColGolden};
-        if (dma_share < 8) sums[n_sums++] = HostSum{row_ptr, 0, n_nodes + 1, kChecksumRowGolden};
+        // The content check runs beside the pipeline, shared between the copy engine (pinned arrays only: it re-reads
+        // pieces over the upload direction and the device sums them) and the host team -- see HostTeam.
+        ContentCheck check;
+        if (nnz > 0) check.sums[check.n_sums++] = HostSum{col_idx, 0, nnz, kChecksumColGolden};
+        check.sums[check.n_sums++] = HostSum{row_ptr, 0, n_nodes + 1, kChecksumRowGolden};
+        if (host_pinned(row_ptr) && host_pinned(col_idx)) check.dma_eighths = (int)std::min<int64_t>(std::max<int64_t>(options().host_check_dma, 0), 8);
         const int mode = download_mode(n_threads, n_nodes, wide_targets.load() == 0, /*checking=*/true);
-        uint64_t host_sum = 0;
-        rc = host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, mode, n_threads, sums, n_sums, &host_sum);
+        rc = host_pipeline_any(r, d, plan, (const int64_t*)r.ptr[kBufTargets], shape, out, mode, n_threads, &check);
         if (rc) return rc;
-        if (dma_share > 0) {
-            TRW_TRY(cudaStreamSynchronize(r.check), "sync content check");
-            host_sum += ((const uint64_t*)r.pinned[kPinUp0])[1];
-        }
+        const uint64_t host_sum = check.sum;
         if (host_sum == r.replica_checksum) {
             if (timing)
                 fprintf(stderr, "[trw_walk_csr_host] kept replica (level %d, hit %d), content check by %s, %d of 8 chunks packed, %d host threads | total %.1f ms\n",
-                        r.level, r.hits, dma_share >= 8 ? "copy engine + device" : dma_share > 0 ? "copy engine and host threads" : "host threads", mode, n_threads, ms_since(t_hit));
+                        r.level, r.hits, check.dma_eighths > 0 ? "copy engine and host threads" : "host threads", mode, n_threads, ms_since(t_hit));
             r.last_call = 1;
             return TRW_OK;
         }
@@ -844,7 +906,7 @@ extern "C" int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_
     TRW_TRY(cudaMemcpyAsync(r.ptr[kBufTargets], targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
     const int n_threads = host_thread_count();
     bool ids_fit = true;
-    if (options().host_compress != 0 && n_threads >= kMinCompressThreads) {
+    if (options().host_compress != 0 && n_threads >= 2) {
         std::atomic<int> wide{0};
         parallel_for(n_threads, [&](int tid, int nt) {
             bool bad = false;
