@@ -87,9 +87,10 @@ def main():
     blocks = (trw_dist.DEFAULT_BLOCK, trw_dist.DEFAULT_BLOCK * world)
     steps = n_walks * L
     runs = {}
-    variants = arg("variants", "host_packed_share:0,host_packed_share:8,host_packed_share:4,"
-                               "host_packed_share:0+host_chunk_walks:262144,host_packed_share:8+host_chunk_walks:262144,"
-                               "host_packed_share:8+host_chunk_walks:262144+host_threads:8,host_packed_share:4+host_chunk_walks:262144+host_threads:8")
+    variants = arg("variants", "host_packed_share:0,host_packed_share:-1,host_packed_share:8,"
+                               "host_packed_share:0+host_chunk_walks:131072,host_packed_share:-1+host_chunk_walks:131072,"
+                               "host_packed_share:8+host_chunk_walks:131072,host_packed_share:-1+host_chunk_walks:131072+host_threads:8,"
+                               "host_packed_share:-1+host_chunk_walks:262144")
     for variant in variants.split(","):
         opts = {kv.split(":")[0]: int(kv.split(":")[1]) for kv in variant.split("+")}
         saved = {k_: native.get_option(k_) for k_ in opts}
