@@ -104,7 +104,7 @@ def test_positives_match_reference_goldens(rw, orc, golden):
 
 
 @pytest.mark.parametrize("n,wl,W", [(1, 5, 5), (2, 7, 1), (33, 81, 5), (1000, 81, 5), (257, 41, 10), (5, 3001, 7),
-                                    (3, 30001, 3), (64, 13, 6), (511, 21, 4)])
+                                    (3, 30001, 3), (64, 13, 6), (511, 21, 4), (100, 41, 11), (70, 61, 12), (129, 81, 9), (77, 9, 2)])
 def test_all_variants_against_oracle(rw, orc, n, wl, W):
     g = torch.Generator().manual_seed(n * 1000 + wl)
     walks = torch.randint(0, 500, (n, wl), generator=g)
@@ -167,6 +167,26 @@ def test_bulk_store_path_of_the_triple_windows_equals_plain_stores(rw):
         finally:
             native.set_option("win_bulk", 0)
         for a, b in zip(plain, bulk):
+            assert torch.equal(a, b), (n, wl, W)
+
+
+def test_direct_positive_windows_of_the_triple_kernels_equal_the_staged_ones(rw):
+    """Option win_direct_pos (the default) writes the positive windows of the triple kernels straight from the walk tile,
+    one fixed 16-byte piece slot per lane; off, they go through the per-warp stage like the other rows.  Same tensors for every
+    window size the direct form takes (3W <= 32) and beyond, full and ragged tiles, walks shorter than a window."""
+    from torch_random_walk_b200 import native
+
+    triples = torch.randint(0, 5000, (20011, 3), device="cuda")
+    for n, wl, W in ((1001, 81, 5), (37, 7, 2), (5, 3, 1), (64, 21, 3), (333, 41, 10), (50, 41, 11), (129, 5, 4), (2, 81, 7), (4097, 13, 6)):
+        walks = torch.randint(0, 5000, (n, wl), device="cuda")
+        assert native.get_option("win_direct_pos") == 1
+        direct = rw.to_windows_triples(walks, W, 5000, 4999, triples, 3) + rw.to_windows_triples_cbow(walks, W, 5000, 4999, triples, 3)
+        native.set_option("win_direct_pos", 0)
+        try:
+            staged = rw.to_windows_triples(walks, W, 5000, 4999, triples, 3) + rw.to_windows_triples_cbow(walks, W, 5000, 4999, triples, 3)
+        finally:
+            native.set_option("win_direct_pos", 1)
+        for a, b in zip(direct, staged):
             assert torch.equal(a, b), (n, wl, W)
 
 

@@ -39,6 +39,8 @@ struct Options {
     int64_t host_cache_buffers = 1;  // 1: trw_walk_csr_host keeps its device buffers between calls
     int64_t win_table16 = 1;      // 1: the triple window kernels gather their negative rows from a 16-byte uint32 copy of `triples` when the caller
                                   // passes a workspace (trw_windows_triples_ws) and every id fits; 0: always the int64 table (A/B)
+    int64_t win_direct_pos = 1;   // 1: triple window kernels write the positive windows straight from the walk tile in 16-byte pieces (window_size <= 10);
+                                  // 0: through the per-warp stage like the other rows
     int64_t win_bulk = 0;         // 1: the warps' stages of the triple window kernels leave as bulk stores (cp.async.bulk, SASS UBLKCP) instead of 16-byte
                                   // stores.  A/B only: measured equal for to_windows_triples (2.58 vs 2.60 ms) and slower for the CBOW form, whose
                                   // occupancy the second stage costs (profiles/r02_summary.md) -- the kernels are bound by index arithmetic and
@@ -53,7 +55,7 @@ struct Options {
 #define TRW_OPTION_LIST                                                                      \
     TRW_OPT(stage_output) TRW_OPT(n2v_table) TRW_OPT(n2v_speculate) TRW_OPT(persist_row_ptr) \
     TRW_OPT(persist_l2_mb) TRW_OPT(host_chunk_walks) TRW_OPT(time_kernels) TRW_OPT(n2v_min_ctas) TRW_OPT(row32)       \
-    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk) TRW_OPT(n2v_warp) TRW_OPT(win_table16) TRW_OPT(host_check_dma) TRW_OPT(host_sum_piece)
+    TRW_OPT(build_mode) TRW_OPT(calib_mode) TRW_OPT(n2v_fold) TRW_OPT(host_cache_buffers) TRW_OPT(host_compress) TRW_OPT(host_threads) TRW_OPT(host_up_chunk) TRW_OPT(store_mode) TRW_OPT(records) TRW_OPT(el_table) TRW_OPT(n2v_mix) TRW_OPT(n2v_slots) TRW_OPT(calib_aux_mb) TRW_OPT(smem_carveout_kb) TRW_OPT(edge_filter_mb) TRW_OPT(edge_bloom_cap) TRW_OPT(host_keep_graph) TRW_OPT(host_packed_share) TRW_OPT(win_bulk) TRW_OPT(win_direct_pos) TRW_OPT(n2v_warp) TRW_OPT(win_table16) TRW_OPT(host_check_dma) TRW_OPT(host_sum_piece)
 
 Options& options();
 void count_launch(int n);

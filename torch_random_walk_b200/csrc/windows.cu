@@ -41,6 +41,7 @@ struct WinArgs {
     int tile_walks;
     int use_smem;
     int bulk;          // triple modes: the warps' stages leave as bulk stores (cp.async.bulk) instead of 16-byte stores
+    int direct_pos;    // triple modes: positive windows go from the tile to global memory in 16-byte pieces, no stage (window_size <= 10)
     int64_t num_nodes, pad;
     const int64_t* triples;
     int64_t n_triples;
@@ -182,10 +183,44 @@ __device__ __forceinline__ void triple_tile(const WinArgs& a, const int64_t* til
         const int64_t* w = tile + (size_t)i * a.wl + 2u * ti;
         o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
     });
-    // positive windows: row (i, ti, h), the three slots at once, through the per-warp stage.  (Storing them element by element from
-    // the tile instead -- a (walk, target) block per warp round, one lane per element -- measured 2.7 vs 2.1 ms: 30 of 32 lanes
-    // busy and one division per 30 elements cost more than the stage's shared-memory traffic.)
-    if (R > 0) {
+    // Positive windows.  The 2W rows of one (walk, target) are 6W consecutive elements = 3W 16-byte pieces, and which walk
+    // position (relative to the target) a piece's two elements come from depends on the piece alone.  So for 3W <= 32 a
+    // lane keeps ONE piece slot for the whole tile -- its two source offsets are worked out once -- and a warp round
+    // writes floor(32 / 3W) whole blocks: per piece two shared-memory loads and one 16-byte store, against the stage's
+    // three loads, three 8-byte stage stores, one 16-byte stage load and the store (the kernel is bound by L1/shared-memory
+    // wavefronts, ncu).  An earlier element-per-lane form (8-byte stores, offsets recomputed per element) lost to the stage.
+    int64_t* const pos_dst = a.out[pos_out] + (uint64_t)i0 * K * R * 3u;
+    const uint32_t P = 3u * (uint32_t)a.W;  // pieces per block
+    const bool direct = R > 0 && a.direct_pos != 0 && P <= 32u && (((uintptr_t)pos_dst) & 15) == 0;
+    if (direct) {
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t per_round = 32u / P, blk = lane / P, jp = lane - blk * P;
+        // slot j of a block = row h = j / 3, column c = j % 3.  Left rows (h < W): (walk[ri], walk[ri], walk[ri+1]) with
+        // ri = r - 2(h+1), the first two only where ri >= 1, the third where ri >= -1 (windows_cuda.cu:284-313); right rows:
+        // walk[idx + c] with idx = r + 2(h-W+1) - 1 where it exists (:315-345).  As (offset from r, lowest valid position):
+        int off[2], lo[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int j = 2 * (int)jp + k, h = j / 3, c = j - 3 * h;
+            if (h < a.W) { off[k] = -2 * (h + 1) + (c == 2 ? 1 : 0); lo[k] = c == 2 ? 0 : 1; }
+            else { off[k] = 2 * (h - a.W + 1) - 1 + c; lo[k] = 0; }
+        }
+        const uint32_t n_blocks = (uint32_t)tw * K;
+        if (blk < per_round) {
+            for (uint32_t b = warp * per_round + blk; b < n_blocks; b += (BLOCK / 32) * per_round) {
+                uint32_t i, ti;
+                a.by_per_walk.divmod(b, i, ti);
+                const int64_t* w = tile + (size_t)i * a.wl;
+                const int s0 = 2 * (int)ti + 1 + off[0], s1 = 2 * (int)ti + 1 + off[1];
+                longlong2 v;
+                v.x = (s0 >= lo[0] && s0 < a.wl) ? w[s0] : a.pad;
+                v.y = (s1 >= lo[1] && s1 < a.wl) ? w[s1] : a.pad;
+                reinterpret_cast<longlong2*>(pos_dst)[(uint64_t)b * P + jp] = v;
+            }
+        }
+    }
+    // (3W > 32, or an odd destination:) row (i, ti, h), the three slots at once, through the per-warp stage
+    if (R > 0 && !direct) {
         emit_rows<BLOCK, BULK>(a.out[pos_out] + (uint64_t)i0 * K * R * 3u, (uint32_t)tw * K * R, stage, round, [&](uint32_t row, int64_t* o) {
             uint32_t k, h, i, ti;
             a.by_row.divmod(row, k, h);
@@ -465,6 +500,7 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     a.tile_walks = (int)tw;
     // bulk stores need 16-byte aligned segments: true for whole tensors from any allocator worth the name and for
     // tiles that start on a multiple of four walks
+    a.direct_pos = options().win_direct_pos != 0 ? 1 : 0;
     a.bulk = 0;
     if (kTripleMode && options().win_bulk != 0 && (((uintptr_t)o0 | (uintptr_t)o1 | (uintptr_t)o2) & 15) == 0) a.bulk = 1;
     const bool bulk = kTripleMode && a.bulk != 0;
