@@ -689,8 +689,8 @@ def measure_e2e(native, trw_dist, rep, row_ptr, col_idx, targets, p, q, L, e2e_s
     if world == 1:
         rp_h, ci_h, tg_h = row_ptr.cpu().pin_memory(), col_idx.cpu().pin_memory(), targets.cpu().pin_memory()
         out_h = torch.empty((n_walks, L + 1), dtype=torch.int64, pin_memory=True)
-        # a caller that comes back with the same host arrays finds the device replica kept (content re-checked by the host
-        # threads on every call); like the device-side cache its preparation grows with use, so warm up until it has settled
+        # a caller that comes back with the same host arrays finds the device replica kept (content re-checked on every
+        # call); like the device-side cache its preparation grows with use, so warm up until it has settled
         fresh_ms = []
         native.set_option("host_keep_graph", 0)
         for k in range(2):
@@ -713,14 +713,16 @@ def measure_e2e(native, trw_dist, rep, row_ptr, col_idx, targets, p, q, L, e2e_s
         e2e = {"value": steps_per_call * e2e_steps / dt, "unit": "steps/s", "ms_per_step": dt / e2e_steps * 1e3,
                "h2d_bytes_per_step": int(tg_h.numel() * 8), "d2h_bytes_per_step": int(out_h.numel() * 8), "steps": e2e_steps,
                "graph_bytes_checksummed_on_host_per_step": graph_bytes,
+               "replica_after_timed_calls": native.host_replica_info(local_rank),  # last_call must read "kept replica validated"
                "warmup_call_ms": warm_ms,
                "fresh_upload": {"value": steps_per_call / (min(fresh_ms) / 1e3), "unit": "steps/s", "ms_per_step": min(fresh_ms),
                                 "h2d_bytes_per_step": graph_bytes + int(tg_h.numel() * 8),
                                 "note": "option host_keep_graph=0: the graph crosses PCIe and is prepared inside every call"},
                "api": "native.walk_host -> trw_walk_csr_host (pinned host tensors in, pinned host walks out).  The device replica of "
-                      "the graph is kept between calls with the same host arrays; every call walks on it at once while the host threads "
-                      "checksum row_ptr and col_idx against it (a mismatch uploads afresh and walks again), so per step only the start "
-                      "nodes go up and the walks come down"}
+                      "the graph is kept between calls with the same host arrays; every call walks on it at once while row_ptr and "
+                      "col_idx are checksummed against it (copy engine re-reading part of the pinned arrays, host threads the rest; a "
+                      "mismatch uploads afresh and walks again), so per step only the start nodes go up and the walks come down -- as "
+                      "uint32 widened by the host threads for as many chunks as they keep up with, else as int64"}
         # the device path and the host path must agree on the result
         check = native.walk(row_ptr, col_idx, targets[:4096].contiguous(), p, q, L, 3000 + e2e_steps - 1, cache=False)
         assert torch.equal(check.cpu(), out_h[:4096]), "host path and device path disagree"
