@@ -710,10 +710,15 @@ def measure_e2e(native, trw_dist, rep, row_ptr, col_idx, targets, p, q, L, e2e_s
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         graph_bytes = int((rp_h.numel() + ci_h.numel()) * 8)
+        info = native.host_replica_info(local_rank)  # of the last timed call
+        # h2d / d2h: what crossed PCIe in the last timed call as the library counted its copies -- upwards the start nodes plus
+        # the copy engine's share of the content check, downwards the walks at 4 bytes per entry for the chunks that travelled
+        # packed and 8 for the others (the split is decided call by call); the tensors themselves are listed beside them
         e2e = {"value": steps_per_call * e2e_steps / dt, "unit": "steps/s", "ms_per_step": dt / e2e_steps * 1e3,
-               "h2d_bytes_per_step": int(tg_h.numel() * 8), "d2h_bytes_per_step": int(out_h.numel() * 8), "steps": e2e_steps,
-               "graph_bytes_checksummed_on_host_per_step": graph_bytes,
-               "replica_after_timed_calls": native.host_replica_info(local_rank),  # last_call must read "kept replica validated"
+               "h2d_bytes_per_step": info["h2d_bytes"], "d2h_bytes_per_step": info["d2h_bytes"], "steps": e2e_steps,
+               "input_tensor_bytes_per_step": int(tg_h.numel() * 8), "result_tensor_bytes_per_step": int(out_h.numel() * 8),
+               "graph_bytes_checksummed_per_step": graph_bytes,
+               "replica_after_timed_calls": info,  # last_call must read "kept replica validated"
                "warmup_call_ms": warm_ms,
                "fresh_upload": {"value": steps_per_call / (min(fresh_ms) / 1e3), "unit": "steps/s", "ms_per_step": min(fresh_ms),
                                 "h2d_bytes_per_step": graph_bytes + int(tg_h.numel() * 8),
@@ -747,8 +752,12 @@ def measure_e2e(native, trw_dist, rep, row_ptr, col_idx, targets, p, q, L, e2e_s
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
+    info = native.host_replica_info(local_rank)  # this rank's last timed call: bytes as the library counted its copies
+    moved = torch.tensor([info["h2d_bytes"], info["d2h_bytes"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(moved, op=dist.ReduceOp.SUM)
     return {"value": steps_per_call * e2e_steps / dt, "unit": "steps/s", "ms_per_step": dt / e2e_steps * 1e3,
-            "h2d_bytes_per_step": int(n_walks * 8), "d2h_bytes_per_step": int(n_walks * (L + 1) * 8), "steps": e2e_steps,
+            "h2d_bytes_per_step": int(moved[0].item()), "d2h_bytes_per_step": int(moved[1].item()), "steps": e2e_steps,
+            "input_tensor_bytes_per_step": int(n_walks * 8), "result_tensor_bytes_per_step": int(n_walks * (L + 1) * 8),
             "api": "per rank: dist.ReplicatedCsr.walk_local_to_host -> trw_walk_csr_to_host (pinned host start nodes of its shard in, "
                    "walks into its pinned host buffer, chunks walked and copied back in a pipeline); the graph replica was broadcast "
                    "over NVLink once, outside the timed region (bytes are totals over the ranks)"}

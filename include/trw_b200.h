@@ -192,7 +192,9 @@ int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_t* targets,
 /* The replica trw_walk_csr_host keeps on `device`: out[0] one is held, out[1] its preparation level (-1 none, 0 one
  * call's needs, 1 the full kept preparation, 2 with triangle Blooms), out[2] validated hits so far, out[3] how the last
  * call got its graph (0 no call yet, 1 kept replica validated, 2 fresh upload, 3 kept replica found changed and
- * uploaded afresh).  n_out >= 4. */
+ * uploaded afresh).  n_out >= 4; with n_out >= 6 also out[4], out[5] = the bytes the last host-path call on the device
+ * (trw_walk_csr_host or trw_walk_csr_to_host) moved over PCIe host->device (start nodes, graph upload, the copy engine's
+ * share of the content check) and device->host (walks, 4 or 8 bytes per entry). */
 int trw_host_replica_info(int device, int64_t* out, int n_out);
 
 /* Frees the device buffers, streams and events trw_walk_csr_host keeps between calls. */

@@ -935,6 +935,9 @@ def test_walk_host_keeps_the_replica_and_notices_changes(native):
                     assert torch.equal(native.walk_host(rp, ci, nodes, law[0], law[1], 20, 3, device=0), expect[law]), (threads, compress, rounds, law)
             info = native.host_replica_info(0)  # a content check that failed would show as a fresh upload on every call
             assert info["held"] and info["level"] == 2 and info["last_call"] == "kept replica validated", (threads, compress, dma, share, info)
+            # the bytes the call moved: walks at 4 or 8 bytes per entry; start nodes plus at most the copy engine's share of the check
+            assert n * 21 * (4 if share == 8 else 8 if compress == 0 or share == 0 else 4) <= info["d2h_bytes"] <= n * 21 * 8 + 64, info
+            assert n * 8 <= info["h2d_bytes"] <= n * 8 + (rp.numel() + ci.numel()) * 8 * dma // 8 + 8 * 10007 * 2, info
         assert native.csr_checksum_host(rp, ci) == native.csr_checksum(rp.cuda(), ci.cuda())
         # pageable arrays: kept as well, always summed by the host threads
         rp_p, ci_p = rp.clone(), ci.clone()

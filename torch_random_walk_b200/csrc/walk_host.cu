@@ -60,6 +60,7 @@ struct HostWalkCache {
     int64_t key_n_nodes = -1, key_nnz = -1;
     uint64_t replica_checksum = 0;
     bool have_replica = false;
+    int64_t up_bytes = 0, down_bytes = 0;  // what the last call moved over PCIe in each direction (trw_host_replica_info)
     int last_call = 0;    // how the last call through this cache got its graph: 1 kept replica validated, 2 fresh upload, 3 kept replica
                           // found changed (then uploaded afresh)
     int level = -1;       // -1 nothing prepared, 0 what one call's (p, q) needed, 1 the full kept preparation, 2 with triangle Blooms
@@ -530,6 +531,7 @@ static int host_pipeline(HostWalkCache& r, int d, const CsrWalkPlan& plan, const
             if (!team.claim_front(&pc, dma_max)) { dma_issued = (int)dma_max; return TRW_OK; }
             int64_t* side = (int64_t*)r.ptr[kBufCheck] + (size_t)slot * kMaxSumPiece;
             TRW_TRY(cudaMemcpyAsync(side, pc.v + pc.lo, (size_t)(pc.hi - pc.lo) * 8, cudaMemcpyHostToDevice, r.check), "H2D check piece");
+            r.up_bytes += (pc.hi - pc.lo) * 8;
             const int rc2 = csr_checksum_part(IdxPtr((const int64_t*)side), pc.hi - pc.lo, pc.lo, pc.golden == kChecksumColGolden, d_sum, d, r.check);
             if (rc2) return rc2;
             TRW_TRY(cudaEventRecord(summed[slot], r.check), "record check piece");
@@ -561,6 +563,7 @@ static int host_pipeline(HostWalkCache& r, int d, const CsrWalkPlan& plan, const
                                     r.copy), "D2H walks (uint32)");
         else
             TRW_TRY(cudaMemcpyAsync(out + done * row_len, r.ptr[kBufOut0 + b], (size_t)m * row_len * 8, cudaMemcpyDeviceToHost, r.copy), "D2H walks");
+        r.down_bytes += m * row_len * (packed ? 4 : 8);
         TRW_TRY(cudaEventRecord(r.landed[(size_t)c], r.copy), "record landed");
         return TRW_OK;
     };
@@ -728,6 +731,8 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     rc = r.reserve(kBufTargets, (size_t)n_walks * 8, "cudaMalloc targets");
     if (rc) return rc;
     TRW_TRY(cudaMemcpyAsync(r.ptr[kBufTargets], targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
+    r.up_bytes = n_walks * 8;
+    r.down_bytes = 0;
     std::atomic<int> wide_targets{0};  // start nodes travel as int64, but their values come back inside the walks
     if (options().host_compress != 0 && n_threads >= 2)  // (a wide id that slips through is caught on the device: kRetryPlain)
         parallel_for(n_threads, [&](int tid, int nt) {
@@ -806,6 +811,7 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
     const double ms_alloc = ms_since(t_start);
     const auto t_up = now();
     TRW_TRY(cudaMemcpyAsync(d_row_ptr, row_ptr, (size_t)(n_nodes + 1) * 8, cudaMemcpyHostToDevice, r.compute), "H2D row_ptr");
+    r.up_bytes += (n_nodes + 1) * 8 + nnz * (compress ? 4 : 8);
     if (compress) {
         std::atomic<int> wide{0};
         int64_t sent = 0;
@@ -829,6 +835,7 @@ extern "C" int trw_walk_csr_host(const int64_t* row_ptr, const int64_t* col_idx,
         TRW_TRY(cudaGetLastError(), "widen launch");
         if (wide.load()) {  // an id that needs more than 32 bits: plain copies for the whole call
             compress = false;
+            r.up_bytes += nnz * 8;  // (col_idx goes up a second time, as int64)
             TRW_TRY(cudaStreamSynchronize(r.compute), "sync before the uncompressed upload");
         }
     }
@@ -910,6 +917,8 @@ extern "C" int trw_walk_csr_to_host(const trw_csr_graph_view* view, const int64_
     rc = r.reserve(kBufTargets, (size_t)n_walks * 8, "cudaMalloc targets");
     if (rc) return rc;
     TRW_TRY(cudaMemcpyAsync(r.ptr[kBufTargets], targets, (size_t)n_walks * 8, cudaMemcpyHostToDevice, r.compute), "H2D targets");
+    r.up_bytes = n_walks * 8;
+    r.down_bytes = 0;
     const int n_threads = host_thread_count();
     bool ids_fit = true;
     if (options().host_compress != 0 && n_threads >= 2) {
@@ -967,7 +976,9 @@ extern "C" int trw_csr_checksum_host(const int64_t* row_ptr, const int64_t* col_
 
 // The kept replica of trw_walk_csr_host on `device`: out[0] a replica is held, out[1] its preparation level (-1 none, 0
 // one call's needs, 1 the full kept preparation, 2 with triangle Blooms), out[2] validated hits so far, out[3] how the
-// last call got its graph (0 no call yet, 1 kept replica validated, 2 fresh upload, 3 kept replica found changed).
+// last call got its graph (0 no call yet, 1 kept replica validated, 2 fresh upload, 3 kept replica found changed); with
+// n_out >= 6 also out[4], out[5]: the bytes the last host-path call on the device (either entry) moved host->device and
+// device->host.
 extern "C" int trw_host_replica_info(int device, int64_t* out, int n_out) {
     const int d = resolve_device(device);
     if (d < 0 || d >= 64 || !out || n_out < 4) {
@@ -980,5 +991,6 @@ extern "C" int trw_host_replica_info(int device, int64_t* out, int n_out) {
     out[1] = c.level;
     out[2] = c.hits;
     out[3] = c.last_call;
+    if (n_out >= 6) { out[4] = c.up_bytes; out[5] = c.down_bytes; }
     return TRW_OK;
 }

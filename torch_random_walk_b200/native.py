@@ -578,10 +578,11 @@ def csr_checksum_host(row_ptr, column_idx, threads=0, simd=True):
 
 def host_replica_info(device=0):
     """What trw_walk_csr_host keeps on `device` (trw_host_replica_info)."""
-    out = (ctypes.c_int64 * 4)()
-    _check(_lib.trw_host_replica_info(int(device), out, 4))
+    out = (ctypes.c_int64 * 6)()
+    _check(_lib.trw_host_replica_info(int(device), out, 6))
     return {"held": bool(out[0]), "level": int(out[1]), "hits": int(out[2]),
-            "last_call": {0: "none", 1: "kept replica validated", 2: "fresh upload", 3: "kept replica found changed"}[int(out[3])]}
+            "last_call": {0: "none", 1: "kept replica validated", 2: "fresh upload", 3: "kept replica found changed"}[int(out[3])],
+            "h2d_bytes": int(out[4]), "d2h_bytes": int(out[5])}  # what the last host-path call moved over PCIe
 
 
 def walk_host(row_ptr, column_idx, target_nodes, p, q, walk_length, seed, device=0, walk_id_offset=0, out=None):
