@@ -351,6 +351,8 @@ int trw_device_info(int device, int64_t* out, int n_out);
  * that sets it: other threads keep the defaults, and concurrent callers do not see each other's settings. */
 int trw_set_option(const char* name, int64_t value);
 int64_t trw_get_option(const char* name);
+/* Puts every option of the calling thread back to the shipped default. */
+void trw_reset_options(void);
 
 #ifdef __cplusplus
 }

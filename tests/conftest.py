@@ -39,3 +39,4 @@ def _graph_cache_off_by_default(request):
     native.set_graph_cache(False)
     yield
     native.set_graph_cache(False)
+    native.reset_options()  # a test that changed library options must not pass them on to the next one

@@ -90,7 +90,7 @@ def test_shards_are_bit_identical_to_one_call(native, p, q):
 
 
 DEFAULTS = {"n2v_table": 1, "n2v_speculate": -1, "stage_output": 1, "row32": 1, "build_mode": 2, "n2v_min_ctas": -1, "n2v_fold": 1,
-            "records": -1, "n2v_slots": 8, "edge_filter_mb": 64}
+            "records": -1, "n2v_slots": 8, "edge_filter_mb": 32}
 
 
 def test_kernel_variants_agree_bit_for_bit(native):
@@ -365,21 +365,31 @@ def test_triangle_blooms_and_edge_filter_do_not_change_a_walk(native, kind):
     n = rp.numel() - 1
     nodes = torch.arange(n, device="cuda")
     laws = ((1.0, 0.5), (0.5, 2.0), (0.25, 4.0), (0.4, 0.8), (2.0, 3.0))
+    saved = {k: native.get_option(k) for k in ("edge_bloom_cap", "edge_filter_mb")}
     try:
         native.set_option("edge_filter_mb", 0)
         base = [native.walk(rp, ci, nodes, p_, q_, 40, 3, cache=False) for p_, q_ in laws]
-        for cap, filter_mb in ((256, 64), (8, 64), (1 << 20, 0), (0, 64), (256, 1)):
+        # cap 8 and 2: most edges join two rows longer than the cap, so their questions go to the hub-pair filter (1 MB: crowded)
+        for cap, filter_mb in ((256, 64), (8, 64), (2, 1), (1 << 20, 0), (0, 64), (256, 1), (8, 0)):
             native.set_option("edge_bloom_cap", cap)
             native.set_option("edge_filter_mb", filter_mb)
             g = native.prepare_csr(rp, ci)
+            assert (g.info()["edge_filter_bits"] > 0) == (cap > 0 and filter_mb > 0)
             for (p_, q_), b in zip(laws, base):
                 assert torch.equal(g.walk(nodes, p_, q_, 40, 3), b), (kind, cap, filter_mb, p_, q_)
+            if cap == 8 and filter_mb == 64:  # the same through kernels without edge records: the filter must stay out of it
+                native.set_option("records", 0)
+                try:
+                    for (p_, q_), b in zip(laws[:2], base[:2]):
+                        assert torch.equal(g.walk(nodes, p_, q_, 40, 3), b), (kind, "records off", p_, q_)
+                finally:
+                    native.set_option("records", -1)
             if cap == 256 and filter_mb == 64:
                 assert g.symmetric == (kind in ("rmat", "clustered", "self_loops"))
             del g
     finally:
-        native.set_option("edge_bloom_cap", 256)
-        native.set_option("edge_filter_mb", 64)
+        for k, v in saved.items():
+            native.set_option(k, v)
 
 
 def test_unsorted_rows_and_duplicate_edges(native):

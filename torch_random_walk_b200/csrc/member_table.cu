@@ -54,8 +54,6 @@ struct BuildArgs {
     unsigned long long* next_segment; // work counter of build_hub_kernel
     int* failed;                     // set when a segment had no room (see member_table.cuh)
     uint32_t* row32;                 // optional uint32 copy of row_ptr
-    uint32_t* filter;                // optional edge filter (member_table.cuh), cleared before the build
-    uint32_t filter_bits;
     int64_t n_tiles, n_buckets, max_hubs, max_segs;
 };
 
@@ -63,7 +61,7 @@ struct BuildArgs {
 // is_member scans for such ids).
 __device__ __forceinline__ uint32_t slot_id(int64_t x) { return (uint64_t)x < (uint64_t)kEmpty ? (uint32_t)x : kEmpty; }
 
-// Edge filter: set the bit of the unordered pair {row, x}.  On a symmetric graph the mirror entry
+// Hub-pair filter (member_table.cuh): set the bit of the unordered pair {row, x}.  On a symmetric graph the mirror entry
 // (x, row) sets the same bit, so the larger-row half looks first and usually finds it set: half the
 // atomics.  A stale look only costs a redundant RED.
 __device__ __forceinline__ void filter_insert(uint32_t* __restrict__ filter, uint32_t n_bits, uint32_t row, uint32_t x,
@@ -233,7 +231,6 @@ __global__ void __launch_bounds__(kBuildThreads, 4) build_tiled_kernel(const Bui
     for (int k = 0; k < kRangePerThread; ++k) {
         if (xs[k] == kEmpty) continue;  // not ours, or an id the uint32 slots cannot hold
         const int64_t r = r0 + head[head_at(k * kBuildThreads + tid)] - 1;
-        if (a.filter) filter_insert(a.filter, a.filter_bits, (uint32_t)r, xs[k], pol_keep);
         if (r != cur_row) {
             cur_row = r;
             const int64_t b = ldg_idx(a.row_ptr + r), en = ldg_idx(a.row_ptr + r + 1);
@@ -296,7 +293,6 @@ __global__ void __launch_bounds__(kHubThreads, 1) build_hub_kernel(const BuildAr
                 const int64_t home = home_bucket(x[u], nb);
                 if (home >= lo && home < hi) {  // every entry of the row has its home in exactly one segment
                     ok &= smem_insert(hub_image, hub_count, size, home - lo, x[u]);
-                    if (a.filter) filter_insert(a.filter, a.filter_bits, (uint32_t)work.row, x[u], pol_keep);
                 }
             }
         }
@@ -486,7 +482,8 @@ template <bool WIDE>
 __global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col_any, int64_t nnz,
                                                                       const uint32_t* __restrict__ row32, int64_t n_nodes,
                                                                       uint4* __restrict__ records,
-                                                                      const uint32_t* __restrict__ table, EdgeFilter filter,
+                                                                      const uint32_t* __restrict__ table,
+                                                                      uint32_t* __restrict__ hub_bits, uint32_t hub_n_bits,
                                                                       uint32_t cap, const int* __restrict__ table_failed,
                                                                       int* __restrict__ asymmetric) {
     const IdxPtrT<WIDE> col_idx(col_any);
@@ -518,6 +515,8 @@ __global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col
             v = rec.x; dv = rec.y; vb = rec.z;
         }
         const bool live = valid && dv > 0;  // a neighbour without out-edges (or outside the graph) keeps its word
+        // an edge between two rows longer than the cap keeps its saturated word: it goes into the hub-pair filter instead
+        if (hub_bits != nullptr && live && dt > cap && dv > cap) filter_insert(hub_bits, hub_n_bits, t, v, pol_keep);
         const bool owner = live && (dt > dv || (dt == dv && t >= v));
         const bool exact = owner && dv <= cap;
         // every other live entry only has to know that its mirror exists
@@ -563,7 +562,7 @@ __global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col
 #pragma unroll
             for (int u = 0; u < kBloomUnroll; ++u) {
                 if (act[u] && w[u] == (int64_t)row[u]) s_mirror[warp][j[u]] = pos[u];
-                maybe[u] = act[u] && filter_maybe(filter, (int64_t)row[u], w[u], pol_keep);
+                maybe[u] = act[u];
             }
 #pragma unroll
             for (int u = 0; u < kBloomUnroll; ++u)
@@ -612,7 +611,7 @@ CsrWorkspace csr_workspace_layout(int64_t n_nodes, int64_t nnz, bool uniform, bo
     w.has_records = records && w.has_row32 && nnz > 0;  // spans are stored as uint32 (start, degree)
     w.records = off;
     if (w.has_records) off += align256((size_t)nnz * 16);
-    // edge filter: 32 bits per CSR entry for small graphs, capped at edge_filter_mb (it has to stay L2-resident)
+    // hub-pair filter: 32 bits per CSR entry for small graphs, capped at edge_filter_mb (it has to stay L2-resident)
     w.filter = off;
     w.filter_bits = 0;
     const int64_t filter_mb = options().edge_filter_mb > 511 ? 511 : options().edge_filter_mb;
@@ -639,14 +638,8 @@ int csr_prepare_device(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t 
     b.row_ptr = row_ptr; b.col_idx = col_idx; b.n_nodes = n_nodes; b.nnz = nnz;
     b.n_tiles = w.n_tiles; b.n_buckets = w.n_buckets; b.max_hubs = w.max_hubs; b.max_segs = w.max_segs;
     b.row32 = want_row32 ? (uint32_t*)(ws + w.row32) : nullptr;
-    const bool want_filter = want_table && build_mode != 0 && w.filter_bits != 0;
+    const bool want_filter = want_table && build_mode != 0 && w.filter_bits != 0;  // (filled by csr_add_blooms)
     int rc;
-    if (want_filter) {
-        b.filter = (uint32_t*)(ws + w.filter);
-        b.filter_bits = w.filter_bits;
-        rc = check_cuda(cudaMemsetAsync(b.filter, 0, (size_t)w.filter_bits / 8, st), "edge filter memset");
-        if (rc) return rc;
-    }
     if (want_table) {
         b.table = (uint32_t*)(ws + w.table);
         b.tile_row0 = (int64_t*)(ws + w.tile_row0);
@@ -716,7 +709,7 @@ int csr_prepare_device(IdxPtr row_ptr, IdxPtr col_idx, int64_t n_nodes, int64_t 
         if (rc) return rc;
         out->table = b.table;
         out->table_failed = b.failed;
-        if (want_filter) { out->filter.bits = b.filter; out->filter.n_bits = b.filter_bits; }
+        if (want_filter) { out->filter_space = (uint32_t*)(ws + w.filter); out->filter_space_bits = w.filter_bits; }
     }
     out->row32 = b.row32;
     if (want_records) {
@@ -741,16 +734,23 @@ int csr_add_blooms(CsrPrepared* pr, IdxPtr col_idx, int64_t n_nodes, int64_t nnz
     const unsigned grid = (unsigned)sm_count(device) * 8;
     uint4* records = const_cast<uint4*>(pr->records);
     const uint32_t cap32 = (uint32_t)std::min<int64_t>(cap, 1 << 20);
+    if (pr->filter_space) {
+        rc = check_cuda(cudaMemsetAsync(pr->filter_space, 0, (size_t)pr->filter_space_bits / 8, st), "hub-pair filter memset");
+        if (rc) return rc;
+    }
     if (col_idx.wide())
-        edge_bloom_kernel<true><<<grid, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, records, pr->table, pr->filter, cap32,
-                                                                  pr->table_failed, pr->bloom_flag);
+        edge_bloom_kernel<true><<<grid, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, records, pr->table, pr->filter_space,
+                                                                  pr->filter_space_bits, cap32, pr->table_failed, pr->bloom_flag);
     else
-        edge_bloom_kernel<false><<<grid, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, records, pr->table, pr->filter, cap32,
-                                                                   pr->table_failed, pr->bloom_flag);
+        edge_bloom_kernel<false><<<grid, kBloomWarps * 32, 0, st>>>(col_idx, nnz, pr->row32, n_nodes, records, pr->table, pr->filter_space,
+                                                                   pr->filter_space_bits, cap32, pr->table_failed, pr->bloom_flag);
     count_launch(1);
     rc = check_cuda(cudaGetLastError(), "edge bloom launch");
     if (rc) return rc;
     pr->asymmetric = pr->bloom_flag;
+    // (a pass that found the table overflowed returns at once and leaves the filter empty: the walk kernels do not consult
+    // it then, they scan -- walk_csr.cu)
+    if (pr->filter_space) pr->filter = EdgeFilter{pr->filter_space, pr->filter_space_bits, cap32};
     return TRW_OK;
 }
 

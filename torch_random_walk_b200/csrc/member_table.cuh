@@ -104,18 +104,20 @@ __device__ __forceinline__ bool is_member(int64_t x, int64_t b, int64_t e, IdxPt
     return false;
 }
 
-// ---------------------------------------------------------------- edge filter (L2-resident)
-// Most membership questions of a walk on a sparse graph are answered "no" (R-MAT: 96 %), and each
-// of them costs a random 128-byte line of HBM for the table sector.  The edge filter answers most of
-// the "no"s from L2: one bit per hashed unordered pair {row, id}, set for every CSR entry, in a
-// bitmap small enough to stay L2-resident (evict_last; default 64 MB, option edge_filter_mb).  A
-// clear bit proves that neither (row, id) nor (id, row) is stored, so "not a member" is exact; a set
-// bit says "maybe" and the caller asks the table as before.  Same answers, fewer lines: with n/2
-// distinct pairs of a symmetric graph in M bits a fraction exp(-n/2M) of the "no"s stops here
-// (c3: 0.62 at 64 MB).  Ids that do not fit 32 bits are never inserted and never asked.
+// ---------------------------------------------------------------- hub-pair filter (L2-resident)
+// The triangle Blooms (below) answer most membership questions of a walk for free, but a 32-bit word cannot describe the
+// common neighbourhood of two hubs: edges whose shorter row exceeds the Bloom cap keep a saturated word, and on an R-MAT
+// graph those are 40 % of the edges a walk crosses -- a fifth of the questions still reach the table (one random
+// 128-byte line of HBM each), nearly all of them to hear "no".  They all concern pairs of hubs, and the hub-hub edges are
+// few enough for a bitmap that stays in L2: one bit per hashed unordered pair {row, id}, set by the Bloom pass for every
+// stored entry whose two endpoints both have more than `min_deg` out-entries (evict_last; option edge_filter_mb).  For
+// such a pair a clear bit proves that neither (row, id) nor (id, row) is stored, so "not a member" is exact; a set bit
+// says "maybe" and the caller asks the table as before; any other pair is never asked.  Same answers, fewer lines.
+// Ids that do not fit 32 bits are never inserted and never asked.
 struct EdgeFilter {
     const uint32_t* bits = nullptr;
     uint32_t n_bits = 0;
+    uint32_t min_deg = 0;  // the filter knows every stored pair whose endpoints both have more out-entries than this
 };
 __host__ __device__ __forceinline__ uint32_t pair_slot(uint32_t a, uint32_t b, uint32_t n_bits) {
     const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
@@ -124,9 +126,9 @@ __host__ __device__ __forceinline__ uint32_t pair_slot(uint32_t a, uint32_t b, u
     z *= 0xD6E8FEB86659FD93ull;
     return mulhi32((uint32_t)(z >> 32), n_bits);
 }
-// false: `x` is certainly not stored in the row of node `row`; true: ask the table.
-__device__ __forceinline__ bool filter_maybe(const EdgeFilter& f, int64_t row, int64_t x, uint64_t pol_keep) {
-    if (f.bits == nullptr || ((uint64_t)row | (uint64_t)x) >= (uint64_t)kEmpty) return true;
+// false: `x` is certainly not stored in the row of node `row`; true: ask the table.  d_row, d_x: their out-degrees.
+__device__ __forceinline__ bool filter_maybe(const EdgeFilter& f, int64_t row, int64_t x, int64_t d_row, int64_t d_x, uint64_t pol_keep) {
+    if (f.bits == nullptr || d_row <= (int64_t)f.min_deg || d_x <= (int64_t)f.min_deg || ((uint64_t)row | (uint64_t)x) >= (uint64_t)kEmpty) return true;
     const uint32_t slot = pair_slot((uint32_t)row, (uint32_t)x, f.n_bits);
     return (ldg32_l2keep(f.bits + (slot >> 5), pol_keep) >> (slot & 31)) & 1u;
 }
@@ -203,7 +205,9 @@ struct CsrPrepared {
     const int* table_failed = nullptr;   // device flag: non-zero when a hub segment overflowed
     const unsigned long long* strict_counts = nullptr;  // [descents in col_idx, descents at row boundaries]
     const uint4* records = nullptr;      // edge records, or nullptr
-    EdgeFilter filter;                   // L2-resident edge filter (bits == nullptr: none)
+    EdgeFilter filter;                   // L2-resident hub-pair filter, filled by the Bloom pass (bits == nullptr: none, or not filled yet)
+    uint32_t* filter_space = nullptr;    // where it goes: workspace reserved by csr_prepare_device
+    uint32_t filter_space_bits = 0;
     const int* asymmetric = nullptr;     // device flag of the triangle-Bloom pass: non-zero when some (t -> v) has no (v -> t); nullptr: not checked
     int* bloom_flag = nullptr;           // where that flag lives once the pass has run (workspace cell)
 };

@@ -277,6 +277,8 @@ int trw_set_option(const char* name, int64_t value) {
     return TRW_ERR_ARG;
 }
 
+void trw_reset_options(void) { options() = Options{}; }
+
 int64_t trw_get_option(const char* name) {
     if (!name) return -1;
     Options& o = options();

@@ -18,7 +18,8 @@ struct Options {
     int64_t el_table = 1;         // 1: edge-list node2vec walks test membership through the hashed table (needs workspace); 0: the reference's scan
     int64_t records = -1;         // 16-byte edge records (neighbour id + its row span; the walk then needs no row-index loads): 1 always, 0 never,
                                   // -1 kept graphs always, one-shot calls when the walk is long enough to repay one pass over col_idx (csr_one_shot_needs)
-    int64_t edge_filter_mb = 0;   // L2-resident edge filter in front of the membership table (member_table.cuh): size cap in MB, 0 = none
+    int64_t edge_filter_mb = 32;  // L2-resident hub-pair filter in front of the membership table (member_table.cuh; filled by the triangle-Bloom pass
+                                  // for edges between rows longer than the Bloom cap): size cap in MB, 0 = none
                                   // (default: measured -8 % on the c3 walk alone, but nothing on top of the triangle Blooms, and 2.9 ms per build)
     int64_t edge_bloom_cap = 256; // kept graphs: triangle Blooms in the edge records (member_table.cuh) for pairs whose shorter row has at most
                                   // this many entries (the pass is quadratic in it); 0 = none

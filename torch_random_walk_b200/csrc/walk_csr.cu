@@ -87,12 +87,14 @@ __device__ __forceinline__ bool triangle_maybe(uint32_t carried, int64_t x, bool
     return (carried & bloom_bit(x)) != 0 && (!symmetric || (fresh & other_bit) != 0);
 }
 
-// "x in adj(row)?" where the usual answer is no: the L2-resident edge filter first (a clear bit is a
-// proof), the table sector only for a "maybe".  Identical answers with and without the filter.
+// "x in adj(row)?" once the triangle Blooms have said "maybe": for a pair of hubs the L2-resident hub-pair filter first (a
+// clear bit is a proof), the table sector only for another "maybe".  Identical answers with and without the filter.
+// d_x: out-degree of x (0 when not known -- only an edge record brings it along: the filter is then not asked).  A table that failed to build leaves the filter
+// unfilled, so without a table there is no filter either.
 template <bool TABLE>
-__device__ __forceinline__ bool is_member_filtered(const WalkArgs& a, int64_t x, int64_t row, int64_t b, int64_t e,
+__device__ __forceinline__ bool is_member_filtered(const WalkArgs& a, int64_t x, int64_t d_x, int64_t row, int64_t b, int64_t e,
                                                    const uint32_t* table, uint64_t pol_stream, uint64_t pol_keep) {
-    if (TABLE && e > b && !filter_maybe(a.filter, row, x, pol_keep)) return false;
+    if (TABLE && table != nullptr && e > b && !filter_maybe(a.filter, row, x, e - b, d_x, pol_keep)) return false;
     return is_member<TABLE>(x, b, e, a.col_idx, table, pol_stream);
 }
 
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
                 const bool ask = term_b ? (x != t && triangle_maybe(ctx, x, symmetric, xw, bloom_bit(from_t ? v : t))) : (term_c && !symmetric);
                 const bool in_v = from_t || term_c;
                 bool member = false;
-                if (ask) member = is_member_filtered<TABLE>(a, term_c ? t : x, in_v ? v : t, in_v ? vb : tb, in_v ? ve : te, table, pol_stream, pol_keep);
+                if (ask) member = is_member_filtered<TABLE>(a, term_c ? t : x, REC ? xe - xb : 0, in_v ? v : t, in_v ? vb : tb, in_v ? ve : te, table, pol_stream, pol_keep);
                 accept = stay || term_a || member || (term_c && symmetric);
                 if (accept) {
                     if (!REC && s < L) load_row<ROW32>(a, x, xb, xe, pol_keep);
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
                 const bool regular = !stay && !extra && x != t && u >= fthr_any && u < fthr_top;
                 const bool ask = extra ? !symmetric : (regular && triangle_maybe(ctx, x, symmetric, xw, bloom_bit(t)));
                 bool member = false;
-                if (ask) member = is_member_filtered<TABLE>(a, extra ? t : x, extra ? v : t, extra ? vb : tb, extra ? ve : te, table, pol_stream, pol_keep);
+                if (ask) member = is_member_filtered<TABLE>(a, extra ? t : x, REC ? xe - xb : 0, extra ? v : t, extra ? vb : tb, extra ? ve : te, table, pol_stream, pol_keep);
                 if (stay) accept = true;
                 else if (extra) accept = symmetric || member;
                 else if (x == t || u < fthr_any) accept = true;
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) node2vec_walk_kernel(const Wa
             else if (a.thr1 == a.thr2) accept = true;  // q == 1: membership cannot change the answer
             else {
                 const bool member = triangle_maybe(ctx, x, symmetric, xw, bloom_bit(t)) &&
-                                    is_member_filtered<TABLE>(a, x, t, tb, te, table, pol_stream, pol_keep);
+                                    is_member_filtered<TABLE>(a, x, REC ? xe - xb : 0, t, tb, te, table, pol_stream, pol_keep);
                 accept = u < (member ? a.thr1 : a.thr2);
             }
             if (accept) {
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(BLOCK) node2vec_warp_walk_kernel(const WalkArg
                     if (xj == t) w = a.w_back;
                     else if (a.w_common == a.w_far) w = a.w_far;
                     else w = (triangle_maybe(ctx, xj, symmetric, wj, bloom_bit(t)) &&
-                              is_member_filtered<true>(a, xj, t, tb, te, table, pol_stream, pol_keep)) ? a.w_common : a.w_far;
+                              is_member_filtered<true>(a, xj, 0, t, tb, te, table, pol_stream, pol_keep)) ? a.w_common : a.w_far;
                 }
                 double incl = w;
 #pragma unroll
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(BLOCK) node2vec_warp_walk_kernel(const WalkArg
                 else if (u >= thr_far) accept = false;
                 else if (a.thr1 == a.thr2) accept = true;
                 else accept = u < ((triangle_maybe(ctx, x, symmetric, xw, bloom_bit(t)) &&
-                                    is_member_filtered<true>(a, x, t, tb, te, table, pol_stream, pol_keep)) ? a.thr1 : a.thr2);
+                                    is_member_filtered<true>(a, x, 0, t, tb, te, table, pol_stream, pol_keep)) ? a.thr1 : a.thr2);
                 if (accept) break;
             }
         }

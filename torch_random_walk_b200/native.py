@@ -68,6 +68,7 @@ def _load():
     lib.trw_host_replica_info.argtypes = [_c_int, ctypes.POINTER(_c_i64), _c_int]
     lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
     lib.trw_csr_graph_destroy.restype = None
+    lib.trw_reset_options.restype = None
     lib.trw_csr_graph_info.argtypes = [_c_ptr, _c_ptr, ctypes.POINTER(_c_i64), _c_int]
     lib.trw_walk_csr.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
                                  _c_i64, _c_ptr, _c_i64, _c_ptr, _c_size, _c_int, _c_ptr]
@@ -136,6 +137,11 @@ def _ptr(t):
 
 def set_option(name, value):
     _check(_lib.trw_set_option(name.encode(), int(value)))
+
+
+def reset_options():
+    """Every option of the calling thread back to the shipped default (trw_reset_options)."""
+    _lib.trw_reset_options()
 
 
 def get_option(name):
