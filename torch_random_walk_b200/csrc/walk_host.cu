@@ -198,13 +198,17 @@ constexpr int kMinCompressThreads = 12;
 
 // Host threads available to this process for the wire compression: the machine's, shared among the ranks of
 // a torchrun launch on this node (LOCAL_WORLD_SIZE), or option host_threads.
+// Ranks of a torchrun launch that share this host (LOCAL_WORLD_SIZE), 1 otherwise.
+static int local_rank_count() {
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    const int ranks = lws ? atoi(lws) : 1;
+    return ranks > 1 ? ranks : 1;
+}
 static int host_thread_count() {
     if (options().host_threads > 0) return (int)options().host_threads;
     int n = (int)std::thread::hardware_concurrency();
     if (n <= 0) n = 1;
-    const char* lws = getenv("LOCAL_WORLD_SIZE");
-    const int ranks = lws ? atoi(lws) : 1;
-    if (ranks > 1) n /= ranks;
+    n /= local_rank_count();
     return n > 0 ? n : 1;
 }
 
@@ -678,6 +682,12 @@ static int download_mode(int n_threads, int64_t n_nodes, bool ids_fit, bool chec
     const int share = (int)options().host_packed_share;  // of 8 chunks, how many travel packed (-1: adaptive)
     if (share >= 0) return share > 8 ? 8 : share;
     if (want == 2) return n_threads >= 4 ? 4 : 0;
+    // The packed form trades PCIe bytes for host memory traffic (16 bytes per entry through the host's memory system against
+    // 8).  That pays while a rank's own PCIe link is what limits it: one or two ranks on a host (c3: 111 -> 85-105 ms at one
+    // rank, 84.8 -> 69.3 ms at two).  With four or eight ranks the host's aggregate device->host ceiling and its memory
+    // bandwidth are the limit, every rank's team hammers the same DIMMs, and plain copies win (four ranks: 45 ms plain, 83 ms
+    // adaptive; eight: 62 vs 65 ms) -- and no rank can see that from its own backlog.
+    if (local_rank_count() > 2) return 0;
     return n_threads >= 2 ? -1 : 0;
 }
 
