@@ -146,6 +146,17 @@ def test_options_belong_to_the_calling_thread():
     assert lib.trw_set_option(b"no_such_option", ctypes.c_int64(1)) != 0
 
 
+def test_reset_options_restores_the_shipped_defaults():
+    from torch_random_walk_b200 import native
+
+    before = {k: native.get_option(k) for k in ("edge_bloom_cap", "edge_filter_mb", "host_chunk_walks", "records", "win_direct_pos")}
+    for k in before:
+        native.set_option(k, 5)
+    native.reset_options()
+    assert {k: native.get_option(k) for k in before} == before
+    assert before["edge_bloom_cap"] == 256 and before["edge_filter_mb"] == 32 and before["records"] == -1
+
+
 def test_host_checksum_forms_agree():
     """trw_csr_checksum_host (what the host path compares with its kept device replica): the AVX-512 loop, the scalar
     loop and a numpy restatement of the definition give one value, for every length around the vector width and any
