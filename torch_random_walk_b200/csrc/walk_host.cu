@@ -7,10 +7,11 @@
 //   * the start nodes are walked in chunks on one stream and each finished chunk is copied back on a
 //     second stream while the next chunk is being walked (PCIe is full duplex, the copy engines run
 //     beside the SMs);
-//   * node ids fit 32 bits for every graph the fast paths take and the host can narrow/widen at
-//     ~100 GB/s with its cores, so with enough threads col_idx goes up and the walks come back as
-//     uint32, converted chunk by chunk while the neighbouring chunk is in flight; any id that does
-//     not fit falls back to plain copies;
+//   * node ids fit 32 bits for every graph the fast paths take and the host can narrow/widen with its
+//     cores (14 G entries/s on 16 threads), so with enough threads col_idx goes up as uint32, and the
+//     walks come back as uint32 for as many chunks as the host team keeps up with (HostTeam below; only
+//     while the rank's own PCIe link is the limit: download_mode), converted while the neighbouring
+//     chunks are in flight; any id that does not fit falls back to plain copies;
 //   * the graph does not cross PCIe again when the caller comes back with the same arrays: the device
 //     replica and its preparation are kept per device, keyed by the host pointers and sizes and
 //     VALIDATED BY CONTENT on every call -- row_ptr and col_idx are summed again (the same 64-bit
@@ -192,8 +193,9 @@ static void widen_to_i64(const uint32_t* src, int64_t* dst, int64_t n) {
     widen_scalar(src, dst, n);
 }
 
-// Measured on the GPU box (16 cores): 16 threads per rank turn 190 ms into 144 ms per C3 call; two ranks with 8
-// threads each share the host's memory bandwidth and come out 3 % behind the plain copies.
+// Threads a rank needs before the UPLOAD of a fresh graph narrows col_idx on the host (round 1, 16 cores: 16 threads per
+// rank turn 190 ms into 144 ms per C3 call; with 8 the narrowing does not keep up with the upload).  The download format
+// is decided separately (download_mode).
 constexpr int kMinCompressThreads = 12;
 
 // Host threads available to this process for the wire compression: the machine's, shared among the ranks of
