@@ -469,15 +469,20 @@ __global__ void __launch_bounds__(256) edge_records_kernel(IdxPtr col_any, int64
 // Triangle Blooms of a kept graph (member_table.cuh): word .w of record (t -> v) becomes the 32-bit Bloom
 // of adj(t) & adj(v).  The set is the same from either end, so each unordered pair is worked out once, by
 // the entry that sits in the LONGER row (ties: the larger id): it walks the shorter row adj(v), asks row
-// t's table about every w (edge filter first) and, on the way, meets t itself -- at the position of the
+// t's table about every w and, on the way, meets t itself -- at the position of the
 // mirror entry (v -> t), which receives the same word.  A warp owns 32 consecutive CSR entries; the
 // (entry, neighbour) pairs of the tile are flattened over the lanes, two per lane and round, so short
 // rows do not idle the warp and two gathers are in flight per lane.  Pairs whose shorter row exceeds
 // `cap` keep the saturated word: their Bloom would be full anyway and the work is quadratic in hub size.
 // The same pass proves or refutes that the graph is symmetric (every (t -> v) has its (v -> t)), which
 // the walk needs before it may look at a triangle from its far side.
+//
+// Which row an entry belongs to is a search of the row index (24 dependent L2 reads on c3).  A warp therefore takes runs
+// of kBloomRun consecutive tiles: the first tile of a run bisects, the others gallop forward from the row where the
+// previous tile ended (a read or two).
 constexpr int kBloomWarps = 8;
 constexpr int kBloomUnroll = 2;
+constexpr int kBloomRun = 8;
 template <bool WIDE>
 __global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col_any, int64_t nnz,
                                                                       const uint32_t* __restrict__ row32, int64_t n_nodes,
@@ -497,13 +502,22 @@ __global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col
         if (threadIdx.x == 0) *asymmetric = 1;
         return;
     }
-    for (int64_t tile = (int64_t)blockIdx.x * kBloomWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kBloomWarps) {
+    const int64_t n_runs = (n_tiles + kBloomRun - 1) / kBloomRun;
+    for (int64_t run = (int64_t)blockIdx.x * kBloomWarps + warp; run < n_runs; run += (int64_t)gridDim.x * kBloomWarps) {
+      int64_t row_from = -1;  // a row at or before the rows of the next tile (-1: not known yet)
+      for (int64_t tile = run * kBloomRun; tile < min((run + 1) * kBloomRun, n_tiles); ++tile) {
         const int64_t k = tile * 32 + lane;
         const bool valid = k < nnz;
-        // this lane's entry: row t (bisection of the L2-resident row index), neighbour v with its span from the record
+        // this lane's entry: row t (a search of the L2-resident row index), neighbour v with its span from the record
         uint32_t t = 0, tb = 0, dt = 0, v = 0, vb = 0, dv = 0;
         if (valid) {
             int64_t lo = 0, hi = n_nodes;  // row32[lo] <= k < row32[hi]
+            if (row_from >= 0) {  // gallop forward from where the previous tile ended
+                lo = row_from;
+                int64_t step = 1;
+                while (lo + step < n_nodes && (int64_t)ldg32_keep(row32 + lo + step, pol_keep) <= k) { lo += step; step <<= 1; }
+                hi = min(lo + step, n_nodes);
+            }
             while (hi - lo > 1) {
                 const int64_t mid = (lo + hi) >> 1;
                 if ((int64_t)ldg32_keep(row32 + mid, pol_keep) <= k) lo = mid; else hi = mid;
@@ -578,7 +592,9 @@ __global__ void __launch_bounds__(kBloomWarps * 32) edge_bloom_kernel(IdxPtr col
             if (mirror != kNoMirror) reinterpret_cast<uint32_t*>(records + mirror)[3] = word;
             else *asymmetric = 1;
         }
+        row_from = (int64_t)__shfl_sync(0xFFFFFFFFu, t, 31);  // (the last tile's lanes past nnz hold 0, and no tile follows it)
         __syncwarp();
+      }
     }
 }
 
