@@ -287,6 +287,21 @@ int trw_windows(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int wi
                 int64_t num_nodes, int64_t seed,
                 int64_t* target, int64_t* pos, int64_t* neg, int device, void* stream);
 
+/* Negatives of the node windows from a caller-supplied distribution instead of the uniform one (SURVEY.md section 8 f3,
+ * optional; no counterpart in the reference, whose negatives are rand() % num_nodes, csrc/cuda/windows_cuda.cu:57-62):
+ * trw_alias_table_build (HOST code, O(n)) turns weights[n] >= 0 into an alias table for P(v) ~ weights[v]^power --
+ * word2vec's unigram^0.75 with weights = degrees, power = 0.75 -- one 8-byte cell per node, threshold | alias << 32;
+ * copy it to the device and pass it to trw_windows_alias / trw_windows_cbow_alias, which are trw_windows /
+ * trw_windows_cbow with every negative drawn from it (n == num_nodes < 2^32; the CBOW form still redraws a negative
+ * equal to its positive node, up to 101 times).  Targets and positives are unchanged. */
+int trw_alias_table_build(const double* weights, int64_t n, double power, uint64_t* table_out);
+int trw_windows_alias(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                      int64_t num_nodes, int64_t seed, const uint64_t* alias_table,
+                      int64_t* target, int64_t* pos, int64_t* neg, int device, void* stream);
+int trw_windows_cbow_alias(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
+                           int64_t num_nodes, int64_t seed, const uint64_t* alias_table,
+                           int64_t* pos_nodes, int64_t* neg_nodes, int64_t* windows, int device, void* stream);
+
 int trw_windows_cbow(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
                      int64_t num_nodes, int64_t seed,
                      int64_t* pos_nodes, int64_t* neg_nodes, int64_t* windows,

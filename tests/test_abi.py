@@ -194,3 +194,36 @@ def test_host_checksum_forms_agree():
     a = native.csr_checksum_host(rp, ci)
     ci[50], ci[51] = ci[51].item(), ci[50].item()  # position-sensitive: a swap is seen
     assert native.csr_checksum_host(rp, ci) != a
+
+
+def test_alias_table_reproduces_the_weights():
+    """trw_alias_table_build (host code): the table's cells must add up to P(v) ~ weights[v]**power -- a node's mass is
+    what its own cell keeps plus what the cells aliased to it give away -- for skewed, flat, sparse and single-node inputs."""
+    import numpy as np
+
+    from torch_random_walk_b200 import native
+
+    lib = native.lib()
+    rng = np.random.default_rng(3)
+    cases = [(rng.pareto(1.2, 5000) + 1.0, 0.75), (np.ones(17), 0.75), (np.r_[np.zeros(50), rng.integers(1, 9, 200)].astype(float), 0.75),
+             (np.array([7.0]), 0.75), (rng.integers(0, 1000, 4096).astype(float), 1.0), (np.r_[1e6, np.ones(999)], 0.5)]
+    for weights, power in cases:
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        table = np.zeros(w.size, dtype=np.uint64)
+        rc = lib.trw_alias_table_build(w.ctypes.data_as(ctypes.c_void_p), w.size, float(power), table.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0, native.lib().trw_last_error()
+        keep = (table & np.uint64(0xFFFFFFFF)).astype(np.float64) / 2.0**32
+        alias = (table >> np.uint64(32)).astype(np.int64)
+        assert alias.min() >= 0 and alias.max() < w.size
+        mass = keep.copy()
+        np.add.at(mass, alias, 1.0 - keep)
+        want = np.where(w > 0, w**power, 0.0)
+        want = want / want.sum() * w.size
+        assert np.allclose(mass, want, rtol=0, atol=1e-6 * max(1.0, want.max())), (w.size, power, np.abs(mass - want).max())
+        assert (keep[w == 0] < 1e-9).all()  # a node of weight 0 is never drawn: its own cell keeps nothing, nothing is aliased to it
+        assert not np.isin(alias[keep < 1.0 - 1e-9], np.nonzero(w == 0)[0]).any()
+    bad = np.array([1.0, -1.0])
+    out = np.zeros(2, dtype=np.uint64)
+    assert lib.trw_alias_table_build(bad.ctypes.data_as(ctypes.c_void_p), 2, 0.75, out.ctypes.data_as(ctypes.c_void_p)) != 0
+    zero = np.zeros(4)
+    assert lib.trw_alias_table_build(zero.ctypes.data_as(ctypes.c_void_p), 4, 0.75, out.ctypes.data_as(ctypes.c_void_p)) != 0

@@ -275,3 +275,58 @@ def test_non_contiguous_walks_raise_like_reference(rw):
     empty = torch.empty((0, 11), dtype=torch.int64, device="cuda")
     t, p, n = rw.to_windows(empty, 5, 10, 1)
     assert t.shape == (0,) and p.shape == (0, 4) and n.shape == (0, 4)
+
+
+def test_negatives_from_an_alias_table_follow_the_weights(rw):
+    """Extension: with neg_table= the negatives of to_windows / to_windows_cbow are drawn with
+    P(v) ~ degree[v]**0.75 instead of uniformly.  Targets and positives are untouched, the draws follow the distribution
+    (chi-square), nodes of weight 0 never appear, the CBOW form still avoids its positive node, and the 16-byte pair path
+    writes what the per-element path writes."""
+    import ctypes
+
+    from scipy import stats
+
+    from torch_random_walk_b200 import native
+
+    nodes, n, wl, W = 600, 3000, 41, 5
+    g = torch.Generator().manual_seed(11)
+    degree = torch.randint(1, 400, (nodes,), generator=g).double()
+    degree[::7] = 0.0
+    table = native.negative_table(degree, power=0.75, device="cuda")
+    walks = torch.randint(0, nodes, (n, wl), generator=g).cuda()
+    plain = rw.to_windows(walks, W, nodes, 4)
+    tgt, pos, neg = native.to_windows(walks, W, nodes, 4, neg_table=table)
+    assert torch.equal(tgt, plain[0]) and torch.equal(pos, plain[1]) and neg.shape == plain[2].shape
+    assert torch.equal(neg, native.to_windows(walks, W, nodes, 4, neg_table=table)[2])            # deterministic
+    assert not torch.equal(neg, native.to_windows(walks, W, nodes, 5, neg_table=table)[2])        # seeded
+    want = degree.numpy() ** 0.75
+    want[degree.numpy() == 0] = 0.0
+    want = want / want.sum()
+
+    def follows(sample, from_table=True):
+        counts = np.bincount(sample.cpu().numpy().ravel(), minlength=nodes).astype(np.float64)
+        if from_table:
+            assert counts[want == 0].sum() == 0  # a node of weight 0 is never drawn
+        keep = want > 0
+        return stats.chisquare(counts[keep], want[keep] * counts[keep].sum()).pvalue
+
+    assert follows(neg) > 1e-3
+    assert follows(plain[2], from_table=False) < 1e-6  # (the uniform negatives do not: the test can tell the two apart)
+    pos_nodes, neg_nodes, windows = native.to_windows_cbow(walks, W, nodes, 4, neg_table=table)
+    plain_cbow = rw.to_windows_cbow(walks, W, nodes, 4)
+    assert torch.equal(pos_nodes, plain_cbow[0]) and torch.equal(windows, plain_cbow[2])
+    assert not bool((neg_nodes == pos_nodes).any())
+    assert follows(neg_nodes) > 1e-4  # (conditioned on != the positive node: a small, second-order distortion)
+    # element path (output shifted by one element) == pair path
+    lib = native.lib()
+    k = n * (wl - W + 1)
+    bufs = [torch.empty(k * (W - 1) + 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    out_t = torch.empty(k, dtype=torch.int64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.trw_windows_alias(ctypes.c_void_p(walks.data_ptr()), n, wl, W, nodes, 4, ctypes.c_void_p(table.data_ptr()),
+                               ctypes.c_void_p(out_t.data_ptr()), ctypes.c_void_p(bufs[0].data_ptr() + 8),
+                               ctypes.c_void_p(bufs[1].data_ptr() + 8), 0, st)
+    assert rc == 0, lib.trw_last_error()
+    assert torch.equal(bufs[1][1:1 + k * (W - 1)].view(k, W - 1), neg)
+    with pytest.raises(RuntimeError):
+        native.to_windows(walks, W, nodes + 1, 4, neg_table=table)

@@ -78,6 +78,9 @@ def main():
         rw.to_windows(walks, W, n, 1)
         rw.to_windows_cbow(walks, W, n, 1)
     rw.to_windows(walks[:3].contiguous(), 5, n, 1)
+    table = native.negative_table((rp[1:] - rp[:-1]).double(), device="cuda")    # weighted negatives (alias table)
+    native.to_windows(walks, 5, n, 1, neg_table=table)
+    native.to_windows_cbow(walks, 6, n, 1, neg_table=table)
     triples = rmat.kg_triples(200, 7, 3000, device="cuda")
     index, ts = rmat.relation_tail_index(triples, 200)
     tw = rw.walk_triples(ts, index, torch.arange(200, device="cuda").repeat(3), walk_length=13, padding_idx=207, seed=1)

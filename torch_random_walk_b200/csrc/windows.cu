@@ -14,6 +14,8 @@
 // with the reference; negatives are Philox draws indexed by the output element (one block per
 // aligned quad of draws), so they do not depend on the launch shape or on which path wrote them.
 #include <algorithm>
+#include <cmath>
+#include <vector>
 
 #include "trw_common.cuh"
 #include "trw_options.h"
@@ -47,6 +49,7 @@ struct WinArgs {
     int64_t n_triples;
     const uint4* triples16;   // optional 16-byte copy of `triples` (x, y, z = head, relation, tail as uint32), see compact_triples_kernel
     const int* triples16_bad; // device flag: some value did not fit, the copy must not be used
+    const uint2* alias;       // optional alias table over [0, num_nodes) for the node windows' negatives ({threshold, alias} per node; see alias_draw)
     uint2 key;
     int64_t* out[3];       // outputs in the API's order
     uint32_t epw[3];       // elements of out[k] per walk
@@ -58,6 +61,15 @@ struct WinArgs {
 __device__ __forceinline__ uint2 draw64(const uint2 key, uint64_t g, uint32_t stream, uint32_t draw) {
     uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), stream, draw >> 1), key);
     return (draw & 1u) ? make_uint2(r.z, r.w) : make_uint2(r.x, r.y);
+}
+
+// One draw from an alias table (Walker/Vose): a uniform cell i, then i itself with probability threshold_i / 2^32, else the
+// cell's alias.  Two random words per draw, one 8-byte gather.  (negatives from a non-uniform
+// distribution such as word2vec's degree^0.75; the reference draws uniformly, windows_cuda.cu:57-62.)
+__device__ __forceinline__ int64_t alias_draw(const uint2* __restrict__ alias, uint32_t n, uint32_t r_cell, uint32_t r_keep) {
+    const uint32_t i = __umulhi(r_cell, n);
+    const uint2 c = __ldg(alias + i);
+    return (int64_t)(r_keep < c.x ? i : c.y);
 }
 
 template <int MODE>
@@ -78,6 +90,10 @@ __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_
         }
         (void)neg_out;
         if (MODE == kSkipGram) {  // neg_windows: uniform node id (windows_cuda.cu:57-62)
+            if (a.alias != nullptr) {  // ... or a draw from the caller's distribution: two draws per Philox block, shared by the aligned pair
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(g >> 1), (uint32_t)(g >> 33), 5u, 0x414C4941u), a.key);
+                return (g & 1) ? alias_draw(a.alias, (uint32_t)a.num_nodes, r.z, r.w) : alias_draw(a.alias, (uint32_t)a.num_nodes, r.x, r.y);
+            }
             if ((uint64_t)a.num_nodes <= 0xFFFFFFFFull) {  // four draws per Philox block, shared by the aligned quad
                 const uint4 r = philox4x32_10(make_uint4((uint32_t)(g >> 2), (uint32_t)(g >> 34), 1u, 0x51554144u), a.key);
                 const uint32_t w = (g & 2) ? ((g & 1) ? r.w : r.z) : ((g & 1) ? r.y : r.x);
@@ -92,8 +108,8 @@ __device__ __forceinline__ int64_t window_element(const WinArgs& a, const int64_
         const int64_t pos = tile[(size_t)i * a.wl + s + a.mid];
         int64_t neg = 0;
         for (uint32_t attempt = 0; attempt <= 101u; ++attempt) {
-            uint2 r = draw64(a.key, g, 2u, attempt);
-            neg = bounded(r.x, r.y, a.num_nodes);
+            uint2 r = draw64(a.key, g, a.alias != nullptr ? 6u : 2u, attempt);
+            neg = a.alias != nullptr ? alias_draw(a.alias, (uint32_t)a.num_nodes, r.x, r.y) : bounded(r.x, r.y, a.num_nodes);
             if (neg != pos) break;
         }
         return neg;
@@ -372,7 +388,20 @@ __global__ void __launch_bounds__(BLOCK) windows_kernel(const WinArgs a) {
         // divisions per 8-byte element and, for the negatives, one Philox block per element although a
         // block yields the four draws of an aligned quad -- that redundancy alone kept the kernel
         // issue-bound at 4.0 TB/s.
-        if (MODE == kSkipGram && which == 2 && (uint64_t)a.num_nodes <= 0xFFFFFFFFull && (gbase & 3u) == 0 &&
+        if (MODE == kSkipGram && which == 2 && a.alias != nullptr && (gbase & 1u) == 0 && (((uintptr_t)dst) & 15) == 0) {
+            const uint32_t np = n >> 1, nn = (uint32_t)a.num_nodes;  // a pair of negatives per thread: one Philox block, two gathers, one 16-byte store
+            for (uint32_t q = threadIdx.x; q < np; q += BLOCK) {
+                const uint64_t gp = (gbase >> 1) + q;  // same block and word order as window_element()
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)gp, (uint32_t)(gp >> 32), 5u, 0x414C4941u), a.key);
+                longlong2 v;
+                v.x = alias_draw(a.alias, nn, r.x, r.y);
+                v.y = alias_draw(a.alias, nn, r.z, r.w);
+                reinterpret_cast<longlong2*>(dst)[q] = v;
+            }
+            if ((n & 1u) && threadIdx.x == 0) dst[n - 1] = window_element<MODE>(a, tile, which, n - 1, gbase + n - 1);
+            continue;
+        }
+        if (MODE == kSkipGram && which == 2 && a.alias == nullptr && (uint64_t)a.num_nodes <= 0xFFFFFFFFull && (gbase & 3u) == 0 &&
             (((uintptr_t)dst) & 31) == 0) {
             const uint32_t nq = n >> 2, nn = (uint32_t)a.num_nodes;
             for (uint32_t q = threadIdx.x; q < nq; q += BLOCK) {
@@ -429,7 +458,7 @@ template <int MODE>
 static int launch_windows(const char* name, const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size,
                           int64_t num_nodes, int64_t pad, const int64_t* triples, int64_t n_triples, int64_t seed,
                           int64_t* o0, int64_t* o1, int64_t* o2, int device, void* stream, void* workspace = nullptr,
-                          size_t workspace_bytes = 0) {
+                          size_t workspace_bytes = 0, const uint64_t* alias_table = nullptr) {
     constexpr bool kTripleMode = (MODE == kTriples || MODE == kTriplesCbow);
     if (n_walks < 0 || walk_cols < 0 || window_size < 0) { set_error("%s: negative size", name); return TRW_ERR_ARG; }
     if (walk_cols > (1 << 24) || window_size > (1 << 15)) {
@@ -467,6 +496,11 @@ static int launch_windows(const char* name, const int64_t* walks, int64_t n_walk
     a.walks = walks; a.n_walks = n_walks; a.wl = (int)walk_cols; a.W = W; a.mid = W / 2; a.per_walk = (int)per_walk;
     a.num_nodes = num_nodes; a.pad = pad; a.triples = triples; a.n_triples = n_triples;
     a.triples16 = nullptr; a.triples16_bad = nullptr;
+    a.alias = reinterpret_cast<const uint2*>(alias_table);
+    if (alias_table != nullptr && (kTripleMode || (uint64_t)num_nodes > 0xFFFFFFFFull || ((uintptr_t)alias_table & 7))) {
+        set_error("%s: an alias table needs node windows, num_nodes < 2^32 and 8-byte alignment", name);
+        return TRW_ERR_ARG;
+    }
     if (kTripleMode && workspace != nullptr && options().win_table16 != 0) {
         if (workspace_bytes < triples_workspace_bytes(n_triples) || ((uintptr_t)workspace & 255)) {
             set_error("%s: workspace needs %zu bytes at 256-byte alignment", name, triples_workspace_bytes(n_triples));
@@ -573,4 +607,58 @@ extern "C" int trw_windows_triples_cbow(const int64_t* walks, int64_t n_walks, i
     return launch_windows<kTriplesCbow>("trw_windows_triples_cbow", walks, n_walks, walk_cols, window_size, num_nodes,
                                         padding_idx, triples, n_triples, seed, pos_triples, neg_triples, pos_windows, device,
                                         stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Negatives from a caller-supplied distribution (optional): an alias table over the node ids.
+// trw_alias_table_build runs on the HOST (Vose's O(n) construction): cell i = {threshold_i, alias_i} packed as
+// threshold | alias << 32, P(v) proportional to weights[v]^power (weights >= 0, not all zero).
+extern "C" int trw_alias_table_build(const double* weights, int64_t n, double power, uint64_t* table_out) {
+    if (!weights || !table_out || n <= 0 || (uint64_t)n > 0xFFFFFFFFull) { set_error("trw_alias_table_build: bad argument"); return TRW_ERR_ARG; }
+    std::vector<double> p((size_t)n);
+    double total = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double w = weights[i];
+        if (!(w >= 0.0)) { set_error("trw_alias_table_build: weights must be >= 0"); return TRW_ERR_ARG; }
+        p[(size_t)i] = w > 0.0 ? pow(w, power) : 0.0;
+        total += p[(size_t)i];
+    }
+    if (!(total > 0.0)) { set_error("trw_alias_table_build: all weights are zero"); return TRW_ERR_ARG; }
+    const double scale = (double)n / total;  // cell mass 1 = the average
+    std::vector<uint32_t> small, large;
+    small.reserve((size_t)n);
+    large.reserve((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        p[(size_t)i] *= scale;
+        (p[(size_t)i] < 1.0 ? small : large).push_back((uint32_t)i);
+    }
+    auto cell = [](double keep, uint32_t alias) {
+        const double t = keep * 4294967296.0;
+        const uint64_t thr = t >= 4294967295.0 ? 0xFFFFFFFFull : (t <= 0.0 ? 0ull : (uint64_t)t);
+        return thr | ((uint64_t)alias << 32);
+    };
+    while (!small.empty() && !large.empty()) {
+        const uint32_t s_ = small.back(), l_ = large.back();
+        small.pop_back();
+        table_out[s_] = cell(p[s_], l_);
+        p[l_] -= 1.0 - p[s_];
+        if (p[l_] < 1.0) { large.pop_back(); small.push_back(l_); }
+    }
+    for (uint32_t i : large) table_out[i] = cell(1.0, i);
+    for (uint32_t i : small) table_out[i] = cell(1.0, i);  // rounding leftovers: mass 1 up to floating-point error
+    return TRW_OK;
+}
+
+extern "C" int trw_windows_alias(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size, int64_t num_nodes,
+                                 int64_t seed, const uint64_t* alias_table, int64_t* target, int64_t* pos, int64_t* neg, int device,
+                                 void* stream) {
+    return launch_windows<kSkipGram>("trw_windows_alias", walks, n_walks, walk_cols, window_size, num_nodes, 0, nullptr, 0, seed,
+                                     target, pos, neg, device, stream, nullptr, 0, alias_table);
+}
+
+extern "C" int trw_windows_cbow_alias(const int64_t* walks, int64_t n_walks, int64_t walk_cols, int window_size, int64_t num_nodes,
+                                      int64_t seed, const uint64_t* alias_table, int64_t* pos_nodes, int64_t* neg_nodes, int64_t* windows,
+                                      int device, void* stream) {
+    return launch_windows<kCbow>("trw_windows_cbow_alias", walks, n_walks, walk_cols, window_size, num_nodes, 0, nullptr, 0, seed,
+                                 pos_nodes, neg_nodes, windows, device, stream, nullptr, 0, alias_table);
 }

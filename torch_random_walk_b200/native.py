@@ -68,6 +68,9 @@ def _load():
     lib.trw_host_replica_info.argtypes = [_c_int, ctypes.POINTER(_c_i64), _c_int]
     lib.trw_csr_graph_destroy.argtypes = [_c_ptr]
     lib.trw_csr_graph_destroy.restype = None
+    lib.trw_alias_table_build.argtypes = [_c_ptr, _c_i64, _c_dbl, _c_ptr]
+    lib.trw_windows_alias.argtypes = [_c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
+    lib.trw_windows_cbow_alias.argtypes = [_c_ptr, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
     lib.trw_reset_options.restype = None
     lib.trw_csr_graph_info.argtypes = [_c_ptr, _c_ptr, ctypes.POINTER(_c_i64), _c_int]
     lib.trw_walk_csr.argtypes = [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_int,
@@ -498,30 +501,50 @@ def _require_walks(walks):
         raise RuntimeError("walks must be a contigous tensor")
 
 
-def _node_windows(fn, walks, window_size, num_nodes, seed, cbow):
+def _node_windows(fn, walks, window_size, num_nodes, seed, cbow, neg_table=None):
     _require_walks(walks)
     dev = walks.device
     n, wl = walks.shape
     w = int(window_size)
     k = (wl - w + 1) * n
+    if neg_table is not None:
+        if not (isinstance(neg_table, torch.Tensor) and neg_table.is_cuda and neg_table.device == dev and neg_table.dtype == torch.int64 and
+                neg_table.dim() == 1 and neg_table.is_contiguous() and neg_table.numel() == int(num_nodes)):
+            raise RuntimeError("neg_table must be the tensor native.negative_table made for num_nodes nodes, on the walks' device")
+        fn = _lib.trw_windows_cbow_alias if cbow else _lib.trw_windows_alias
     with torch.cuda.device(dev):
         first = torch.empty((k,), dtype=torch.int64, device=dev)
         win_a = torch.empty((k, w - 1), dtype=torch.int64, device=dev)
         other = torch.empty((k,) if cbow else (k, w - 1), dtype=torch.int64, device=dev)
         outs = (first, other, win_a) if cbow else (first, win_a, other)
-        _check(fn(_ptr(walks), n, wl, w, int(num_nodes), int(seed), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
+        table = () if neg_table is None else (_ptr(neg_table),)
+        _check(fn(_ptr(walks), n, wl, w, int(num_nodes), int(seed), *table, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
                   dev.index, _stream(dev)))
     return outs
 
 
-def to_windows(walks, window_size, num_nodes, seed):
-    """csrc/rw_init.cpp:77-88 -> (target_nodes[K], pos_windows[K,W-1], neg_windows[K,W-1])."""
-    return _node_windows(_lib.trw_windows, walks, window_size, num_nodes, seed, cbow=False)
+def negative_table(weights, power=0.75, device=None):
+    """Alias table for drawing window negatives with P(v) ~ weights[v]**power instead of uniformly (trw_alias_table_build; SURVEY
+    section 8 f3 -- word2vec's unigram^0.75 with weights = node degrees).  Built on the host in O(n); returns an int64 tensor of
+    num_nodes cells on `device` (default: the current CUDA device) for the `neg_table=` argument of to_windows / to_windows_cbow.
+    An extension: the reference's negatives are uniform, and so are ours without it."""
+    w = torch.as_tensor(weights).detach().to("cpu", torch.float64).contiguous()
+    if w.dim() != 1 or w.numel() == 0:
+        raise RuntimeError("weights must be a non-empty 1-D tensor (one weight per node)")
+    table = torch.empty(w.numel(), dtype=torch.int64)
+    _check(_lib.trw_alias_table_build(_ptr(w), w.numel(), float(power), _ptr(table)))
+    return table.to(torch.device("cuda", torch.cuda.current_device()) if device is None else device)
 
 
-def to_windows_cbow(walks, window_size, num_nodes, seed):
-    """csrc/rw_init.cpp:90-101 -> (pos_nodes[K], neg_nodes[K], windows[K,W-1])."""
-    return _node_windows(_lib.trw_windows_cbow, walks, window_size, num_nodes, seed, cbow=True)
+def to_windows(walks, window_size, num_nodes, seed, neg_table=None):
+    """csrc/rw_init.cpp:77-88 -> (target_nodes[K], pos_windows[K,W-1], neg_windows[K,W-1]).  neg_table (extension): see
+    negative_table."""
+    return _node_windows(_lib.trw_windows, walks, window_size, num_nodes, seed, cbow=False, neg_table=neg_table)
+
+
+def to_windows_cbow(walks, window_size, num_nodes, seed, neg_table=None):
+    """csrc/rw_init.cpp:90-101 -> (pos_nodes[K], neg_nodes[K], windows[K,W-1]).  neg_table (extension): see negative_table."""
+    return _node_windows(_lib.trw_windows_cbow, walks, window_size, num_nodes, seed, cbow=True, neg_table=neg_table)
 
 
 def _triple_windows(fn, walks, window_size, num_nodes, padding_idx, triples, seed, cbow):
